@@ -1,0 +1,448 @@
+// Device-side LDU -> row-major COO/CSR assembly.
+//
+// Replaces, bit for bit on the integer structures:
+//   init_local_sparsity            HostMatrix/HostMatrixFreeFunctions.C:105-201
+//   cyclic interface merge          HostMatrix/HostMatrix.C:504-586
+//   init_non_local_sparsity_pattern HostMatrix/HostMatrix.C:438-466
+//   update_local_matrix_data        HostMatrix/HostMatrix.C:592-705
+//   update_non_local_matrix_data    HostMatrix/HostMatrix.C:708-732
+//
+// The reference sorts two arrays of (row, col, face) tuples with std::sort on
+// the host and merges them row by row.  Here the same ordering is produced by a
+// counting sort on the row (histogram -> scan -> scatter) followed by an
+// in-row sort on (col, staging slot): inside a row the lower entries have
+// col < row, the diagonal col == row, the upper entries col > row, and a cyclic
+// interface entry that collides with an existing (row, col) has the larger
+// staging slot, so it lands behind it exactly like HostMatrix.C:543-575.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace ogl {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t work, int threads = kThreads)
+{
+    int64_t g = (work + threads - 1) / threads;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+// row histogram; counts start at 1 (the diagonal).  Also validates the
+// addressing: 0 <= lower < upper < n (OpenFOAM owner < neighbour).
+__global__ void k_count_rows(label n, label nf, const label *__restrict__ lower,
+                             const label *__restrict__ upper, label n_if,
+                             const label *__restrict__ if_rows,
+                             const label *__restrict__ if_cols, label *counts,
+                             int *bad)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nf) {
+        const label l = lower[i], u = upper[i];
+        if (l < 0 || u >= n || l >= u) {
+            atomicExch(bad, 1);
+            return;
+        }
+        atomicAdd(&counts[l], 1);
+        atomicAdd(&counts[u], 1);
+    } else if (i < (int64_t)nf + n_if) {
+        const label k = (label)(i - nf);
+        const label r = if_rows[k], c = if_cols[k];
+        if (r < 0 || r >= n || c < 0 || c >= n) {
+            atomicExch(bad, 2);
+            return;
+        }
+        atomicAdd(&counts[r], 1);
+    }
+}
+
+__global__ void k_fill_ones(label n, label *a)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = 1;
+}
+
+// scatter every entry into its row segment (order inside the row is fixed by
+// k_sort_rows afterwards, so the atomics do not leak nondeterminism)
+__global__ void k_scatter(label n, label nf, int symmetric,
+                          const label *__restrict__ lower,
+                          const label *__restrict__ upper, label n_if,
+                          const label *__restrict__ if_rows,
+                          const label *__restrict__ if_cols,
+                          const label *__restrict__ row_ptrs, label *cursor,
+                          label *cols, label *map)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const label diag_base = symmetric ? nf : 2 * nf;
+    if (i < nf) {
+        const label f = (label)i;
+        const label l = lower[f], u = upper[f];
+        // upper-triangle entry: row = lowerAddr, col = upperAddr, slot f
+        label pos = row_ptrs[l] + atomicAdd(&cursor[l], 1);
+        cols[pos] = u;
+        map[pos] = f;
+        // lower-triangle entry: row = upperAddr, col = lowerAddr,
+        // slot f (symmetric: shares the upper coefficient) or F + f
+        pos = row_ptrs[u] + atomicAdd(&cursor[u], 1);
+        cols[pos] = l;
+        map[pos] = symmetric ? f : nf + f;
+    } else if (i < (int64_t)nf + n) {
+        const label r = (label)(i - nf);
+        const label pos = row_ptrs[r] + atomicAdd(&cursor[r], 1);
+        cols[pos] = r;
+        map[pos] = diag_base + r;
+    } else if (i < (int64_t)nf + n + n_if) {
+        const label k = (label)(i - nf - n);
+        const label r = if_rows[k];
+        const label pos = row_ptrs[r] + atomicAdd(&cursor[r], 1);
+        cols[pos] = if_cols[k];
+        map[pos] = diag_base + n + k;   // HostMatrix.C:574
+    }
+}
+
+// one thread per row: insertion sort on (col, slot), write the COO row index,
+// track the longest row
+__global__ void k_sort_rows(label n, const label *__restrict__ row_ptrs, label *rows,
+                            label *cols, label *map, label *max_len)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const label s = row_ptrs[r], e = row_ptrs[r + 1];
+    for (label i = s + 1; i < e; ++i) {
+        const label c = cols[i], m = map[i];
+        label j = i - 1;
+        while (j >= s && (cols[j] > c || (cols[j] == c && map[j] > m))) {
+            cols[j + 1] = cols[j];
+            map[j + 1] = map[j];
+            --j;
+        }
+        cols[j + 1] = c;
+        map[j + 1] = m;
+    }
+    for (label i = s; i < e; ++i) rows[i] = (label)r;
+    atomicMax(max_len, e - s);
+}
+
+__global__ void k_iota(label n, label *a)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (label)i;
+}
+
+__global__ void k_validate_rows(label n_rows, label n, const label *__restrict__ rows,
+                                int *bad)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && (rows[i] < 0 || rows[i] >= n_rows)) atomicExch(bad, 3);
+}
+
+// heads of the runs of equal rows in the sorted non-local pattern
+__global__ void k_mark_heads(label n, const label *__restrict__ rows, label *head)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || rows[i] != rows[i - 1]) ? 1 : 0;
+}
+
+__global__ void k_compact_heads(label n, const label *__restrict__ rows,
+                                const label *__restrict__ head,
+                                const label *__restrict__ head_scan, label *row_ids,
+                                label *row_ptrs, label n_unique)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && head[i]) {
+        row_ids[head_scan[i]] = rows[i];
+        row_ptrs[head_scan[i]] = (label)i;
+    }
+    if (i == 0) row_ptrs[n_unique] = n;
+}
+
+// coefficient gather (HostMatrix.C:685-703 row_gather + CsrMatrixWrapper.H:123-135
+// value copy, fused): vals[k] = scaling * staging[map[k]], the local interface
+// segment negated (HostMatrix.C:204).
+__global__ void k_gather_values(int64_t nnz, const label *__restrict__ map,
+                                const double *__restrict__ staging, label iface_base,
+                                double scaling, double *__restrict__ vals)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += stride) {
+        const label m = __ldcs(&map[k]);
+        double v = __ldg(&staging[m]);
+        if (m >= iface_base) v = v * -1.0;
+        __stcs(&vals[k], scaling == 1.0 ? v : scaling * v);
+    }
+}
+
+__global__ void k_gather_nonlocal(label n_halo, const label *__restrict__ map,
+                                  const double *__restrict__ bou, double scaling,
+                                  double *__restrict__ vals)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_halo) {
+        const double v = bou[map[k]] * -1.0;   // HostMatrix.C:204 then :723-726
+        vals[k] = scaling == 1.0 ? v : scaling * v;
+    }
+}
+
+}  // namespace
+
+int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *lower,
+                     const label *upper, label n_if, const label *if_rows,
+                     const label *if_cols)
+{
+    if (n < 0 || nf < 0 || n_if < 0) return fail(ctx, OGL_ERR_INVALID, "negative size");
+    if ((nf > 0 && (!lower || !upper)) || (n_if > 0 && (!if_rows || !if_cols)))
+        return fail(ctx, OGL_ERR_INVALID, "null addressing pointer");
+    const int64_t nnz = (int64_t)n + 2 * (int64_t)nf + n_if;
+    if (nnz > INT32_MAX)
+        return fail(ctx, OGL_ERR_UNSUPPORTED, "local nnz exceeds label (int32) range");
+    cudaStream_t st = ctx->stream;
+
+    label *d_lower = nullptr, *d_upper = nullptr, *d_ifr = nullptr, *d_ifc = nullptr;
+    label *d_cursor = nullptr, *d_counts = nullptr, *d_max = nullptr;
+    int *d_bad = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_lower), cudaFree(d_upper), cudaFree(d_ifr), cudaFree(d_ifc);
+        cudaFree(d_cursor), cudaFree(d_counts), cudaFree(d_max), cudaFree(d_bad);
+        cudaFree(d_tmp);
+    };
+#define TRY_CLEAN(expr)                      \
+    do {                                     \
+        int rc__ = (expr);                   \
+        if (rc__ != OGL_OK) {                \
+            cleanup();                       \
+            return rc__;                     \
+        }                                    \
+    } while (0)
+
+    TRY_CLEAN(dev_alloc(ctx, &d_lower, nf));
+    TRY_CLEAN(dev_alloc(ctx, &d_upper, nf));
+    TRY_CLEAN(dev_alloc(ctx, &d_ifr, n_if));
+    TRY_CLEAN(dev_alloc(ctx, &d_ifc, n_if));
+    TRY_CLEAN(dev_alloc(ctx, &d_counts, (size_t)n + 1));
+    TRY_CLEAN(dev_alloc(ctx, &d_cursor, n));
+    TRY_CLEAN(dev_alloc(ctx, &d_max, 1));
+    TRY_CLEAN(dev_alloc(ctx, &d_bad, 1));
+    TRY_CLEAN(upload(ctx, d_lower, lower, sizeof(label) * nf));
+    TRY_CLEAN(upload(ctx, d_upper, upper, sizeof(label) * nf));
+    TRY_CLEAN(upload(ctx, d_ifr, if_rows, sizeof(label) * n_if));
+    TRY_CLEAN(upload(ctx, d_ifc, if_cols, sizeof(label) * n_if));
+
+    TRY_CLEAN(dev_alloc(ctx, &ctx->d_rows, nnz));
+    TRY_CLEAN(dev_alloc(ctx, &ctx->d_cols, nnz));
+    TRY_CLEAN(dev_alloc(ctx, &ctx->d_map, nnz));
+    TRY_CLEAN(dev_alloc(ctx, &ctx->d_row_ptrs, (size_t)n + 1));
+
+    cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    cudaMemsetAsync(d_max, 0, sizeof(label), st);
+    cudaMemsetAsync(d_cursor, 0, sizeof(label) * (size_t)(n > 0 ? n : 1), st);
+    cudaMemsetAsync(d_counts, 0, sizeof(label) * ((size_t)n + 1), st);
+    k_fill_ones<<<grid_for(n), kThreads, 0, st>>>(n, d_counts);
+    k_count_rows<<<grid_for((int64_t)nf + n_if), kThreads, 0, st>>>(
+        n, nf, d_lower, d_upper, n_if, d_ifr, d_ifc, d_counts, d_bad);
+    {
+        // stop before the scatter if the addressing is malformed (the counts
+        // would not cover the entries the scatter writes)
+        int bad0 = 0;
+        cudaMemcpyAsync(&bad0, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaError_t e0 = cudaStreamSynchronize(st);
+        if (e0 != cudaSuccess || bad0 != 0) {
+            cleanup();
+            if (e0 != cudaSuccess)
+                return fail(ctx, OGL_ERR_CUDA,
+                            std::string("pattern_from_ldu: ") + cudaGetErrorString(e0));
+            return fail(ctx, OGL_ERR_INVALID,
+                        bad0 == 1 ? "lduAddressing violates 0 <= lowerAddr < upperAddr < nRows"
+                                  : "local interface index out of range");
+        }
+    }
+    // exclusive scan of the n counts (+ trailing 0) -> row_ptrs[0..n]
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, ctx->d_row_ptrs, n + 1, st);
+    if (cudaMalloc(&d_tmp, tmp_bytes + 16) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, OGL_ERR_CUDA, "cudaMalloc(scan temp)");
+    }
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, ctx->d_row_ptrs, n + 1, st);
+    k_scatter<<<grid_for((int64_t)nf + n + n_if), kThreads, 0, st>>>(
+        n, nf, sym ? 1 : 0, d_lower, d_upper, n_if, d_ifr, d_ifc, ctx->d_row_ptrs, d_cursor,
+        ctx->d_cols, ctx->d_map);
+    k_sort_rows<<<grid_for(n), kThreads, 0, st>>>(n, ctx->d_row_ptrs, ctx->d_rows,
+                                                   ctx->d_cols, ctx->d_map, d_max);
+    int bad = 0;
+    label max_len = 0;
+    cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&max_len, d_max, sizeof(label), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+#undef TRY_CLEAN
+    if (e != cudaSuccess)
+        return fail(ctx, OGL_ERR_CUDA, std::string("pattern_from_ldu: ") + cudaGetErrorString(e));
+    (void)bad;
+
+    ctx->n = n;
+    ctx->n_faces = nf;
+    ctx->n_local_iface = n_if;
+    ctx->symmetric = sym;
+    ctx->nnz = nnz;
+    ctx->max_row_len = max_len;
+    ctx->have_pattern = true;
+    ctx->have_values = false;
+    ctx->have_precond = false;
+    ctx->have_b = ctx->have_x = false;
+    // a new local pattern invalidates the halo description built on the old one
+    ctx->have_nonlocal = false;
+    ctx->have_partition = false;
+    ctx->n_halo = 0;
+    ctx->n_nl_rows = 0;
+    ctx->n_targets = 0;
+    ctx->n_send = 0;
+    ctx->global_n = n;
+    ctx->n_blocks = 0;
+    ctx->bj_pattern_mbs = 0;
+    if (ctx->graph_exec) {
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+    }
+    // value buffers sized for this pattern
+    ctx->staging_len = (size_t)nf * (sym ? 1 : 2) + n + n_if;
+    OGL_TRY(dev_alloc(ctx, &ctx->d_staging, ctx->staging_len));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_vals, nnz));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_b, n));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_x, n));
+    for (auto &w : ctx->work) {
+        if (w) cudaFree(w);
+        w = nullptr;
+    }
+    return spmv_setup(ctx);
+}
+
+int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
+{
+    if (!ctx->have_pattern)
+        return fail(ctx, OGL_ERR_INVALID, "ogl_nonlocal_pattern before ogl_pattern_from_ldu");
+    if (n_halo < 0 || (n_halo > 0 && !face_cells))
+        return fail(ctx, OGL_ERR_INVALID, "bad halo arguments");
+    cudaStream_t st = ctx->stream;
+    ctx->n_halo = n_halo;
+    ctx->n_nl_rows = 0;
+    OGL_TRY(dev_alloc(ctx, &ctx->d_nl_rows, n_halo));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_nl_cols, n_halo));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_nl_map, n_halo));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_nl_vals, n_halo));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_nl_staging, n_halo));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_nl_row_ids, n_halo));
+    OGL_TRY(dev_alloc(ctx, &ctx->d_nl_row_ptrs, (size_t)n_halo + 1));
+    ctx->have_nonlocal = true;
+    if (n_halo == 0) return OGL_OK;
+
+    label *d_keys = nullptr, *d_iota = nullptr, *d_head = nullptr, *d_scan = nullptr;
+    int *d_bad = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_keys), cudaFree(d_iota), cudaFree(d_head), cudaFree(d_scan);
+        cudaFree(d_bad), cudaFree(d_tmp);
+    };
+    int rc = OGL_OK;
+    if ((rc = dev_alloc(ctx, &d_keys, n_halo)) || (rc = dev_alloc(ctx, &d_iota, n_halo)) ||
+        (rc = dev_alloc(ctx, &d_head, n_halo)) || (rc = dev_alloc(ctx, &d_scan, n_halo)) ||
+        (rc = dev_alloc(ctx, &d_bad, 1)) ||
+        (rc = upload(ctx, d_keys, face_cells, sizeof(label) * n_halo))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    k_validate_rows<<<grid_for(n_halo), kThreads, 0, st>>>(ctx->n, n_halo, d_keys, d_bad);
+    k_iota<<<grid_for(n_halo), kThreads, 0, st>>>(n_halo, d_iota);
+    // stable LSD radix sort by row: ties keep the running interface index order
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, ctx->d_nl_rows, d_iota,
+                                    ctx->d_nl_cols, n_halo, 0, 32, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_head, d_scan, n_halo, st);
+    const size_t tmp_bytes = (sort_bytes > scan_bytes ? sort_bytes : scan_bytes) + 16;
+    if (cudaMalloc(&d_tmp, tmp_bytes) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, OGL_ERR_CUDA, "cudaMalloc(sort temp)");
+    }
+    cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, d_keys, ctx->d_nl_rows, d_iota,
+                                    ctx->d_nl_cols, n_halo, 0, 32, st);
+    // cols == mapping == running interface index (HostMatrix.C:459-465)
+    cudaMemcpyAsync(ctx->d_nl_map, ctx->d_nl_cols, sizeof(label) * n_halo,
+                    cudaMemcpyDeviceToDevice, st);
+    // group by row for the non-local SpMV
+    k_mark_heads<<<grid_for(n_halo), kThreads, 0, st>>>(n_halo, ctx->d_nl_rows, d_head);
+    cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, d_head, d_scan, n_halo, st);
+    label last_head = 0, last_scan = 0;
+    int bad = 0;
+    cudaMemcpyAsync(&last_head, d_head + (n_halo - 1), sizeof(label), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&last_scan, d_scan + (n_halo - 1), sizeof(label), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(ctx, OGL_ERR_CUDA, std::string("nonlocal_pattern: ") + cudaGetErrorString(e));
+    }
+    if (bad) {
+        cleanup();
+        ctx->have_nonlocal = false;
+        return fail(ctx, OGL_ERR_INVALID, "processor faceCells index out of range");
+    }
+    ctx->n_nl_rows = last_scan + last_head;
+    k_compact_heads<<<grid_for(n_halo), kThreads, 0, st>>>(
+        n_halo, ctx->d_nl_rows, d_head, d_scan, ctx->d_nl_row_ids, ctx->d_nl_row_ptrs,
+        ctx->n_nl_rows);
+    e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess)
+        return fail(ctx, OGL_ERR_CUDA, std::string("nonlocal_pattern: ") + cudaGetErrorString(e));
+    return OGL_OK;
+}
+
+int values_update(Context *ctx, const double *diag, const double *upper,
+                  const double *lower, const double *if_bou, const double *nl_bou,
+                  double scaling)
+{
+    if (!ctx->have_pattern)
+        return fail(ctx, OGL_ERR_INVALID, "ogl_values_update before ogl_pattern_from_ldu");
+    const label n = ctx->n, nf = ctx->n_faces, n_if = ctx->n_local_iface;
+    if ((n > 0 && !diag) || (nf > 0 && !upper) || (nf > 0 && !ctx->symmetric && !lower) ||
+        (n_if > 0 && !if_bou) || (ctx->n_halo > 0 && !nl_bou))
+        return fail(ctx, OGL_ERR_INVALID, "null coefficient pointer");
+    cudaStream_t st = ctx->stream;
+    // staging layout of HostMatrix.C:644-681: [upper | lower (asym) | diag | iface]
+    size_t off = 0;
+    OGL_TRY(upload(ctx, ctx->d_staging + off, upper, sizeof(double) * nf));
+    off += nf;
+    if (!ctx->symmetric) {
+        OGL_TRY(upload(ctx, ctx->d_staging + off, lower, sizeof(double) * nf));
+        off += nf;
+    }
+    OGL_TRY(upload(ctx, ctx->d_staging + off, diag, sizeof(double) * n));
+    off += n;
+    const label iface_base = (label)off;
+    OGL_TRY(upload(ctx, ctx->d_staging + off, if_bou, sizeof(double) * n_if));
+    int g = grid_for(ctx->nnz);
+    if (g > kNumSM * 16) g = kNumSM * 16;
+    k_gather_values<<<g, kThreads, 0, st>>>(ctx->nnz, ctx->d_map, ctx->d_staging, iface_base,
+                                            scaling, ctx->d_vals);
+    ctx->launches++;
+    if (ctx->n_halo > 0) {
+        if (!ctx->have_nonlocal)
+            return fail(ctx, OGL_ERR_INVALID, "non-local coefficients without ogl_nonlocal_pattern");
+        OGL_TRY(upload(ctx, ctx->d_nl_staging, nl_bou, sizeof(double) * ctx->n_halo));
+        k_gather_nonlocal<<<grid_for(ctx->n_halo), kThreads, 0, st>>>(
+            ctx->n_halo, ctx->d_nl_map, ctx->d_nl_staging, scaling, ctx->d_nl_vals);
+        ctx->launches++;
+    }
+    OGL_CUDA(ctx, cudaGetLastError());
+    ctx->have_values = true;
+    ctx->have_precond = false;   // regenerated every solve (caching 0, Preconditioner.H:416-422)
+    return OGL_OK;
+}
+
+}  // namespace ogl

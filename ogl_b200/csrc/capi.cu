@@ -1,0 +1,520 @@
+// extern "C" entry points of libogl_b200.so (include/ogl_b200.h) and the small
+// host-side helpers shared by the kernels' launchers.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <mutex>
+
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace ogl {
+
+static thread_local std::string g_last_error;
+
+void set_error(Context *ctx, const std::string &msg)
+{
+    if (ctx) ctx->error = msg;
+    g_last_error = msg;
+}
+
+int fail(Context *ctx, int code, const std::string &msg)
+{
+    set_error(ctx, msg);
+    return code;
+}
+
+int upload(Context *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return OGL_OK;
+    if (!src) return fail(ctx, OGL_ERR_INVALID, "null host pointer in upload");
+    // pinned sources are DMA'd directly; pageable ones are staged by the driver
+    OGL_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return OGL_OK;
+}
+
+int download(Context *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return OGL_OK;
+    if (!dst) return fail(ctx, OGL_ERR_INVALID, "null host pointer in download");
+    OGL_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OGL_OK;
+}
+
+int get_work(Context *ctx, int idx, double **out)
+{
+    if ((int)ctx->work.size() <= idx) ctx->work.resize(idx + 1, nullptr);
+    if (!ctx->work[idx]) OGL_TRY(dev_alloc(ctx, &ctx->work[idx], ctx->n));
+    *out = ctx->work[idx];
+    return OGL_OK;
+}
+
+static void destroy(Context *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->comm) ncclCommDestroy(c->comm);
+    void *ptrs[] = {c->d_rows,       c->d_cols,       c->d_map,        c->d_row_ptrs,
+                    c->d_send_idxs,  c->d_send_buf,   c->d_recv_buf,   c->d_nl_rows,
+                    c->d_nl_cols,    c->d_nl_map,     c->d_nl_row_ids, c->d_nl_row_ptrs,
+                    c->d_staging,    c->d_vals,       c->d_nl_vals,    c->d_nl_staging,
+                    c->d_b,          c->d_x,          c->d_krylov,     c->d_hess,
+                    c->d_inv_diag,   c->d_block_ptrs, c->d_row_block,  c->d_block_offs,
+                    c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
+                    c->d_history};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (double *w : c->work)
+        if (w) cudaFree(w);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaEvent_t evs[] = {c->ev_pack, c->ev_recv, c->ev_t0, c->ev_t1, c->ev_poll[0], c->ev_poll[1]};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete static_cast<ogl_ctx *>(c);
+}
+
+}  // namespace ogl
+
+using namespace ogl;
+
+#define CHECK_CTX(ctx)                                                      \
+    do {                                                                    \
+        if (!(ctx)) {                                                       \
+            ogl::set_error(nullptr, "null context");                        \
+            return OGL_ERR_INVALID;                                         \
+        }                                                                   \
+        cudaError_t e__ = cudaSetDevice((ctx)->device);                     \
+        if (e__ != cudaSuccess)                                             \
+            return ogl::fail(ctx, OGL_ERR_CUDA,                             \
+                             std::string("cudaSetDevice: ") + cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" {
+
+int ogl_nccl_unique_id(void *out_id)
+{
+    if (!out_id) return OGL_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) <= OGL_NCCL_ID_BYTES, "ncclUniqueId grew");
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) {
+        ogl::set_error(nullptr, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+        return OGL_ERR_NCCL;
+    }
+    std::memset(out_id, 0, OGL_NCCL_ID_BYTES);
+    std::memcpy(out_id, &id, sizeof(id));
+    return OGL_OK;
+}
+
+int ogl_device_count(int *count)
+{
+    if (!count) return OGL_ERR_INVALID;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        ogl::set_error(nullptr, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        return OGL_ERR_CUDA;
+    }
+    return OGL_OK;
+}
+
+int ogl_ctx_create(int device_id, int rank, int n_ranks, const void *nccl_id, void *stream,
+                   ogl_ctx **out)
+{
+    if (!out) return OGL_ERR_INVALID;
+    *out = nullptr;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return ogl::fail(nullptr, OGL_ERR_INVALID, "bad rank / n_ranks");
+    if (n_ranks > 1 && !nccl_id)
+        return ogl::fail(nullptr, OGL_ERR_INVALID, "n_ranks > 1 needs an NCCL unique id");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return ogl::fail(nullptr, OGL_ERR_CUDA,
+                         std::string("no CUDA device usable (there is no CPU fallback): ") +
+                             (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices"));
+    // ExecutorHandler.H:57-58: device_id % num_devices
+    const int dev = ((device_id % ndev) + ndev) % ndev;
+    e = cudaSetDevice(dev);
+    if (e != cudaSuccess)
+        return ogl::fail(nullptr, OGL_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    if (prop.major < 10)
+        return ogl::fail(nullptr, OGL_ERR_CUDA,
+                         "device is not Blackwell-class (sm_100a cubin only, no fallback)");
+    ogl_ctx *c = new ogl_ctx();
+    c->device = dev;
+    c->rank = rank;
+    c->n_ranks = n_ranks;
+    auto bail = [&](int code, const std::string &msg) {
+        ogl::set_error(nullptr, msg);
+        ogl::destroy(c);
+        return code;
+    };
+    if (stream) {
+        c->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+            return bail(OGL_ERR_CUDA, "cudaStreamCreate failed");
+        c->own_stream = true;
+    }
+    bool ok = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->ev_t0) == cudaSuccess && cudaEventCreate(&c->ev_t1) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_poll[1], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_state, sizeof(SolveState)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_ticket, sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_state, 3 * sizeof(SolveState)) == cudaSuccess;
+    if (!ok) return bail(OGL_ERR_CUDA, std::string("context allocation failed: ") +
+                                           cudaGetErrorString(cudaGetLastError()));
+    cudaMemset(c->d_state, 0, sizeof(SolveState));
+    cudaMemset(c->d_ticket, 0, sizeof(unsigned int));
+    std::memset(c->h_state, 0, 3 * sizeof(SolveState));
+    if (n_ranks > 1) {
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t r = ncclCommInitRank(&c->comm, n_ranks, id, rank);
+        if (r != ncclSuccess)
+            return bail(OGL_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    }
+    *out = c;
+    return OGL_OK;
+}
+
+int ogl_ctx_destroy(ogl_ctx *ctx)
+{
+    if (!ctx) return OGL_ERR_INVALID;
+    ogl::destroy(ctx);
+    return OGL_OK;
+}
+
+const char *ogl_last_error(const ogl_ctx *ctx)
+{
+    return ctx ? ctx->error.c_str() : ogl::g_last_error.c_str();
+}
+
+int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
+{
+    CHECK_CTX(ctx);
+    if (!key) return fail(ctx, OGL_ERR_INVALID, "null option key");
+    const std::string k(key);
+    if (k == "spmv_variant") {
+        if (value < 0 || value > 4) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,4]");
+        ctx->spmv_variant = value;
+    } else if (k == "chunk_iters") {
+        if (value < 1) return fail(ctx, OGL_ERR_INVALID, "chunk_iters >= 1");
+        ctx->chunk_iters = value;
+    } else if (k == "use_graph") {
+        ctx->use_graph = value != 0;
+    } else if (k == "profile_stride") {
+        ctx->profile_stride = value < 0 ? 0 : value;
+    } else if (k == "blas1_blocks") {
+        if (value < 1 || value > 65535) return fail(ctx, OGL_ERR_INVALID, "blas1_blocks in [1,65535]");
+        ctx->blas1_blocks = value;
+        if (ctx->have_pattern) OGL_TRY(spmv_setup(ctx));
+    } else {
+        return fail(ctx, OGL_ERR_INVALID, "unknown option: " + k);
+    }
+    if (ctx->graph_exec) {
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+    }
+    return OGL_OK;
+}
+
+int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
+{
+    CHECK_CTX(ctx);
+    if (!key || !value) return fail(ctx, OGL_ERR_INVALID, "null argument");
+    const std::string k(key);
+    if (k == "spmv_variant") *value = ctx->spmv_variant;
+    else if (k == "chunk_iters") *value = ctx->chunk_iters;
+    else if (k == "use_graph") *value = ctx->use_graph;
+    else if (k == "profile_stride") *value = ctx->profile_stride;
+    else if (k == "blas1_blocks") *value = ctx->blas1_blocks;
+    else if (k == "max_row_len") *value = ctx->max_row_len;
+    else if (k == "max_block_nnz") *value = ctx->max_block_nnz;
+    else if (k == "launches") *value = ctx->launches;
+    else return fail(ctx, OGL_ERR_INVALID, "unknown option: " + k);
+    return OGL_OK;
+}
+
+int ogl_pattern_from_ldu(ogl_ctx *ctx, int32_t n_rows, int32_t n_faces, int symmetric,
+                         const int32_t *lower_addr, const int32_t *upper_addr,
+                         int32_t n_local_iface, const int32_t *iface_rows,
+                         const int32_t *iface_cols)
+{
+    CHECK_CTX(ctx);
+    return pattern_from_ldu(ctx, n_rows, n_faces, symmetric != 0, lower_addr, upper_addr,
+                            n_local_iface, iface_rows, iface_cols);
+}
+
+int ogl_pattern_nnz(ogl_ctx *ctx, int64_t *local_nnz, int64_t *nonlocal_nnz)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_pattern) return fail(ctx, OGL_ERR_INVALID, "no pattern");
+    if (local_nnz) *local_nnz = ctx->nnz;
+    if (nonlocal_nnz) *nonlocal_nnz = ctx->n_halo;
+    return OGL_OK;
+}
+
+int ogl_pattern_download(ogl_ctx *ctx, int32_t *rows, int32_t *cols, int32_t *ldu_mapping,
+                         int32_t *row_ptrs)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_pattern) return fail(ctx, OGL_ERR_INVALID, "no pattern");
+    if (rows) OGL_TRY(download(ctx, rows, ctx->d_rows, sizeof(label) * ctx->nnz));
+    if (cols) OGL_TRY(download(ctx, cols, ctx->d_cols, sizeof(label) * ctx->nnz));
+    if (ldu_mapping) OGL_TRY(download(ctx, ldu_mapping, ctx->d_map, sizeof(label) * ctx->nnz));
+    if (row_ptrs) OGL_TRY(download(ctx, row_ptrs, ctx->d_row_ptrs, sizeof(label) * (ctx->n + 1)));
+    return OGL_OK;
+}
+
+int ogl_partition_create(ogl_ctx *ctx, int32_t n_local, int32_t n_targets,
+                         const int32_t *target_ids, const int32_t *target_sizes,
+                         const int32_t *send_idxs)
+{
+    CHECK_CTX(ctx);
+    return partition_create(ctx, n_local, n_targets, target_ids, target_sizes, send_idxs);
+}
+
+int ogl_partition_sizes(ogl_ctx *ctx, int64_t *local_size, int64_t *global_size)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_pattern) return fail(ctx, OGL_ERR_INVALID, "no pattern");
+    if (local_size) *local_size = ctx->n;
+    if (global_size) *global_size = ctx->global_n;
+    return OGL_OK;
+}
+
+int ogl_nonlocal_pattern(ogl_ctx *ctx, int32_t n_halo, const int32_t *face_cells)
+{
+    CHECK_CTX(ctx);
+    return nonlocal_pattern(ctx, n_halo, face_cells);
+}
+
+int ogl_nonlocal_pattern_download(ogl_ctx *ctx, int32_t *rows, int32_t *cols, int32_t *mapping)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_nonlocal) return fail(ctx, OGL_ERR_INVALID, "no non-local pattern");
+    if (rows) OGL_TRY(download(ctx, rows, ctx->d_nl_rows, sizeof(label) * ctx->n_halo));
+    if (cols) OGL_TRY(download(ctx, cols, ctx->d_nl_cols, sizeof(label) * ctx->n_halo));
+    if (mapping) OGL_TRY(download(ctx, mapping, ctx->d_nl_map, sizeof(label) * ctx->n_halo));
+    return OGL_OK;
+}
+
+int ogl_values_update(ogl_ctx *ctx, const double *diag, const double *upper, const double *lower,
+                      const double *local_iface_bou, const double *nonlocal_bou, double scaling)
+{
+    CHECK_CTX(ctx);
+    return values_update(ctx, diag, upper, lower, local_iface_bou, nonlocal_bou, scaling);
+}
+
+int ogl_values_download(ogl_ctx *ctx, double *local_vals, double *nonlocal_vals)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_values) return fail(ctx, OGL_ERR_INVALID, "no values");
+    if (local_vals) OGL_TRY(download(ctx, local_vals, ctx->d_vals, sizeof(double) * ctx->nnz));
+    if (nonlocal_vals && ctx->n_halo)
+        OGL_TRY(download(ctx, nonlocal_vals, ctx->d_nl_vals, sizeof(double) * ctx->n_halo));
+    return OGL_OK;
+}
+
+int ogl_vector_upload(ogl_ctx *ctx, int which, const double *host, double scale)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_pattern) return fail(ctx, OGL_ERR_INVALID, "vector upload before the pattern");
+    if (which != OGL_VEC_B && which != OGL_VEC_X) return fail(ctx, OGL_ERR_INVALID, "bad vector id");
+    double *dst = which == OGL_VEC_B ? ctx->d_b : ctx->d_x;
+    OGL_TRY(upload(ctx, dst, host, sizeof(double) * ctx->n));
+    // lduLduBase.H:242-252: b is scaled when `scaling` != 1
+    if (scale != 1.0 && ctx->n > 0) OGL_TRY(vec_scale(ctx, dst, scale));
+    (which == OGL_VEC_B ? ctx->have_b : ctx->have_x) = true;
+    return OGL_OK;
+}
+
+int ogl_vector_download(ogl_ctx *ctx, int which, double *host)
+{
+    CHECK_CTX(ctx);
+    if (which != OGL_VEC_B && which != OGL_VEC_X) return fail(ctx, OGL_ERR_INVALID, "bad vector id");
+    if (!(which == OGL_VEC_B ? ctx->have_b : ctx->have_x))
+        return fail(ctx, OGL_ERR_INVALID, "vector was never set");
+    return download(ctx, host, which == OGL_VEC_B ? ctx->d_b : ctx->d_x, sizeof(double) * ctx->n);
+}
+
+int ogl_vector_fill(ogl_ctx *ctx, int which, double value)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_pattern) return fail(ctx, OGL_ERR_INVALID, "vector fill before the pattern");
+    if (which != OGL_VEC_B && which != OGL_VEC_X) return fail(ctx, OGL_ERR_INVALID, "bad vector id");
+    if (ctx->n > 0) OGL_TRY(vec_fill(ctx, which == OGL_VEC_B ? ctx->d_b : ctx->d_x, value));
+    (which == OGL_VEC_B ? ctx->have_b : ctx->have_x) = true;
+    return OGL_OK;
+}
+
+int ogl_precond_setup(ogl_ctx *ctx, int kind, int32_t max_block_size, int skip_sorting)
+{
+    CHECK_CTX(ctx);
+    (void)skip_sorting;   // the assembled pattern is always row-sorted (skipSorting true)
+    return precond_setup(ctx, kind, max_block_size);
+}
+
+int ogl_precond_download(ogl_ctx *ctx, int32_t *n_blocks, int32_t *block_ptrs, double *inv_blocks)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_precond || ctx->precond_kind != OGL_PRECOND_BJ)
+        return fail(ctx, OGL_ERR_INVALID, "no BJ preconditioner");
+    if (ctx->max_block_size == 1) {
+        if (n_blocks) *n_blocks = ctx->n;
+        if (inv_blocks) OGL_TRY(download(ctx, inv_blocks, ctx->d_inv_diag, sizeof(double) * ctx->n));
+        if (block_ptrs) {
+            std::vector<label> bp(ctx->n + 1);
+            for (label i = 0; i <= ctx->n; ++i) bp[i] = i;
+            std::memcpy(block_ptrs, bp.data(), sizeof(label) * (ctx->n + 1));
+        }
+        return OGL_OK;
+    }
+    if (n_blocks) *n_blocks = ctx->n_blocks;
+    if (block_ptrs)
+        OGL_TRY(download(ctx, block_ptrs, ctx->d_block_ptrs, sizeof(label) * (ctx->n_blocks + 1)));
+    if (inv_blocks)
+        OGL_TRY(download(ctx, inv_blocks, ctx->d_inv_blocks, sizeof(double) * ctx->inv_blocks_len));
+    return OGL_OK;
+}
+
+int ogl_solve(ogl_ctx *ctx, const ogl_solve_params *params, ogl_solve_result *result)
+{
+    CHECK_CTX(ctx);
+    return solve(ctx, params, result);
+}
+
+int ogl_residual_history(ogl_ctx *ctx, double *out, int32_t capacity, int32_t *written)
+{
+    CHECK_CTX(ctx);
+    if (!out || capacity < 0) return fail(ctx, OGL_ERR_INVALID, "bad history buffer");
+    int n = ctx->h_state[0].n_history;
+    if (n > capacity) n = capacity;
+    if (n > 0 && ctx->d_history) OGL_TRY(download(ctx, out, ctx->d_history, sizeof(double) * n));
+    if (written) *written = n;
+    return OGL_OK;
+}
+
+int ogl_spmv(ogl_ctx *ctx, const double *x_host, double *y_host)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_values) return fail(ctx, OGL_ERR_INVALID, "ogl_spmv before the matrix is assembled");
+    double *x, *y;
+    OGL_TRY(get_work(ctx, 0, &x));
+    OGL_TRY(get_work(ctx, 1, &y));
+    OGL_TRY(upload(ctx, x, x_host, sizeof(double) * ctx->n));
+    SpmvArgs s;
+    s.x = x;
+    s.y = y;
+    OGL_TRY(dist_spmv(ctx, s));
+    return download(ctx, y_host, y, sizeof(double) * ctx->n);
+}
+
+int ogl_spmv_bench(ogl_ctx *ctx, int32_t reps, int fused_dot, float *ms)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_values || reps < 1 || !ms)
+        return fail(ctx, OGL_ERR_INVALID, "ogl_spmv_bench: bad state or arguments");
+    double *x, *y;
+    OGL_TRY(get_work(ctx, 2, &x));
+    OGL_TRY(get_work(ctx, 3, &y));
+    OGL_TRY(vec_fill(ctx, x, 1.0));
+    ogl_solve_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.frequency = 1;
+    p.max_iter = 1;
+    OGL_TRY(init_state(ctx, &p));
+    SpmvArgs s;
+    s.x = x;
+    s.y = y;
+    if (fused_dot) {
+        s.dot_with = x;
+        s.nred = 1;
+        s.epi = EPI_CG_BETA;
+    }
+    for (int i = 0; i < 3; ++i) OGL_TRY(dist_spmv(ctx, s));
+    OGL_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    for (int i = 0; i < reps; ++i) OGL_TRY(dist_spmv(ctx, s));
+    OGL_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    OGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    OGL_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return OGL_OK;
+}
+
+int ogl_pcg_bench(ogl_ctx *ctx, int32_t iters, float *ms)
+{
+    CHECK_CTX(ctx);
+    if (iters < 1 || !ms) return fail(ctx, OGL_ERR_INVALID, "ogl_pcg_bench: bad arguments");
+    // a solve that can only stop on maxIter: tolerance 0 is never undercut
+    ogl_solve_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.solver = OGL_SOLVER_CG;
+    p.tolerance = 0.0;
+    p.rel_tol = 0.0;
+    p.max_iter = iters;
+    p.frequency = 1;
+    ogl_solve_result r;
+    OGL_TRY(solve(ctx, &p, &r));
+    *ms = (float)(r.solve_us * 1e-3);
+    return OGL_OK;
+}
+
+int ogl_synchronize(ogl_ctx *ctx)
+{
+    CHECK_CTX(ctx);
+    OGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    OGL_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    return OGL_OK;
+}
+
+int ogl_export_mtx(ogl_ctx *ctx, int which, const char *path)
+{
+    CHECK_CTX(ctx);
+    if (!path) return fail(ctx, OGL_ERR_INVALID, "null path");
+    if (which < 0 || which > 2) return fail(ctx, OGL_ERR_INVALID, "which in {0,1,2}");
+    std::ofstream os(path);
+    if (!os) return fail(ctx, OGL_ERR_INVALID, std::string("cannot open ") + path);
+    os << std::setprecision(15);   // common.C:48
+    if (which == 2) {
+        if (!ctx->have_b) return fail(ctx, OGL_ERR_INVALID, "no rhs");
+        std::vector<double> b(ctx->n);
+        OGL_TRY(download(ctx, b.data(), ctx->d_b, sizeof(double) * ctx->n));
+        // gko::write of a Dense: array layout
+        os << "%%MatrixMarket matrix array real general\n" << ctx->n << " 1\n";
+        for (double v : b) os << v << "\n";
+        return OGL_OK;
+    }
+    if (!ctx->have_values) return fail(ctx, OGL_ERR_INVALID, "no matrix values");
+    const int64_t nnz = which == 0 ? ctx->nnz : ctx->n_halo;
+    std::vector<label> rows(nnz), cols(nnz);
+    std::vector<double> vals(nnz);
+    if (nnz > 0) {
+        OGL_TRY(download(ctx, rows.data(), which == 0 ? ctx->d_rows : ctx->d_nl_rows, sizeof(label) * nnz));
+        OGL_TRY(download(ctx, cols.data(), which == 0 ? ctx->d_cols : ctx->d_nl_cols, sizeof(label) * nnz));
+        OGL_TRY(download(ctx, vals.data(), which == 0 ? ctx->d_vals : ctx->d_nl_vals, sizeof(double) * nnz));
+    }
+    // gko::write(stream, mtx): coordinate layout, 1-based, row-major order
+    os << "%%MatrixMarket matrix coordinate real general\n"
+       << ctx->n << " " << (which == 0 ? (int64_t)ctx->n : (int64_t)ctx->n_halo) << " " << nnz << "\n";
+    for (int64_t k = 0; k < nnz; ++k)
+        os << rows[k] + 1 << " " << cols[k] + 1 << " " << vals[k] << "\n";
+    return OGL_OK;
+}
+
+}  // extern "C"

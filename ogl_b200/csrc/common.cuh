@@ -1,0 +1,243 @@
+// Shared declarations of libogl_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "ogl_b200.h"
+
+namespace ogl {
+
+using label = int32_t;
+using scalar = double;
+
+constexpr int kMaxReduce = 4;          // scalars reduced by one kernel launch
+constexpr int kNumSM = 148;            // B200
+constexpr int kBlas1Threads = 256;
+constexpr int kBlas1BlocksPerSM = 8;   // 2048 resident threads per SM
+constexpr int kMaxPartialBlocks = 4096;
+
+// Device-resident scalar state of a solve.  Every kernel of the iteration reads
+// its coefficients from here, so the host never has to see alpha/beta/rho
+// (StoppingCriterion.C:95-97 costs the reference one D2H + sync per iteration).
+struct SolveState {
+    // --- Krylov scalars
+    double rho, prev_rho, beta, alpha, omega, gamma;
+    double coef_p;        // CG: rho/prev_rho (0 => p = z); BiCGStab: step_1 factor
+    double coef_x;        // CG: rho/beta (0 => skip update)
+    // --- OGL criterion (StoppingCriterion.C:71-151)
+    double norm_factor, init_res, res;
+    double tolerance, rel_tol;
+    int iter, min_iter, max_iter, frequency;
+    int done;             // 1 once the criterion fired; kernels early-exit
+    int stop_half;        // BiCGStab: stopped at the first (s) check => finalize
+    int export_res, history_cap, n_history;
+    int flag_p_is_z;      // CG step_1: prev_rho == 0
+    int pad;
+    // --- reduction mailboxes (local partial results, then all-reduced in place)
+    double red[kMaxReduce];
+    // --- GMRES
+    int restart_iter, final_iter, krylov_dim, need_restart;
+    double res_norm2;
+};
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct Context;
+
+// error plumbing ---------------------------------------------------------------
+void set_error(Context *ctx, const std::string &msg);
+int fail(Context *ctx, int code, const std::string &msg);
+
+#define OGL_CUDA(ctx, expr)                                                        \
+    do {                                                                           \
+        cudaError_t e__ = (expr);                                                  \
+        if (e__ != cudaSuccess)                                                    \
+            return ::ogl::fail(ctx, OGL_ERR_CUDA,                                  \
+                               std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define OGL_NCCL(ctx, expr)                                                        \
+    do {                                                                           \
+        ncclResult_t r__ = (expr);                                                 \
+        if (r__ != ncclSuccess)                                                    \
+            return ::ogl::fail(ctx, OGL_ERR_NCCL,                                  \
+                               std::string(#expr) + ": " + ncclGetErrorString(r__)); \
+    } while (0)
+
+#define OGL_TRY(expr)                     \
+    do {                                  \
+        int rc__ = (expr);                \
+        if (rc__ != OGL_OK) return rc__;  \
+    } while (0)
+
+struct Context {
+    int device = 0, rank = 0, n_ranks = 1;
+    cudaStream_t stream = nullptr;       // compute stream
+    bool own_stream = false;
+    cudaStream_t comm_stream = nullptr;  // halo exchange
+    cudaEvent_t ev_pack = nullptr, ev_recv = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+    ncclComm_t comm = nullptr;
+    std::string error;
+
+    // options
+    int64_t spmv_variant = 0;    // 0 auto, 1 stream(LDG), 2 thread-per-row, 3 warp-per-row, 4 TMA pipeline
+    int64_t chunk_iters = 16;    // iterations enqueued between two host polls
+    int64_t use_graph = 1;       // replay a chunk as a CUDA graph
+    int64_t profile_stride = 0;  // sample SpMV launch durations every k-th iteration
+    int64_t blas1_blocks = kNumSM * kBlas1BlocksPerSM;
+
+    // local pattern (a4/a5) -- resident across solves
+    label n = 0, n_faces = 0, n_local_iface = 0;
+    bool symmetric = true, have_pattern = false;
+    int64_t nnz = 0;
+    label *d_rows = nullptr, *d_cols = nullptr, *d_map = nullptr, *d_row_ptrs = nullptr;
+    label max_row_len = 0;
+    int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
+
+    // partition (a6/a11)
+    bool have_partition = false;
+    int64_t global_n = 0;
+    label n_targets = 0, n_send = 0;
+    std::vector<label> target_ids, target_sizes, send_offs;
+    label *d_send_idxs = nullptr;
+    double *d_send_buf = nullptr, *d_recv_buf = nullptr;
+
+    // non-local pattern (a7)
+    label n_halo = 0;
+    bool have_nonlocal = false;
+    label *d_nl_rows = nullptr, *d_nl_cols = nullptr, *d_nl_map = nullptr;
+    // CSR-like grouping of the non-local entries by row (rows touching the halo)
+    label n_nl_rows = 0;
+    label *d_nl_row_ids = nullptr, *d_nl_row_ptrs = nullptr;
+
+    // values (a8/a9)
+    bool have_values = false;
+    double *d_staging = nullptr;   // [upper | lower | diag | iface] as uploaded
+    size_t staging_len = 0;
+    double *d_vals = nullptr, *d_nl_vals = nullptr, *d_nl_staging = nullptr;
+
+    // vectors (a13) + solver workspace
+    double *d_b = nullptr, *d_x = nullptr;
+    bool have_b = false, have_x = false;
+    std::vector<double *> work;   // n-sized work vectors, allocated on demand
+    double *d_krylov = nullptr;   // GMRES basis (krylov_dim+1) * n
+    int64_t krylov_cap = 0;
+    double *d_hess = nullptr;     // GMRES small dense state
+    int64_t hess_cap = 0;
+
+    // preconditioner (a14)
+    int precond_kind = OGL_PRECOND_NONE;
+    label max_block_size = 1;
+    label bj_pattern_mbs = 0;    // block pointers were built for this maxBlockSize
+    bool have_precond = false;
+    double *d_inv_diag = nullptr;
+    label n_blocks = 0;
+    label *d_block_ptrs = nullptr, *d_row_block = nullptr;
+    int64_t *d_block_offs = nullptr;
+    double *d_inv_blocks = nullptr;
+    int64_t inv_blocks_len = 0;
+
+    // reduction scratch
+    double *d_partials = nullptr;          // kMaxPartialBlocks * kMaxReduce
+    unsigned int *d_ticket = nullptr;
+    SolveState *d_state = nullptr;
+    SolveState *h_state = nullptr;         // pinned: [0] final, [1..2] polling slots
+    double *d_history = nullptr;
+    int history_cap = 0;
+
+    // host staging for pageable uploads
+    void *h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+
+    // CUDA graph cache for one chunk of iterations
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_solver = -1;
+    int64_t graph_sig = 0;
+    int64_t graph_kernels = 0;   // kernels inside one replayed chunk
+
+    int64_t launches = 0;
+};
+
+// memory helpers ---------------------------------------------------------------
+template <typename T>
+int dev_alloc(Context *ctx, T **p, size_t count)
+{
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (count == 0) count = 1;
+    OGL_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T) + 64));
+    return OGL_OK;
+}
+
+int ensure_pinned(Context *ctx, size_t bytes);
+int upload(Context *ctx, void *dst, const void *src, size_t bytes);
+int download(Context *ctx, void *dst, const void *src, size_t bytes);
+int get_work(Context *ctx, int idx, double **out);
+
+// assembly.cu ------------------------------------------------------------------
+int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *lower,
+                     const label *upper, label n_if, const label *if_rows,
+                     const label *if_cols);
+int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells);
+int values_update(Context *ctx, const double *diag, const double *upper,
+                  const double *lower, const double *if_bou, const double *nl_bou,
+                  double scaling);
+
+// spmv.cu ------------------------------------------------------------------------
+// y = A_local x (optionally y = alpha*A*x + beta*y), optional fused partial
+// reduction red[0] = <dot_with, y_local_part> left in ctx->d_state->red[0].
+struct SpmvArgs {
+    const double *x = nullptr;
+    double *y = nullptr;
+    const double *y_in = nullptr;       // advanced: y = alpha*A*x + beta*y_in (default y)
+    bool advanced = false;
+    double alpha = 1.0, beta = 0.0;
+    const double *dot_with = nullptr;   // nred >= 1: red[0] = <dot_with, y>
+    int nred = 0;                       // nred == 2: red[1] = <y, y>
+    bool guard_done = false;            // early-exit when state->done
+    int epi = 0;                        // scalar epilogue after the reduction (reduce.cuh)
+    bool inline_epi = true;             // run it inside the kernel (single rank)
+};
+int spmv_local(Context *ctx, const SpmvArgs &a);
+int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
+                  const double *dot_with, int nred, bool guard_done, int epi,
+                  bool inline_epi);
+int spmv_setup(Context *ctx);
+
+// comm.cu ------------------------------------------------------------------------
+int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,
+                     const label *target_sizes, const label *send_idxs);
+int halo_begin(Context *ctx, const double *x);                    // pack + send/recv on comm stream
+int halo_end(Context *ctx);                                       // compute stream waits for recv
+int allreduce_red(Context *ctx, int count);                      // state->red[0..count) summed over ranks
+int dist_spmv(Context *ctx, const SpmvArgs &a);                   // halo + local + non-local
+
+// precond.cu ---------------------------------------------------------------------
+int precond_setup(Context *ctx, int kind, label mbs);
+int precond_apply(Context *ctx, const double *r, double *z, const double *dot_with,
+                  int red_base, bool guard_done, int epi, bool inline_epi);
+
+// solver.cu ----------------------------------------------------------------------
+int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res);
+int finish_reduction(Context *ctx, int count, int epi, bool guard);
+int vec_fill(Context *ctx, double *v, double value);
+int vec_scale(Context *ctx, double *v, double s);
+int init_state(Context *ctx, const ogl_solve_params *p);
+int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, double *w,
+                   double *tmp, int epi);
+
+}  // namespace ogl
+
+struct ogl_ctx : public ogl::Context {};

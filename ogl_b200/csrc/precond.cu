@@ -1,0 +1,304 @@
+// (Block-)Jacobi preconditioner on the LOCAL matrix block.
+//
+// Replaces Preconditioner::init_preconditioner_impl("BJ") + wrap_schwarz
+// (Preconditioner/Preconditioner.H:47-64, :91-105), i.e. Ginkgo
+// preconditioner::Jacobi generated on distributed::Matrix::get_local_matrix()
+// and wrapped in a non-overlapping Schwarz: no communication in the apply.
+//   max_block_size == 1 : jacobi::invert_diagonal + scalar_apply (z = r * 1/a_ii)
+//   max_block_size  > 1 : jacobi::find_blocks (natural blocks = consecutive
+//       rows with identical column pattern, then greedy agglomeration up to
+//       max_block_size), Gauss-Jordan inversion with column pivoting,
+//       apply = dense block mat-vec.
+#include <vector>
+
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace ogl {
+
+namespace {
+
+__global__ void k_invert_diagonal(label n, const label *__restrict__ row_ptrs,
+                                  const label *__restrict__ cols,
+                                  const double *__restrict__ vals, double *inv_diag)
+{
+    const label row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    double d = 0.0;
+    for (label q = row_ptrs[row]; q < row_ptrs[row + 1]; ++q) {
+        if (cols[q] == row) {
+            d = vals[q];
+            break;   // a duplicate (row,row) cyclic coupling sorts behind the diagonal
+        }
+    }
+    inv_diag[row] = 1.0 / d;
+}
+
+// flag[i] = 1 when rows i and i+1 have the same column pattern
+__global__ void k_same_pattern(label n, const label *__restrict__ row_ptrs,
+                               const label *__restrict__ cols, unsigned char *flag,
+                               int *any)
+{
+    const label i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const label a = row_ptrs[i], b = row_ptrs[i + 1], c = row_ptrs[i + 2];
+    unsigned char same = (b - a) == (c - b);
+    for (label k = 0; same && k < b - a; ++k) same = cols[a + k] == cols[b + k];
+    flag[i] = same;
+    if (same) atomicExch(any, 1);
+}
+
+// one thread per block: gather the dense diagonal block (row-major) and invert
+// it in place with Gauss-Jordan + column-max pivoting
+__global__ void k_generate_blocks(label n_blocks, const label *__restrict__ block_ptrs,
+                                  const int64_t *__restrict__ block_offs,
+                                  const label *__restrict__ row_ptrs,
+                                  const label *__restrict__ cols,
+                                  const double *__restrict__ vals, double *inv)
+{
+    const label b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const label lo = block_ptrs[b], hi = block_ptrs[b + 1], sz = hi - lo;
+    double *m = inv + block_offs[b];
+    for (label i = 0; i < sz * sz; ++i) m[i] = 0.0;
+    for (label i = lo; i < hi; ++i)
+        for (label q = row_ptrs[i]; q < row_ptrs[i + 1]; ++q) {
+            const label c = cols[q];
+            if (c >= lo && c < hi) m[(i - lo) * sz + (c - lo)] = vals[q];
+        }
+    label perm[32];
+    for (label i = 0; i < sz; ++i) perm[i] = i;
+    for (label k = 0; k < sz; ++k) {
+        label p = k;
+        double best = fabs(m[k * sz + k]);
+        for (label i = k + 1; i < sz; ++i) {
+            const double v = fabs(m[i * sz + k]);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        if (p != k) {
+            for (label j = 0; j < sz; ++j) {
+                const double t = m[k * sz + j];
+                m[k * sz + j] = m[p * sz + j];
+                m[p * sz + j] = t;
+            }
+            const label t = perm[k];
+            perm[k] = perm[p];
+            perm[p] = t;
+        }
+        const double d = m[k * sz + k];
+        for (label i = 0; i < sz; ++i) m[i * sz + k] = m[i * sz + k] / -d;
+        m[k * sz + k] = 0.0;
+        for (label i = 0; i < sz; ++i) {
+            const double f = m[i * sz + k];
+            for (label j = 0; j < sz; ++j)
+                if (j != k) m[i * sz + j] = __dadd_rn(m[i * sz + j], __dmul_rn(f, m[k * sz + j]));
+        }
+        for (label j = 0; j < sz; ++j) m[k * sz + j] = m[k * sz + j] / d;
+        m[k * sz + k] = 1.0 / d;
+    }
+    // undo the row permutation on the columns: column perm[k] <- column k
+    // (cycle-following would save the scratch; blocks are tiny)
+    double tmp[32];
+    for (label i = 0; i < sz; ++i) {
+        for (label k = 0; k < sz; ++k) tmp[k] = m[i * sz + k];
+        for (label k = 0; k < sz; ++k) m[i * sz + perm[k]] = tmp[k];
+    }
+}
+
+__global__ void k_row_block(label n_blocks, const label *__restrict__ block_ptrs,
+                            label *row_block)
+{
+    const label b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    for (label i = block_ptrs[b]; i < block_ptrs[b + 1]; ++i) row_block[i] = b;
+}
+
+struct ApplyK {
+    label n;
+    const double *r;
+    double *z;
+    const double *inv_diag;
+    const label *row_block, *block_ptrs;
+    const int64_t *block_offs;
+    const double *inv_blocks;
+    const double *dot_with;   // fused <dot_with, z>
+    double *partials;
+    unsigned int *ticket;
+    SolveState *state;
+    int red_base, epi, inline_epi, guard_done;
+    EpiArgs ea;
+};
+
+// z = M^-1 r, one thread per row.  KIND 1: scalar, 2: block.
+template <int KIND, int NRED>
+__global__ void __launch_bounds__(256) k_jacobi_apply(const ApplyK a)
+{
+    if (a.guard_done && a.state->done) return;
+    double red[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
+        double z;
+        if (KIND == 1) {
+            z = __dmul_rn(a.r[row], a.inv_diag[row]);   // jacobi::scalar_apply
+        } else {
+            const label b = a.row_block[row];
+            const label lo = a.block_ptrs[b], sz = a.block_ptrs[b + 1] - lo;
+            const double *m = a.inv_blocks + a.block_offs[b] + (int64_t)(row - lo) * sz;
+            z = 0.0;
+            for (label j = 0; j < sz; ++j) z = __dadd_rn(z, __dmul_rn(m[j], a.r[lo + j]));
+        }
+        a.z[row] = z;
+        if (NRED) red[0] += __dmul_rn(a.dot_with[row], z);
+    }
+    if (NRED)
+        grid_reduce<1>(red, a.partials, a.ticket, a.state, a.red_base, a.epi,
+                       a.inline_epi != 0, a.ea);
+}
+
+}  // namespace
+
+int precond_setup(Context *ctx, int kind, label mbs)
+{
+    if (!ctx->have_pattern || !ctx->have_values)
+        return fail(ctx, OGL_ERR_INVALID, "ogl_precond_setup before the matrix is assembled");
+    if (kind != OGL_PRECOND_NONE && kind != OGL_PRECOND_BJ)
+        return fail(ctx, OGL_ERR_UNSUPPORTED,
+                    "preconditioner not supported; valid choices: none, BJ");
+    if (mbs < 1) mbs = 1;
+    if (mbs > 32) return fail(ctx, OGL_ERR_INVALID, "maxBlockSize must be in [1, 32]");
+    ctx->precond_kind = kind;
+    ctx->max_block_size = mbs;
+    ctx->have_precond = true;
+    if (kind == OGL_PRECOND_NONE || ctx->n == 0) return OGL_OK;
+    cudaStream_t st = ctx->stream;
+    const label n = ctx->n;
+    if (mbs == 1) {
+        if (!ctx->d_inv_diag) OGL_TRY(dev_alloc(ctx, &ctx->d_inv_diag, n));
+        k_invert_diagonal<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->d_row_ptrs, ctx->d_cols,
+                                                         ctx->d_vals, ctx->d_inv_diag);
+        ctx->launches++;
+        OGL_CUDA(ctx, cudaGetLastError());
+        return OGL_OK;
+    }
+    // --- block pointers (structure only; cached while the pattern lives) ---
+    if (!ctx->d_block_ptrs || ctx->n_blocks == 0 || ctx->bj_pattern_mbs != mbs) {
+        unsigned char *d_flag = nullptr;
+        int *d_any = nullptr;
+        OGL_TRY(dev_alloc(ctx, &d_flag, n));
+        OGL_TRY(dev_alloc(ctx, &d_any, 1));
+        cudaMemsetAsync(d_flag, 0, n, st);
+        cudaMemsetAsync(d_any, 0, sizeof(int), st);
+        k_same_pattern<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->d_row_ptrs, ctx->d_cols, d_flag,
+                                                      d_any);
+        int any = 0;
+        cudaMemcpyAsync(&any, d_any, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        std::vector<unsigned char> flag;
+        if (any) {
+            flag.resize(n);
+            cudaMemcpy(flag.data(), d_flag, n, cudaMemcpyDeviceToHost);
+        }
+        cudaFree(d_flag);
+        cudaFree(d_any);
+        // Ginkgo find_natural_blocks + agglomerate_supervariables (sequential by nature)
+        std::vector<label> nat;
+        nat.reserve(n + 1);
+        nat.push_back(0);
+        label cur = 1;
+        for (label i = 0; i + 1 < n; ++i) {
+            if (any && flag[i] && cur < mbs) {
+                ++cur;
+            } else {
+                nat.push_back(nat.back() + cur);
+                cur = 1;
+            }
+        }
+        nat.push_back(nat.back() + cur);
+        std::vector<label> bp;
+        bp.reserve(n / mbs + 2);
+        bp.push_back(0);
+        cur = nat[1] - nat[0];
+        for (size_t i = 1; i + 1 < nat.size(); ++i) {
+            const label bs = nat[i + 1] - nat[i];
+            if (cur + bs <= mbs) {
+                cur += bs;
+            } else {
+                bp.push_back(bp.back() + cur);
+                cur = bs;
+            }
+        }
+        bp.push_back(bp.back() + cur);
+        const label nb = (label)bp.size() - 1;
+        std::vector<int64_t> offs(nb + 1, 0);
+        for (label b = 0; b < nb; ++b) {
+            const int64_t sz = bp[b + 1] - bp[b];
+            offs[b + 1] = offs[b] + sz * sz;
+        }
+        ctx->n_blocks = nb;
+        ctx->inv_blocks_len = offs[nb];
+        ctx->bj_pattern_mbs = mbs;
+        OGL_TRY(dev_alloc(ctx, &ctx->d_block_ptrs, (size_t)nb + 1));
+        OGL_TRY(dev_alloc(ctx, &ctx->d_block_offs, (size_t)nb + 1));
+        OGL_TRY(dev_alloc(ctx, &ctx->d_row_block, n));
+        OGL_TRY(dev_alloc(ctx, &ctx->d_inv_blocks, (size_t)offs[nb]));
+        OGL_CUDA(ctx, cudaMemcpy(ctx->d_block_ptrs, bp.data(), sizeof(label) * (nb + 1),
+                                 cudaMemcpyHostToDevice));
+        OGL_CUDA(ctx, cudaMemcpy(ctx->d_block_offs, offs.data(), sizeof(int64_t) * (nb + 1),
+                                 cudaMemcpyHostToDevice));
+        k_row_block<<<(nb + 255) / 256, 256, 0, st>>>(nb, ctx->d_block_ptrs, ctx->d_row_block);
+        ctx->launches++;
+    }
+    k_generate_blocks<<<(ctx->n_blocks + 127) / 128, 128, 0, st>>>(
+        ctx->n_blocks, ctx->d_block_ptrs, ctx->d_block_offs, ctx->d_row_ptrs, ctx->d_cols,
+        ctx->d_vals, ctx->d_inv_blocks);
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    return OGL_OK;
+}
+
+int precond_apply(Context *ctx, const double *r, double *z, const double *dot_with,
+                  int red_base, bool guard_done, int epi, bool inline_epi)
+{
+    if (ctx->precond_kind == OGL_PRECOND_NONE || ctx->n == 0) {
+        if (r != z)
+            OGL_CUDA(ctx, cudaMemcpyAsync(z, r, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice,
+                                          ctx->stream));
+        return OGL_OK;
+    }
+    ApplyK a;
+    a.n = ctx->n;
+    a.r = r;
+    a.z = z;
+    a.inv_diag = ctx->d_inv_diag;
+    a.row_block = ctx->d_row_block;
+    a.block_ptrs = ctx->d_block_ptrs;
+    a.block_offs = ctx->d_block_offs;
+    a.inv_blocks = ctx->d_inv_blocks;
+    a.dot_with = dot_with;
+    a.partials = ctx->d_partials;
+    a.ticket = ctx->d_ticket;
+    a.state = ctx->d_state;
+    a.red_base = red_base;
+    a.epi = epi;
+    a.inline_epi = inline_epi ? 1 : 0;
+    a.guard_done = guard_done ? 1 : 0;
+    a.ea = make_epi_args(ctx);
+    int grid = (ctx->n + 255) / 256;
+    if (grid > ctx->blas1_blocks) grid = (int)ctx->blas1_blocks;
+    const bool scalar = ctx->max_block_size == 1;
+    if (dot_with) {
+        if (scalar) k_jacobi_apply<1, 1><<<grid, 256, 0, ctx->stream>>>(a);
+        else k_jacobi_apply<2, 1><<<grid, 256, 0, ctx->stream>>>(a);
+    } else {
+        if (scalar) k_jacobi_apply<1, 0><<<grid, 256, 0, ctx->stream>>>(a);
+        else k_jacobi_apply<2, 0><<<grid, 256, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    return OGL_OK;
+}
+
+}  // namespace ogl

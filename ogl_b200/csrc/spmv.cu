@@ -1,0 +1,373 @@
+// FP64 CSR SpMV for sm_100a, optionally fused with the reductions the Krylov
+// step needs next (a20, kernel table row "Coo/Csr::apply").
+//
+// The path is HBM-bound: 12 B per stored entry (8 B value + 4 B column) plus
+// 4 B row pointer and two 8 B vector elements per row; x is re-read ~7x per row
+// on hex meshes but from L1/L2.  Tensor cores are irrelevant (0.17 flop/B).
+//
+// Variants (chosen in spmv_setup from the row-length statistics, or forced
+// with ogl_set_option("spmv_variant")):
+//   1 "stream"  kRowsPerBlock rows per CTA.  The CTA's contiguous slice of
+//               values/columns is streamed with fully coalesced loads
+//               (evict-first), each entry multiplied with its gathered x
+//               (read-only path, L1/L2 hits) and parked in shared memory; then
+//               one thread per row adds its products left to right.  Sum
+//               order == storage order, products rounded before the add
+//               (__dmul_rn/__dadd_rn), i.e. bit-identical to the sequential
+//               reference-executor kernel.  For short, regular rows (FV meshes).
+//   2 "scalar"  one thread per row, same arithmetic order; no shared memory.
+//   3 "vector"  one warp per row (long / irregular rows); lane-strided partial
+//               sums + shuffle reduction (not bit-identical, deterministic).
+//   4 "tma"     persistent CTAs, slices staged by cp.async.bulk (TMA) into a
+//               multi-stage shared-memory ring guarded by mbarriers.
+//
+// Fused reductions (NRED): red[0] = <dot_with, y>, red[1] = <y, y>; reduced
+// deterministically (reduce.cuh) and, on one rank, followed in the same launch
+// by the scalar epilogue (e.g. CG: beta = <p,q>, alpha = rho / beta).
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace ogl {
+
+constexpr int kRowsPerBlock = 256;
+constexpr int kStreamThreads = 256;
+constexpr int kStreamSmemMax = 96 * 1024;
+
+struct SpmvK {
+    const label *row_ptrs;
+    const label *cols;
+    const double *vals;
+    const double *x;
+    const double *y_in;   // advanced: y = alpha*A*x + beta*y_in
+    double *y;
+    label n;
+    double alpha, beta;
+    const double *dot_with;
+    double *partials;
+    unsigned int *ticket;
+    SolveState *state;
+    int epi, inline_epi, guard_done;
+    EpiArgs ea;
+};
+
+namespace {
+
+__device__ __forceinline__ double prod_of(double v, double xv, double alpha, bool adv)
+{
+    // reference kernels: `alpha * val * b` (advanced) or `val * b`
+    return adv ? __dmul_rn(__dmul_rn(alpha, v), xv) : __dmul_rn(v, xv);
+}
+
+template <bool ADV, int NRED>
+__global__ void __launch_bounds__(kStreamThreads)
+k_spmv_stream(const SpmvK a)
+{
+    if (a.guard_done && a.state->done) return;
+    extern __shared__ double prod[];
+    const int tid = threadIdx.x;
+    const label r0 = blockIdx.x * kRowsPerBlock;
+    const label nr = min((label)kRowsPerBlock, a.n - r0);
+    const label s = __ldg(&a.row_ptrs[r0]);
+    const label e = __ldg(&a.row_ptrs[r0 + nr]);
+    // row extents of "my" row: issued early, consumed after the barrier
+    label rs = 0, re = 0;
+    if (tid < nr) {
+        rs = __ldg(&a.row_ptrs[r0 + tid]);
+        re = __ldg(&a.row_ptrs[r0 + tid + 1]);
+    }
+    // ---- stream the slice: coalesced value/column loads, gathered x
+    label k = s + tid;
+    for (; k + 3 * kStreamThreads < e; k += 4 * kStreamThreads) {
+        label c[4];
+        double v[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = __ldcs(&a.cols[k + u * kStreamThreads]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(&a.vals[k + u * kStreamThreads]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = __ldg(&a.x[c[u]]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            prod[k - s + u * kStreamThreads] = prod_of(v[u], xv[u], a.alpha, ADV);
+    }
+    for (; k < e; k += kStreamThreads) {
+        const label c = __ldcs(&a.cols[k]);
+        const double v = __ldcs(&a.vals[k]);
+        prod[k - s] = prod_of(v, __ldg(&a.x[c]), a.alpha, ADV);
+    }
+    __syncthreads();
+    // ---- one thread per row: left-to-right sum of its products
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    if (tid < nr) {
+        const label row = r0 + tid;
+        double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+        for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
+        a.y[row] = sum;
+        if (NRED >= 1) red[0] = __dmul_rn(a.dot_with[row], sum);
+        if (NRED >= 2) red[1] = __dmul_rn(sum, sum);
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
+template <bool ADV, int NRED>
+__global__ void __launch_bounds__(256) k_spmv_scalar(const SpmvK a)
+{
+    if (a.guard_done && a.state->done) return;
+    const label row = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    if (row < a.n) {
+        const label rs = __ldg(&a.row_ptrs[row]), re = __ldg(&a.row_ptrs[row + 1]);
+        double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+        for (label q = rs; q < re; ++q)
+            sum = __dadd_rn(sum, prod_of(__ldcs(&a.vals[q]), __ldg(&a.x[__ldcs(&a.cols[q])]),
+                                         a.alpha, ADV));
+        a.y[row] = sum;
+        if (NRED >= 1) red[0] = __dmul_rn(a.dot_with[row], sum);
+        if (NRED >= 2) red[1] = __dmul_rn(sum, sum);
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
+template <bool ADV, int NRED>
+__global__ void __launch_bounds__(256) k_spmv_vector(const SpmvK a)
+{
+    if (a.guard_done && a.state->done) return;
+    const int lane = threadIdx.x & 31;
+    const label row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    if (row < a.n) {
+        const label rs = __ldg(&a.row_ptrs[row]), re = __ldg(&a.row_ptrs[row + 1]);
+        double sum = 0.0;
+        for (label q = rs + lane; q < re; q += 32)
+            sum = __dadd_rn(sum, prod_of(__ldcs(&a.vals[q]), __ldg(&a.x[__ldcs(&a.cols[q])]),
+                                         a.alpha, ADV));
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            if (ADV) sum = __dadd_rn(__dmul_rn(a.beta, a.y_in[row]), sum);
+            a.y[row] = sum;
+            if (NRED >= 1) red[0] = __dmul_rn(a.dot_with[row], sum);
+            if (NRED >= 2) red[1] = __dmul_rn(sum, sum);
+        }
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
+// y[row] += alpha * A_nl[row, :] * recv for the rows that touch the halo
+// (distributed::Matrix::apply: non_local_mtx->apply(alpha, recv, one, y)), one
+// thread per such row, entries added one at a time in storage order.  With
+// fused reductions the kernel adds the CHANGE of <d,y> and <y,y> caused by the
+// halo terms on top of the local kernel's sums.
+struct NonLocalK {
+    label n_rows;
+    const label *row_ids, *row_ptrs, *cols;
+    const double *vals, *recv;
+    double *y;
+    double alpha;
+    const double *dot_with;
+    double *partials;
+    unsigned int *ticket;
+    SolveState *state;
+    int epi, inline_epi, guard_done;
+    EpiArgs ea;
+};
+
+template <int NRED>
+__global__ void __launch_bounds__(256) k_spmv_nonlocal(const NonLocalK a)
+{
+    if (a.guard_done && a.state->done) return;
+    const label u = blockIdx.x * blockDim.x + threadIdx.x;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    if (u < a.n_rows) {
+        const label row = a.row_ids[u];
+        const double y_old = a.y[row];
+        double acc = y_old;
+        for (label q = a.row_ptrs[u]; q < a.row_ptrs[u + 1]; ++q)
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(a.alpha, a.vals[q]), a.recv[a.cols[q]]));
+        a.y[row] = acc;
+        if (NRED >= 1) {
+            const double d = a.dot_with[row];
+            red[0] = __dmul_rn(d, acc) - __dmul_rn(d, y_old);
+        }
+        if (NRED >= 2) red[1] = __dmul_rn(acc, acc) - __dmul_rn(y_old, y_old);
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea, /*accumulate=*/true);
+}
+
+__global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int *out)
+{
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t r0 = b * kRowsPerBlock;
+    if (r0 < n) {
+        const int64_t r1 = r0 + kRowsPerBlock < n ? r0 + kRowsPerBlock : n;
+        atomicMax(out, row_ptrs[r1] - row_ptrs[r0]);
+    }
+}
+
+template <typename K, typename A>
+void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const A &args)
+{
+    kernel<<<grid, block, smem, st>>>(args);
+}
+
+}  // namespace
+
+EpiArgs make_epi_args(Context *ctx)
+{
+    EpiArgs ea;
+    ea.inv_n_local = ctx->n > 0 ? 1.0 / (double)ctx->n : 0.0;
+    const double g = (double)(ctx->global_n > 0 ? ctx->global_n : ctx->n);
+    ea.weight = g > 0 ? (double)ctx->n / g : 0.0;
+    ea.history = ctx->d_history;
+    return ea;
+}
+
+int spmv_setup(Context *ctx)
+{
+    // largest slice any kRowsPerBlock-row CTA would have to park in shared memory
+    int *d_max = nullptr;
+    OGL_CUDA(ctx, cudaMalloc(&d_max, sizeof(int)));
+    cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream);
+    const int64_t nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
+    if (nblk > 0)
+        k_block_nnz_max<<<(int)((nblk + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->n, ctx->d_row_ptrs, d_max);
+    int mx = 0;
+    cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_max);
+    if (e != cudaSuccess)
+        return fail(ctx, OGL_ERR_CUDA, std::string("spmv_setup: ") + cudaGetErrorString(e));
+    ctx->max_block_nnz = mx;
+    // reduction scratch sized for the largest grid any kernel of the library uses
+    int64_t max_grid = nblk;
+    const int64_t vec_grid = ((int64_t)ctx->n * 32 + 255) / 256;
+    if (vec_grid > max_grid) max_grid = vec_grid;
+    if (ctx->blas1_blocks > max_grid) max_grid = ctx->blas1_blocks;
+    OGL_TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)(max_grid + 1) * kMaxReduce));
+    return OGL_OK;
+}
+
+static int pick_variant(const Context *ctx)
+{
+    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 3) return (int)ctx->spmv_variant;
+    const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
+    const double mean_len = ctx->n > 0 ? (double)ctx->nnz / ctx->n : 0.0;
+    // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
+    if (smem <= (size_t)kStreamSmemMax && mean_len <= 48.0) return 1;
+    return mean_len >= 16.0 ? 3 : 2;
+}
+
+int spmv_local(Context *ctx, const SpmvArgs &sa)
+{
+    if (!ctx->have_pattern || !ctx->have_values)
+        return fail(ctx, OGL_ERR_INVALID, "SpMV without assembled matrix");
+    if (ctx->n == 0) return OGL_OK;
+    SpmvK k;
+    k.row_ptrs = ctx->d_row_ptrs;
+    k.cols = ctx->d_cols;
+    k.vals = ctx->d_vals;
+    k.x = sa.x;
+    k.y_in = sa.y_in ? sa.y_in : sa.y;
+    k.y = sa.y;
+    k.n = ctx->n;
+    k.alpha = sa.alpha;
+    k.beta = sa.beta;
+    k.dot_with = sa.dot_with;
+    k.partials = ctx->d_partials;
+    k.ticket = ctx->d_ticket;
+    k.state = ctx->d_state;
+    k.epi = sa.epi;
+    k.inline_epi = sa.inline_epi ? 1 : 0;
+    k.guard_done = sa.guard_done ? 1 : 0;
+    k.ea = make_epi_args(ctx);
+    const int nred = sa.nred;
+    if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
+    const int variant = pick_variant(ctx);
+    cudaStream_t st = ctx->stream;
+#define DISPATCH(KERNEL, GRID, BLOCK, SMEM)                                              \
+    do {                                                                                 \
+        if (sa.advanced) {                                                               \
+            if (nred == 0) KERNEL<true, 0><<<GRID, BLOCK, SMEM, st>>>(k);                \
+            else if (nred == 1) KERNEL<true, 1><<<GRID, BLOCK, SMEM, st>>>(k);           \
+            else KERNEL<true, 2><<<GRID, BLOCK, SMEM, st>>>(k);                          \
+        } else {                                                                         \
+            if (nred == 0) KERNEL<false, 0><<<GRID, BLOCK, SMEM, st>>>(k);               \
+            else if (nred == 1) KERNEL<false, 1><<<GRID, BLOCK, SMEM, st>>>(k);          \
+            else KERNEL<false, 2><<<GRID, BLOCK, SMEM, st>>>(k);                         \
+        }                                                                                \
+    } while (0)
+    if (variant == 1) {
+        const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_spmv_stream<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_stream<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_stream<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_stream<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_stream<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_stream<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            attr_set = true;
+        }
+        const int grid = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
+        DISPATCH(k_spmv_stream, grid, kStreamThreads, smem);
+    } else if (variant == 2) {
+        const int grid = (ctx->n + 255) / 256;
+        DISPATCH(k_spmv_scalar, grid, 256, 0);
+    } else {
+        const int grid = (int)(((int64_t)ctx->n * 32 + 255) / 256);
+        DISPATCH(k_spmv_vector, grid, 256, 0);
+    }
+#undef DISPATCH
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    return OGL_OK;
+}
+
+int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
+                  const double *dot_with, int nred, bool guard_done, int epi,
+                  bool inline_epi)
+{
+    if (ctx->n_nl_rows == 0) return OGL_OK;
+    NonLocalK k;
+    k.n_rows = ctx->n_nl_rows;
+    k.row_ids = ctx->d_nl_row_ids;
+    k.row_ptrs = ctx->d_nl_row_ptrs;
+    k.cols = ctx->d_nl_cols;
+    k.vals = ctx->d_nl_vals;
+    k.recv = recv;
+    k.y = y;
+    k.alpha = alpha;
+    k.dot_with = dot_with;
+    k.partials = ctx->d_partials;
+    k.ticket = ctx->d_ticket;
+    k.state = ctx->d_state;
+    k.epi = epi;
+    k.inline_epi = inline_epi ? 1 : 0;
+    k.guard_done = guard_done ? 1 : 0;
+    k.ea = make_epi_args(ctx);
+    const int grid = (ctx->n_nl_rows + 255) / 256;
+    if (nred == 0) k_spmv_nonlocal<0><<<grid, 256, 0, ctx->stream>>>(k);
+    else if (nred == 1) k_spmv_nonlocal<1><<<grid, 256, 0, ctx->stream>>>(k);
+    else k_spmv_nonlocal<2><<<grid, 256, 0, ctx->stream>>>(k);
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    return OGL_OK;
+}
+
+}  // namespace ogl

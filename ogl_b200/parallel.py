@@ -1,0 +1,67 @@
+"""Rank bootstrap: one process per GPU, `torch.distributed` for the rendezvous
+(the role MPI_COMM_WORLD / Pstream play in the reference,
+DevicePersistent/ExecutorHandler/ExecutorHandler.H:29-33,140-144), NCCL inside
+libogl_b200.so for the data path."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+
+@dataclass
+class Pstream:
+    """Pstream::parRun()/myProcNo()/nProcs() analogue."""
+    rank: int = 0
+    n_ranks: int = 1
+    local_rank: int = 0
+    nccl_id: Optional[bytes] = None
+
+    @property
+    def par_run(self) -> bool:
+        return self.n_ranks > 1
+
+    @property
+    def master(self) -> bool:
+        return self.rank == 0
+
+
+def init_from_env(backend: Optional[str] = None) -> Pstream:
+    """Join the job described by RANK/WORLD_SIZE/LOCAL_RANK/MASTER_* (torchrun)
+    and agree on an NCCL unique id for the solver library."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world == 1:
+        return Pstream(0, 1, local, None)
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return Pstream(rank, world, local, broadcast_nccl_id(rank))
+
+
+def broadcast_nccl_id(rank: int) -> bytes:
+    """Rank 0 creates the id (ogl_nccl_unique_id), everyone receives it."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib as L
+
+    n = L.OGL_NCCL_ID_BYTES
+    if rank == 0:
+        from .backend import nccl_unique_id
+        payload = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8)
+    else:
+        payload = torch.zeros(n, dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        payload = payload.cuda()
+    dist.broadcast(payload, src=0)
+    return bytes(payload.cpu().tolist())

@@ -405,7 +405,10 @@ struct Criterion {
             init_res = rn / norm_factor;
         }
         rn /= norm_factor;                     // :113
-        if (history && n_history < history_cap) history[n_history++] = rn;
+        if (history && iter < history_cap) {   // :115-117 residual_norms->at(iter)
+            history[iter] = rn;
+            n_history = iter + 1;
+        }
         res = rn;                              // :119
         if (iter >= p.max_iter) stop = true;   // :124-126
         if (rn < p.tolerance) stop = true;     // :128-130

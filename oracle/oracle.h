@@ -164,8 +164,9 @@ typedef struct orc_solve_result {
 void orc_dist_spmv(int n_ranks, const orc_rank_system *ranks,
                    const orc_scalar *const *xs, orc_scalar *const *ys);
 
-/* Solve; returns 0 on success.  history (may be NULL) receives the normalised
- * residual of every evaluated criterion call, capacity history_cap. */
+/* Solve; returns 0 on success.  history (may be NULL, zero-initialised by the
+ * caller) receives the normalised residual indexed by criterion call
+ * (StoppingCriterion.C:115-117); skipped calls stay 0. */
 int orc_solve(int n_ranks, const orc_rank_system *ranks,
               const orc_solve_params *params, orc_solve_result *result,
               orc_scalar *history, orc_label history_cap);

@@ -1,0 +1,216 @@
+"""-m gpu: Krylov solves through the C ABI against the oracle on the same
+assembled systems.  Bars (BASELINE.json north_star): same tolerance reached,
+iteration count within +-2, solution relative L2 difference <= 1e-8."""
+import numpy as np
+import pytest
+
+from gpu_helpers import gpu_solve, rel_l2, upload_system
+from ogl_b200 import _lib as L
+from ogl_b200 import cases
+from ogl_b200.backend import Context, OglError
+from ogl_b200.host import FatalError, ObjectRegistry
+from ogl_b200.plugin import lduMatrix_solver_New
+
+pytestmark = pytest.mark.gpu
+
+ITER_TOL = 2          # iterations
+L2_TOL = 1e-8         # relative L2 difference of the solutions
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = Context()
+    yield c
+    c.close()
+
+
+def check_against_oracle(ctx, oracle, s, solver, precond, mbs=1, **kw):
+    upload_system(ctx, s, partition=False)
+    r, x = gpu_solve(ctx, solver, precond, mbs, **dict(kw))
+    a = oracle.assemble(s)
+    okw = dict(kw)
+    o = oracle.solve([a], solver, precond, max_block_size=mbs, **okw)
+    assert abs(r.n_iterations - o.n_iterations) <= ITER_TOL, (r.n_iterations, o.n_iterations)
+    assert rel_l2(x, o.x[0]) <= L2_TOL
+    assert r.init_residual == pytest.approx(o.init_residual, rel=1e-10)
+    assert r.norm_factor == pytest.approx(o.norm_factor, rel=1e-12)
+    tol = kw.get("tolerance", 1e-6)
+    if r.criterion_calls <= kw.get("max_iter", 1000):
+        assert r.final_residual < max(tol, kw.get("rel_tol", 0.0) * r.init_residual)
+    return r, o, x
+
+
+@pytest.mark.parametrize("precond,mbs", [("none", 1), ("BJ", 1), ("BJ", 2), ("BJ", 8)])
+def test_cg_pressure(ctx, oracle, precond, mbs):
+    s = cases.pressure_3d(24)[0]
+    r, o, x = check_against_oracle(ctx, oracle, s, "GKOCG", precond, mbs, tolerance=1e-8)
+    assert r.kernel_launches > 0
+
+
+def test_cg_spd_sign_and_reltol(ctx, oracle):
+    s = cases.pressure_3d(20, sign=-1.0)[0]
+    check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", tolerance=1e-30, rel_tol=1e-3)
+
+
+@pytest.mark.parametrize("precond,mbs", [("none", 1), ("BJ", 1), ("BJ", 4)])
+def test_bicgstab_momentum(ctx, oracle, precond, mbs):
+    s = cases.momentum_3d(20)[0]
+    r, o, x = check_against_oracle(ctx, oracle, s, "GKOBiCGStab", precond, mbs, tolerance=1e-9)
+    assert abs(r.criterion_calls - o.criterion_calls) <= 2 * ITER_TOL
+
+
+def test_bicgstab_on_symmetric_matrix(ctx, oracle):
+    s = cases.pressure_3d(16)[0]
+    check_against_oracle(ctx, oracle, s, "GKOBiCGStab", "BJ", tolerance=1e-8)
+
+
+@pytest.mark.parametrize("precond,mbs,kdim", [("none", 1, 30), ("BJ", 1, 30), ("BJ", 4, 100)])
+def test_gmres(ctx, oracle, precond, mbs, kdim):
+    s = cases.momentum_3d(14)[0]
+    r, o, x = check_against_oracle(ctx, oracle, s, "GKOGMRES", precond, mbs, tolerance=1e-8,
+                                   krylov_dim=kdim)
+    # restart-residual semantics are reproduced exactly
+    assert r.criterion_calls == o.criterion_calls
+
+
+def test_gmres_channel_cyclic(ctx, oracle):
+    s = cases.channel((16, 8, 8), (1, 1, 1))[0]
+    check_against_oracle(ctx, oracle, s, "GKOGMRES", "BJ", tolerance=1e-7, krylov_dim=20)
+
+
+def test_criterion_options(ctx, oracle):
+    s = cases.pressure_3d(16)[0]
+    for kw in (dict(tolerance=1e-7, frequency=5), dict(tolerance=1e-7, min_iter=80),
+               dict(tolerance=1e-30, max_iter=9), dict(tolerance=1e-7, frequency=3, min_iter=20)):
+        r, o, _ = check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", **kw)
+        if "max_iter" in kw or "min_iter" in kw and "frequency" not in kw:
+            assert r.criterion_calls == o.criterion_calls
+
+
+def test_residual_history(ctx, oracle):
+    s = cases.pressure_3d(16)[0]
+    upload_system(ctx, s, partition=False)
+    r, x = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-7, export_res=True)
+    h = ctx.residual_history(2000)
+    o = oracle.solve([oracle.assemble(s)], "GKOCG", "BJ", tolerance=1e-7)
+    m = min(h.size, o.history.size)
+    assert m >= 10 and h[0] == pytest.approx(1.0, rel=1e-12)
+    assert np.allclose(h[:m - 2], o.history[:m - 2], rtol=1e-6)
+
+
+def test_block_jacobi_inverse_bit_exact(ctx, oracle):
+    s = cases.momentum_3d(10)[0]
+    upload_system(ctx, s, partition=False)
+    a = oracle.assemble(s)
+    for mbs in (1, 3, 16):
+        ctx.precond_setup(L.OGL_PRECOND_BJ, mbs)
+        bp, inv = ctx.precond_download()
+        if mbs == 1:
+            diag = a.vals[a.rows == a.cols]
+            assert np.array_equal(inv, 1.0 / diag)
+        else:
+            obp, oinv = oracle.bj_blocks(a.n, a.row_ptrs, a.cols, a.vals, mbs)
+            assert np.array_equal(bp, obp)
+            assert np.array_equal(inv, oinv)
+
+
+def test_determinism_run_to_run(ctx):
+    s = cases.pressure_3d(32)[0]
+    upload_system(ctx, s, partition=False)
+    outs = []
+    for _ in range(3):
+        ctx.vector_upload(L.OGL_VEC_X, s.psi)
+        r, x = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-9)
+        outs.append((r.n_iterations, r.final_residual, x.copy()))
+    assert outs[0][0] == outs[1][0] == outs[2][0]
+    assert outs[0][1] == outs[1][1] == outs[2][1]
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][2], outs[2][2])
+
+
+def test_graph_and_stream_paths_agree(ctx):
+    s = cases.pressure_3d(24)[0]
+    upload_system(ctx, s, partition=False)
+    res = []
+    for use_graph, chunk in ((1, 16), (0, 16), (1, 3), (0, 1)):
+        ctx.set_option("use_graph", use_graph)
+        ctx.set_option("chunk_iters", chunk)
+        ctx.vector_upload(L.OGL_VEC_X, s.psi)
+        r, x = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-9)
+        res.append((r.n_iterations, x.copy()))
+    ctx.set_option("use_graph", 1)
+    ctx.set_option("chunk_iters", 16)
+    for n_it, x in res[1:]:
+        assert n_it == res[0][0] and np.array_equal(x, res[0][1])
+
+
+def test_full_size_pressure_solve_properties(ctx):
+    # BASELINE configs[1]: 100^3 GKOCG + BJ; oracle-free properties at full size
+    s = cases.pressure_3d(100)[0]
+    upload_system(ctx, s, partition=False)
+    r, x = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-6)
+    assert 0 < r.n_iterations < 1000
+    true_res = np.abs(ctx.spmv(x) - s.source).sum() / r.norm_factor
+    assert true_res == pytest.approx(r.final_residual, rel=1e-6)
+    assert true_res < 1e-6
+    assert r.init_residual == pytest.approx(1.0, rel=1e-12)     # x0 = 0
+    # a tighter solve recovers the manufactured solution
+    ctx.vector_upload(L.OGL_VEC_X, s.psi)
+    r2, x2 = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-12, max_iter=3000)
+    assert rel_l2(x2, s.x_star) < 1e-6
+
+
+def test_plugin_surface_time_steps(oracle):
+    """lduMatrix::solver::New + solve() with the fvSolution keywords; two "time
+    steps" exercising the cached structure / updateInitGuess semantics."""
+    db = ObjectRegistry()
+    controls = {"solver": "GKOCG", "preconditioner": "BJ", "executor": "cuda",
+                "tolerance": 1e-8, "relTol": 0.0, "adaptMinIter": False}
+    s = cases.pressure_3d(20)[0]
+    solver = lduMatrix_solver_New("p", s, controls, db)
+    psi = s.psi.copy()
+    perf = solver.solve(psi, s.source)
+    assert perf.solver_name == "BJcudaGKOCG" and perf.field_name == "p"
+    o = oracle.solve([oracle.assemble(s)], "GKOCG", "BJ", tolerance=1e-8)
+    assert abs(perf.n_iterations - o.n_iterations) <= ITER_TOL
+    assert rel_l2(psi, o.x[0]) <= L2_TOL
+    # second step: new rhs, initial guess = previous DEVICE solution (updateInitGuess false),
+    # whatever psi the caller passes (lduLduBase.H:228-237)
+    solver2 = lduMatrix_solver_New("p", s, controls, db)
+    assert solver2.ctx is solver.ctx
+    psi2 = np.full(s.n, 123.0)
+    perf2 = solver2.solve(psi2, 1.5 * s.source)
+    a = oracle.assemble(s)
+    a.b = 1.5 * a.b
+    a.x = o.x[0].copy()
+    o2 = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-8)
+    assert abs(perf2.n_iterations - o2.n_iterations) <= ITER_TOL
+    assert rel_l2(psi2, o2.x[0]) <= L2_TOL
+    # selection table: GKOCG is registered for symmetric matrices only (GKOCG.C:16-17)
+    with pytest.raises(FatalError):
+        lduMatrix_solver_New("U", cases.momentum_3d(6)[0], controls, ObjectRegistry())
+    with pytest.raises(FatalError):
+        lduMatrix_solver_New("p", s, dict(controls, executor="omp"), ObjectRegistry())
+    with pytest.raises(FatalError):
+        lduMatrix_solver_New("p", s, dict(controls, preconditioner="ILU"), ObjectRegistry())
+
+
+def test_scaling_keyword(oracle):
+    # scaling -1 turns the negative-definite pressure matrix into an SPD one (README.md:101)
+    db = ObjectRegistry()
+    controls = {"solver": "GKOCG", "preconditioner": "BJ", "executor": "cuda",
+                "tolerance": 1e-8, "relTol": 0.0, "adaptMinIter": False, "scaling": -1.0}
+    s = cases.pressure_3d(16)[0]
+    solver = lduMatrix_solver_New("p", s, controls, db)
+    psi = s.psi.copy()
+    solver.solve(psi, s.source)
+    v, _ = solver.ctx.values_download()
+    assert v[0] > 0       # diagonal flipped positive
+    o = oracle.solve([oracle.assemble(s, scaling=-1.0)], "GKOCG", "BJ", tolerance=1e-8)
+    assert rel_l2(psi, o.x[0]) <= L2_TOL
+
+
+def test_solve_call_order_errors(ctx):
+    s = cases.pressure_3d(8)[0]
+    ctx.pattern_from_ldu(s.n, s.lower_addr, s.upper_addr, True)
+    with pytest.raises(OglError):
+        ctx.solve(L.OGL_SOLVER_CG)          # no values / vectors yet

@@ -1,0 +1,87 @@
+"""-m gpu: FP64 CSR SpMV kernels against the oracle (bit-exact where the
+summation order is the reference's) and size-independent properties at the
+BASELINE size."""
+import numpy as np
+import pytest
+
+from gpu_helpers import upload_system
+from ogl_b200 import cases
+from ogl_b200.backend import Context
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = Context()
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("builder", [lambda: cases.pressure_3d(20)[0], lambda: cases.momentum_3d(17)[0],
+                                     lambda: cases.channel((16, 8, 8), (1, 1, 1))[0],
+                                     lambda: cases.cavity_2d((1, 1, 1))[0]])
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_spmv_vs_oracle(ctx, oracle, builder, variant):
+    s = builder()
+    upload_system(ctx, s, partition=False)
+    ctx.set_option("spmv_variant", variant)
+    a = oracle.assemble(s)
+    x = np.random.default_rng(3).normal(size=s.n)
+    y = ctx.spmv(x)
+    y_ref = oracle.dist_spmv([a], [x])[0]
+    if variant in (1, 2):
+        # same left-to-right row sums, products rounded before the add: bit-exact
+        assert np.array_equal(y, y_ref)
+    else:
+        assert np.allclose(y, y_ref, rtol=1e-13, atol=1e-13 * np.abs(y_ref).max())
+    ctx.set_option("spmv_variant", 0)
+
+
+def test_spmv_long_rows_fall_back_to_vector_kernel(ctx, oracle):
+    # an "arrow" matrix: row 0 couples to everything (row length n)
+    n = 3000
+    lower = np.zeros(n - 1, np.int32)
+    upper = np.arange(1, n, dtype=np.int32)
+    rng = np.random.default_rng(0)
+    diag, up = rng.uniform(1, 2, n), rng.normal(size=n - 1)
+    ctx.pattern_from_ldu(n, lower, upper, True)
+    ctx.values_update(diag, up)
+    x = rng.normal(size=n)
+    y = ctx.spmv(x)
+    ref = diag * x
+    ref[0] += up @ x[1:]
+    ref[1:] += up * x[0]
+    assert np.allclose(y, ref, rtol=1e-12, atol=1e-12)
+    assert ctx.get_option("max_row_len") == n
+
+
+def test_spmv_properties_at_baseline_size(ctx):
+    # 100^3 pressure system (BASELINE configs[1]): linearity and the manufactured rhs
+    s = cases.pressure_3d(100)[0]
+    upload_system(ctx, s, partition=False)
+    assert ctx.nnz == 100 ** 3 + 2 * 3 * 100 * 100 * 99
+    rng = np.random.default_rng(11)
+    u, v = rng.normal(size=s.n), rng.normal(size=s.n)
+    yu, yv, yuv = ctx.spmv(u), ctx.spmv(v), ctx.spmv(u + 2.0 * v)
+    scale = np.abs(yu).max() + np.abs(yv).max()
+    assert np.abs(yuv - (yu + 2.0 * yv)).max() <= 1e-14 * scale
+    # b was built as A x*: A x* must reproduce it to rounding
+    assert np.abs(ctx.spmv(s.x_star) - s.source).max() <= 1e-14 * np.abs(s.source).max() + 1e-20
+    # symmetric operator: <u, A v> == <v, A u>
+    assert abs(u @ yv - v @ yu) <= 1e-12 * abs(u @ yv)
+    # all three kernels agree
+    ys = []
+    for variant in (1, 2, 3):
+        ctx.set_option("spmv_variant", variant)
+        ys.append(ctx.spmv(u))
+    ctx.set_option("spmv_variant", 0)
+    assert np.array_equal(ys[0], ys[1])
+    assert np.abs(ys[2] - ys[0]).max() <= 1e-14 * scale
+
+
+def test_spmv_bench_entry_point(ctx):
+    s = cases.pressure_3d(32)[0]
+    upload_system(ctx, s, partition=False)
+    assert ctx.spmv_bench(5) > 0
+    assert ctx.spmv_bench(5, fused_dot=True) > 0

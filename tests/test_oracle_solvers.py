@@ -1,0 +1,126 @@
+"""The oracle's Krylov half checked for self-consistency (it has no reference
+fixture to pin against -- "parity unpinned", see oracle/krylov.cpp): against
+scipy direct solves, across decompositions, and on the criterion's bookkeeping."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spl
+
+from conftest import gather_global
+from ogl_b200 import cases
+
+
+@pytest.mark.parametrize("solver,precond,mbs", [
+    ("GKOCG", "none", 1), ("GKOCG", "BJ", 1), ("GKOCG", "BJ", 4),
+    ("GKOBiCGStab", "BJ", 1), ("GKOGMRES", "BJ", 1)])
+def test_solution_matches_direct_solve(oracle, solver, precond, mbs):
+    systems = cases.pressure_3d(10)
+    A, b = cases.assemble_global_csr(systems)
+    a = oracle.assemble(systems[0])
+    r = oracle.solve([a], solver, precond, max_block_size=mbs, tolerance=1e-10, krylov_dim=40)
+    x_direct = spl.spsolve(A.tocsc(), b)
+    assert np.linalg.norm(r.x[0] - x_direct) / np.linalg.norm(x_direct) < 1e-7
+    assert r.final_residual < 1e-10
+    true_res = np.abs(A @ r.x[0] - b).sum() / r.norm_factor
+    if solver == "GKOGMRES":
+        # the criterion saw the residual of the last restart; the columns built
+        # since then are still added to x afterwards (Ginkgo gmres.cpp epilogue)
+        assert true_res <= r.final_residual * (1 + 1e-6)
+    else:
+        # reported residual is the true normalised L1 residual
+        assert true_res == pytest.approx(r.final_residual, rel=1e-5)
+
+
+def test_momentum_bicgstab(oracle):
+    systems = cases.momentum_3d(8)
+    A, b = cases.assemble_global_csr(systems)
+    assert abs(A - A.T).max() > 0
+    a = oracle.assemble(systems[0])
+    r = oracle.solve([a], "GKOBiCGStab", "BJ", tolerance=1e-10)
+    x_direct = spl.spsolve(A.tocsc(), b)
+    assert np.linalg.norm(r.x[0] - x_direct) / np.linalg.norm(x_direct) < 1e-8
+    assert r.criterion_calls in (2 * r.n_iterations, 2 * r.n_iterations + 1)
+
+
+@pytest.mark.parametrize("procs", [(2, 1, 1), (2, 2, 1), (2, 2, 2)])
+def test_decomposition_invariance(oracle, procs):
+    one = cases.pressure_3d(12)
+    many = cases.pressure_3d(12, procs)
+    r1 = oracle.solve([oracle.assemble(one[0])], "GKOCG", "BJ")
+    rn = oracle.solve([oracle.assemble(s) for s in many], "GKOCG", "BJ")
+    assert abs(rn.n_iterations - r1.n_iterations) <= 1
+    xg = gather_global(many, rn.x)
+    assert np.linalg.norm(xg - r1.x[0]) / np.linalg.norm(r1.x[0]) < 1e-10
+
+
+def test_cyclic_channel_ranks(oracle):
+    ref = None
+    for procs in [(1, 1, 1), (2, 1, 1), (2, 2, 1)]:
+        systems = cases.channel((16, 8, 8), procs)
+        A, b = cases.assemble_global_csr(systems)
+        r = oracle.solve([oracle.assemble(s) for s in systems], "GKOGMRES", "BJ", tolerance=1e-9,
+                         krylov_dim=25)
+        xg = gather_global(systems, r.x)
+        assert np.abs(A @ xg - b).sum() / r.norm_factor < 1e-9
+        if ref is None:
+            ref = xg
+        assert np.linalg.norm(xg - ref) / np.linalg.norm(ref) < 1e-9
+
+
+def test_criterion_bookkeeping(oracle):
+    a = oracle.assemble(cases.pressure_3d(8)[0])
+    base = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-8)
+    # x0 = 0 -> normFactor = |b|_1 (+SMALL) -> initial residual 1
+    assert base.init_residual == pytest.approx(1.0, rel=1e-12)
+    assert base.history.size == base.criterion_calls
+    assert base.history[-1] == base.final_residual
+    # frequency 5: stops at the first multiple of 5 at or after convergence
+    f5 = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-8, frequency=5)
+    assert (f5.criterion_calls - 1) % 5 == 0
+    assert 0 <= f5.criterion_calls - base.criterion_calls < 5
+    # minIter skips checks (but never the one at iter 0)
+    mi = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-8, min_iter=base.criterion_calls + 10)
+    assert mi.criterion_calls == base.criterion_calls + 10 + 1
+    # maxIter
+    mx = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-30, max_iter=7)
+    assert mx.criterion_calls == 8
+    # relTol
+    rt = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-30, rel_tol=1e-2)
+    assert rt.final_residual < 1e-2 * rt.init_residual
+    assert rt.criterion_calls < base.criterion_calls
+    # BiCGStab doubles maxIter (StoppingCriterion.H:188) and reports calls / 2
+    bi = oracle.solve([a], "GKOBiCGStab", "BJ", tolerance=1e-30, max_iter=5)
+    assert bi.criterion_calls == 11 and bi.n_iterations == 5
+
+
+def test_gmres_sees_the_restart_residual_only(oracle):
+    # convergence is only detected one call after a restart
+    a = oracle.assemble(cases.pressure_3d(8)[0])
+    r = oracle.solve([a], "GKOGMRES", "BJ", tolerance=1e-6, krylov_dim=10)
+    assert (r.criterion_calls - 2) % 10 == 0
+    h = r.history
+    assert np.all(h[1:11] == h[0])
+
+
+def test_block_jacobi_blocks(oracle):
+    import scipy.sparse as sp
+
+    a = oracle.assemble(cases.momentum_3d(6)[0])
+    for mbs in (2, 3, 8):
+        bp, inv = oracle.bj_blocks(a.n, a.row_ptrs, a.cols, a.vals, mbs)
+        sizes = np.diff(bp)
+        assert bp[0] == 0 and bp[-1] == a.n and sizes.max() <= mbs and np.all(sizes[:-1] == mbs)
+        A = sp.csr_matrix((a.vals, a.cols, a.row_ptrs), shape=(a.n, a.n)).toarray()
+        off = 0
+        for b in range(sizes.size):
+            lo, hi, s = bp[b], bp[b + 1], sizes[b]
+            m = inv[off:off + s * s].reshape(s, s)
+            off += s * s
+            assert np.abs(m @ A[lo:hi, lo:hi] - np.eye(s)).max() < 1e-13
+    # natural blocks: identical consecutive patterns are merged first
+    rp = np.array([0, 2, 4, 5, 6], np.int32)
+    cols = np.array([0, 1, 0, 1, 2, 3], np.int32)
+    vals = np.array([2., 1., 1., 3., 4., 5.])
+    bp, inv = oracle.bj_blocks(4, rp, cols, vals, 2)
+    assert bp.tolist() == [0, 2, 4]
+    bp, inv = oracle.bj_blocks(4, rp, cols, vals, 3)
+    assert bp.tolist() == [0, 3, 4]
