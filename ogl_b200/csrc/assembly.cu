@@ -305,6 +305,10 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->global_n = n;
     ctx->n_blocks = 0;
     ctx->bj_pattern_mbs = 0;
+    if (ctx->d_inv_diag) {
+        cudaFree(ctx->d_inv_diag);   // sized for the previous pattern
+        ctx->d_inv_diag = nullptr;
+    }
     if (ctx->graph_exec) {
         cudaGraphExecDestroy(ctx->graph_exec);
         ctx->graph_exec = nullptr;

@@ -220,6 +220,9 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->use_graph = value != 0;
     } else if (k == "profile_stride") {
         ctx->profile_stride = value < 0 ? 0 : value;
+    } else if (k == "stream_ctas") {
+        if (value < 0 || value > 65535) return fail(ctx, OGL_ERR_INVALID, "stream_ctas in [0,65535]");
+        ctx->stream_ctas = value;
     } else if (k == "blas1_blocks") {
         if (value < 1 || value > 65535) return fail(ctx, OGL_ERR_INVALID, "blas1_blocks in [1,65535]");
         ctx->blas1_blocks = value;
@@ -244,6 +247,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "use_graph") *value = ctx->use_graph;
     else if (k == "profile_stride") *value = ctx->profile_stride;
     else if (k == "blas1_blocks") *value = ctx->blas1_blocks;
+    else if (k == "stream_ctas") *value = ctx->stream_ctas;
     else if (k == "max_row_len") *value = ctx->max_row_len;
     else if (k == "max_block_nnz") *value = ctx->max_block_nnz;
     else if (k == "launches") *value = ctx->launches;

@@ -19,7 +19,7 @@ using scalar = double;
 constexpr int kMaxReduce = 4;          // scalars reduced by one kernel launch
 constexpr int kNumSM = 148;            // B200
 constexpr int kBlas1Threads = 256;
-constexpr int kBlas1BlocksPerSM = 8;   // 2048 resident threads per SM
+constexpr int kBlas1BlocksPerSM = 4;   // 1024 resident threads per SM, <= 64 registers each
 constexpr int kMaxPartialBlocks = 4096;
 
 // Device-resident scalar state of a solve.  Every kernel of the iteration reads
@@ -95,6 +95,7 @@ struct Context {
     int64_t use_graph = 1;       // replay a chunk as a CUDA graph
     int64_t profile_stride = 0;  // sample SpMV launch durations every k-th iteration
     int64_t blas1_blocks = kNumSM * kBlas1BlocksPerSM;
+    int64_t stream_ctas = 0;     // persistent SpMV grid (0 = 8 CTAs per SM)
 
     // local pattern (a4/a5) -- resident across solves
     label n = 0, n_faces = 0, n_local_iface = 0;

@@ -72,7 +72,7 @@ __global__ void k_gmres_after_residual(SolveState *s, Dense d, int with_norm_fac
 }
 
 // gmres::restart : v_0 = residual / |residual|, g = (|residual|, 0, ...), final_iter = 0
-__global__ void __launch_bounds__(kT) k_gmres_restart(const GmK a, int guard)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_gmres_restart(const GmK a, int guard)
 {
     if (guard && a.state->done) return;
     const double nrm = a.state->res_norm2;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kT) k_gmres_restart(const GmK a, int guard)
 }
 
 // r = in0 (residual): red = {<r,r>, |r|_1}
-__global__ void __launch_bounds__(kT) k_gmres_norms(const GmK a, int guard)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_gmres_norms(const GmK a, int guard)
 {
     if (guard && a.state->done) return;
     double red[2] = {0.0, 0.0};
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kT) k_gmres_norms(const GmK a, int guard)
 //   red[0] = <w, v_{k+1}>   (LAST: <w, w>)
 //   in0 = v_k, in1 = v_{k+1} ; out0 = w
 template <bool LAST>
-__global__ void __launch_bounds__(kT) k_gmres_mgs(const GmK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_gmres_mgs(const GmK a)
 {
     if (a.state->done) return;
     const double h = a.state->red[0];
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kT) k_gmres_mgs(const GmK a)
 
 // v_{ri+1} = w / |w| and, by one thread, common_gmres::hessenberg_qr for column ri
 //   in0 = w ; out0 = v_{ri+1}
-__global__ void __launch_bounds__(kT) k_gmres_normalize_qr(const GmK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_gmres_normalize_qr(const GmK a)
 {
     if (a.state->done) return;
     const double hn = sqrt(a.state->red[0]);
@@ -165,7 +165,7 @@ __global__ void k_gmres_solve_krylov(SolveState *s, Dense d, int guard)
 }
 
 // gmres::multi_axpy : out0 = sum_j y_j v_j   (in0 = V, leading dimension n)
-__global__ void __launch_bounds__(kT) k_gmres_multi_axpy(const GmK a, int guard)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_gmres_multi_axpy(const GmK a, int guard)
 {
     if (guard && a.state->done) return;
     const int fi = a.state->final_iter;
@@ -178,14 +178,14 @@ __global__ void __launch_bounds__(kT) k_gmres_multi_axpy(const GmK a, int guard)
 }
 
 // x += in0
-__global__ void __launch_bounds__(kT) k_gmres_add(const GmK a, int guard)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_gmres_add(const GmK a, int guard)
 {
     if (guard && a.state->done) return;
     GRID_STRIDE(i, a.n) a.out0[i] = __dadd_rn(a.out0[i], __dmul_rn(1.0, a.in0[i]));
 }
 
 // out0 = in0 * inv_diag (scalar Jacobi on a basis vector)
-__global__ void __launch_bounds__(kT) k_gmres_scalar_precond(const GmK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_gmres_scalar_precond(const GmK a)
 {
     if (a.state->done) return;
     GRID_STRIDE(i, a.n) a.out0[i] = __dmul_rn(a.in0[i], a.in1[i]);

@@ -192,6 +192,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
     double acc[NRED];
 #pragma unroll
     for (int j = 0; j < NRED; ++j) acc[j] = 0.0;
+#pragma unroll 4
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
         for (int j = 0; j < NRED; ++j)

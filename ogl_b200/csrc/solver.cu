@@ -44,7 +44,7 @@ struct VecK {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n);         \
          i += (int64_t)gridDim.x * blockDim.x)
 
-__global__ void __launch_bounds__(kT) k_sum(const VecK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_sum(const VecK a)
 {
     double red[1] = {0.0};
     GRID_STRIDE(i, a.n) red[0] = __dadd_rn(red[0], a.in0[i]);
@@ -52,18 +52,18 @@ __global__ void __launch_bounds__(kT) k_sum(const VecK a)
 }
 
 // out0[i] = state->red[0]
-__global__ void __launch_bounds__(kT) k_fill_from_red(const VecK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_fill_from_red(const VecK a)
 {
     const double v = a.state->red[0];
     GRID_STRIDE(i, a.n) a.out0[i] = v;
 }
 
-__global__ void __launch_bounds__(kT) k_fill(label n, double *out, double v)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_fill(label n, double *out, double v)
 {
     GRID_STRIDE(i, n) out[i] = v;
 }
 
-__global__ void __launch_bounds__(kT) k_scale(label n, double *v, double s)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_scale(label n, double *v, double s)
 {
     GRID_STRIDE(i, n) v[i] = __dmul_rn(v[i], s);
 }
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kT) k_scale(label n, double *v, double s)
 //   red = { MODE 0: <r,z>  MODE 1/2: <r,r> ,  |r|_1 ,  normFactor sum (:32-69) }
 // PK: 0 none (z == r), 1 scalar Jacobi fused, 2 deferred (block Jacobi runs after)
 template <int PK, int MODE>
-__global__ void __launch_bounds__(kT) k_init_norms(const VecK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_init_norms(const VecK a)
 {
     double red[3] = {0.0, 0.0, 0.0};
     GRID_STRIDE(i, a.n) {
@@ -102,12 +102,28 @@ __global__ void __launch_bounds__(kT) k_init_norms(const VecK a)
 }
 
 // cg::step_1   in0 = z (or r when unpreconditioned), out0 = p
-__global__ void __launch_bounds__(kT) k_cg_p(const VecK a)
+// 128-bit loads/stores (two rows per thread and trip), 8 CTAs of 256 threads per SM
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
 {
     if (a.guard_done && a.state->done) return;
     const bool p_is_z = a.state->flag_p_is_z != 0;
     const double t = a.state->coef_p;
-    GRID_STRIDE(i, a.n) {
+    const double2 *__restrict__ z2 = reinterpret_cast<const double2 *>(a.in0);
+    double2 *__restrict__ p2 = reinterpret_cast<double2 *>(a.out0);
+    const int64_t n2 = a.n >> 1;
+#pragma unroll 2
+    GRID_STRIDE(i, n2) {
+        const double2 z = z2[i];
+        double2 p = z;
+        if (!p_is_z) {
+            const double2 po = p2[i];
+            p.x = __dadd_rn(z.x, __dmul_rn(t, po.x));
+            p.y = __dadd_rn(z.y, __dmul_rn(t, po.y));
+        }
+        p2[i] = p;
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = a.n - 1;
         const double z = a.in0[i];
         a.out0[i] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.out0[i]));
     }
@@ -116,34 +132,70 @@ __global__ void __launch_bounds__(kT) k_cg_p(const VecK a)
 // cg::step_2 + preconditioner + <r,z> + |r|_1 (+ criterion on one rank)
 //   in0 = p, in1 = q, in2 = inv_diag ; out0 = x, out1 = r, out2 = z
 template <int PK>
-__global__ void __launch_bounds__(kT) k_cg_xr(const VecK a)
+__device__ __forceinline__ void cg_xr_elem(bool upd, double t, double &x, double &r, double p,
+                                           double q, double d, double &z, double (&red)[2])
+{
+    if (upd) {
+        x = __dadd_rn(x, __dmul_rn(t, p));
+        r = __dsub_rn(r, __dmul_rn(t, q));
+    }
+    red[1] = __dadd_rn(red[1], fabs(r));
+    if (PK == 1) {
+        z = __dmul_rn(r, d);
+        red[0] = __dadd_rn(red[0], __dmul_rn(r, z));
+    } else if (PK == 0) {
+        red[0] = __dadd_rn(red[0], __dmul_rn(r, r));
+    }
+}
+
+template <int PK>
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
 {
     if (a.guard_done && a.state->done) return;
     const bool upd = a.state->beta != 0.0;
     const double t = a.state->coef_x;
     double red[2] = {0.0, 0.0};
-    GRID_STRIDE(i, a.n) {
-        double r = a.out1[i];
+    const double2 *__restrict__ p2 = reinterpret_cast<const double2 *>(a.in0);
+    const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(a.in1);
+    const double2 *__restrict__ d2 = reinterpret_cast<const double2 *>(a.in2);
+    double2 *__restrict__ x2 = reinterpret_cast<double2 *>(a.out0);
+    double2 *__restrict__ r2 = reinterpret_cast<double2 *>(a.out1);
+    double2 *__restrict__ z2 = reinterpret_cast<double2 *>(a.out2);
+    const int64_t n2 = a.n >> 1;
+#pragma unroll 2
+    GRID_STRIDE(i, n2) {
+        double2 r = r2[i];
+        double2 x = make_double2(0.0, 0.0), p = x, q = x, d = x, z = x;
         if (upd) {
-            a.out0[i] = __dadd_rn(a.out0[i], __dmul_rn(t, a.in0[i]));
-            r = __dsub_rn(r, __dmul_rn(t, a.in1[i]));
+            x = x2[i];
+            p = p2[i];
+            q = q2[i];
+        }
+        if (PK == 1) d = d2[i];
+        cg_xr_elem<PK>(upd, t, x.x, r.x, p.x, q.x, d.x, z.x, red);
+        cg_xr_elem<PK>(upd, t, x.y, r.y, p.y, q.y, d.y, z.y, red);
+        if (upd) {
+            x2[i] = x;
+            r2[i] = r;
+        }
+        if (PK == 1) z2[i] = z;
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = a.n - 1;
+        double x = a.out0[i], r = a.out1[i], z = 0.0;
+        cg_xr_elem<PK>(upd, t, x, r, a.in0[i], a.in1[i], PK == 1 ? a.in2[i] : 0.0, z, red);
+        if (upd) {
+            a.out0[i] = x;
             a.out1[i] = r;
         }
-        red[1] = __dadd_rn(red[1], fabs(r));
-        if (PK == 1) {
-            const double z = __dmul_rn(r, a.in2[i]);
-            a.out2[i] = z;
-            red[0] = __dadd_rn(red[0], __dmul_rn(r, z));
-        } else if (PK == 0) {
-            red[0] = __dadd_rn(red[0], __dmul_rn(r, r));
-        }
+        if (PK == 1) a.out2[i] = z;
     }
     grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
 }
 
 // bicgstab::step_1 + y = M^-1 p     in0 = r, in1 = v, in2 = inv_diag ; out0 = p, out1 = y
 template <int PK>
-__global__ void __launch_bounds__(kT) k_bicg_step1(const VecK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step1(const VecK a)
 {
     if (a.guard_done && a.state->done) return;
     const bool p_is_r = a.state->flag_p_is_z != 0;
@@ -160,7 +212,7 @@ __global__ void __launch_bounds__(kT) k_bicg_step1(const VecK a)
 
 // bicgstab::step_2 + |s|_1 + z = M^-1 s   in0 = r, in1 = v, in2 = inv_diag ; out0 = s, out1 = z
 template <int PK>
-__global__ void __launch_bounds__(kT) k_bicg_step2(const VecK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step2(const VecK a)
 {
     if (a.guard_done && a.state->done) return;
     const bool upd = a.state->beta != 0.0;
@@ -178,7 +230,7 @@ __global__ void __launch_bounds__(kT) k_bicg_step2(const VecK a)
 
 // bicgstab::step_3 + <rr,r> + |r|_1
 //   in0 = s, in1 = t, in2 = y, in3 = z, in4 = rr ; out0 = x, out1 = r
-__global__ void __launch_bounds__(kT) k_bicg_step3(const VecK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step3(const VecK a)
 {
     if (a.guard_done && a.state->done) return;
     const double alpha = a.state->alpha, omega = a.state->omega;
@@ -195,7 +247,7 @@ __global__ void __launch_bounds__(kT) k_bicg_step3(const VecK a)
 }
 
 // bicgstab::finalize  x += alpha y when the solver stopped at the first check
-__global__ void __launch_bounds__(kT) k_bicg_finalize(const VecK a)
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_finalize(const VecK a)
 {
     if (!a.state->stop_half) return;
     const double alpha = a.state->alpha;

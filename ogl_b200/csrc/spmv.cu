@@ -41,6 +41,7 @@ struct SpmvK {
     const double *y_in;   // advanced: y = alpha*A*x + beta*y_in
     double *y;
     label n;
+    label n_row_blocks;   // stream kernel: ceil(n / kRowsPerBlock)
     double alpha, beta;
     const double *dot_with;
     double *partials;
@@ -59,54 +60,59 @@ __device__ __forceinline__ double prod_of(double v, double xv, double alpha, boo
 }
 
 template <bool ADV, int NRED>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, 8)
 k_spmv_stream(const SpmvK a)
 {
     if (a.guard_done && a.state->done) return;
     extern __shared__ double prod[];
     const int tid = threadIdx.x;
-    const label r0 = blockIdx.x * kRowsPerBlock;
-    const label nr = min((label)kRowsPerBlock, a.n - r0);
-    const label s = __ldg(&a.row_ptrs[r0]);
-    const label e = __ldg(&a.row_ptrs[r0 + nr]);
-    // row extents of "my" row: issued early, consumed after the barrier
-    label rs = 0, re = 0;
-    if (tid < nr) {
-        rs = __ldg(&a.row_ptrs[r0 + tid]);
-        re = __ldg(&a.row_ptrs[r0 + tid + 1]);
-    }
-    // ---- stream the slice: coalesced value/column loads, gathered x
-    label k = s + tid;
-    for (; k + 3 * kStreamThreads < e; k += 4 * kStreamThreads) {
-        label c[4];
-        double v[4], xv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = __ldcs(&a.cols[k + u * kStreamThreads]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldcs(&a.vals[k + u * kStreamThreads]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) xv[u] = __ldg(&a.x[c[u]]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            prod[k - s + u * kStreamThreads] = prod_of(v[u], xv[u], a.alpha, ADV);
-    }
-    for (; k < e; k += kStreamThreads) {
-        const label c = __ldcs(&a.cols[k]);
-        const double v = __ldcs(&a.vals[k]);
-        prod[k - s] = prod_of(v, __ldg(&a.x[c]), a.alpha, ADV);
-    }
-    __syncthreads();
-    // ---- one thread per row: left-to-right sum of its products
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
-    if (tid < nr) {
-        const label row = r0 + tid;
-        double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
-        for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
-        a.y[row] = sum;
-        if (NRED >= 1) red[0] = __dmul_rn(a.dot_with[row], sum);
-        if (NRED >= 2) red[1] = __dmul_rn(sum, sum);
+    // persistent CTAs: a fixed grid (8 per SM) walks the row blocks, so a fused
+    // reduction leaves gridDim.x partials whatever the matrix size
+    for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x) {
+        const label r0 = rb * kRowsPerBlock;
+        const label nr = min((label)kRowsPerBlock, a.n - r0);
+        const label s = __ldg(&a.row_ptrs[r0]);
+        const label e = __ldg(&a.row_ptrs[r0 + nr]);
+        // row extents of "my" row: issued early, consumed after the barrier
+        label rs = 0, re = 0;
+        if (tid < nr) {
+            rs = __ldg(&a.row_ptrs[r0 + tid]);
+            re = __ldg(&a.row_ptrs[r0 + tid + 1]);
+        }
+        // ---- stream the slice: coalesced value/column loads, gathered x
+        label k = s + tid;
+        for (; k + 3 * kStreamThreads < e; k += 4 * kStreamThreads) {
+            label c[4];
+            double v[4], xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = __ldcs(&a.cols[k + u * kStreamThreads]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcs(&a.vals[k + u * kStreamThreads]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = __ldg(&a.x[c[u]]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                prod[k - s + u * kStreamThreads] = prod_of(v[u], xv[u], a.alpha, ADV);
+        }
+        for (; k < e; k += kStreamThreads) {
+            const label c = __ldcs(&a.cols[k]);
+            const double v = __ldcs(&a.vals[k]);
+            prod[k - s] = prod_of(v, __ldg(&a.x[c]), a.alpha, ADV);
+        }
+        __syncthreads();
+        // ---- one thread per row: left-to-right sum of its products
+        if (tid < nr) {
+            const label row = r0 + tid;
+            double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+            for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
+            a.y[row] = sum;
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
+            if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+        }
+        __syncthreads();   // prod is overwritten by the next row block
     }
     if (NRED > 0)
         grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
@@ -286,6 +292,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.y_in = sa.y_in ? sa.y_in : sa.y;
     k.y = sa.y;
     k.n = ctx->n;
+    k.n_row_blocks = 0;
     k.alpha = sa.alpha;
     k.beta = sa.beta;
     k.dot_with = sa.dot_with;
@@ -324,7 +331,10 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
             cudaFuncSetAttribute(k_spmv_stream<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
             attr_set = true;
         }
-        const int grid = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
+        const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
+        k.n_row_blocks = nblk;
+        const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 8;
+        const int grid = nblk < cap ? nblk : (int)cap;
         DISPATCH(k_spmv_stream, grid, kStreamThreads, smem);
     } else if (variant == 2) {
         const int grid = (ctx->n + 255) / 256;
