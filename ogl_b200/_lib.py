@@ -77,6 +77,24 @@ SYMBOLS = {
 _lib = None
 
 
+def _preload_bundled_nccl() -> None:
+    """libogl_b200.so needs `libnccl.so.2`.  PyTorch ships its own (newer) copy
+    and resolves it by SONAME: whichever copy is mapped first serves the whole
+    process, and torch fails to import on top of the older system copy.  Map
+    torch's copy first so that both sides share one NCCL."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    if spec and spec.submodule_search_locations:
+        for base in spec.submodule_search_locations:
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+
+
 def load() -> C.CDLL:
     """Load libogl_b200.so; raises when the CUDA extension has not been built."""
     global _lib
@@ -85,7 +103,8 @@ def load() -> C.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
-        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _preload_bundled_nccl()
+        lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)   # AttributeError if the header and the library diverge
             fn.restype = res

@@ -1,0 +1,51 @@
+"""Worker of tests/test_gpu_multi.py: one process per GPU (torchrun), NCCL.
+Each rank solves its share through the plugin surface and dumps its results."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ogl_b200 import cases  # noqa: E402
+from ogl_b200.host import ObjectRegistry  # noqa: E402
+from ogl_b200.parallel import init_from_env  # noqa: E402
+from ogl_b200.plugin import lduMatrix_solver_New  # noqa: E402
+
+CASES = {
+    "pressure_cg": (lambda p: cases.pressure_3d(16, p), "GKOCG", "BJ", 1, 1e-9),
+    "pressure_cg_bj4": (lambda p: cases.pressure_3d(12, p), "GKOCG", "BJ", 4, 1e-9),
+    "momentum_bicgstab": (lambda p: cases.momentum_3d(14, p), "GKOBiCGStab", "BJ", 1, 1e-10),
+    "channel_gmres": (lambda p: cases.channel((16, 8, 8), p), "GKOGMRES", "BJ", 1, 1e-8),
+    "cavity_cg_none": (lambda p: cases.cavity_2d(p), "GKOCG", "none", 1, 1e-8),
+}
+
+
+def main():
+    out, procs = sys.argv[1], tuple(int(v) for v in sys.argv[2].split(","))
+    ps = init_from_env("nccl")
+    db = ObjectRegistry()
+    results = {}
+    for name, (builder, solver, precond, mbs, tol) in CASES.items():
+        s = builder(procs)[ps.rank]
+        controls = {"solver": solver, "executor": "cuda", "tolerance": tol, "relTol": 0.0,
+                    "adaptMinIter": False, "krylovDim": 30,
+                    "preconditioner": {"preconditioner": precond, "maxBlockSize": mbs}}
+        sol = lduMatrix_solver_New(name, s, controls, db, ps)
+        psi = s.psi.copy()
+        perf = sol.solve(psi, s.source)
+        x = np.random.default_rng(9).normal(size=sum(t.n for t in builder(procs)))[s.global_ids]
+        y = sol.ctx.spmv(x)
+        results[name] = {"iters": perf.n_iterations, "init": perf.initial_residual,
+                         "final": perf.final_residual, "x": psi.tolist(), "y": y.tolist(),
+                         "global_n": sol.ctx.partition_sizes()[1]}
+    json.dump(results, open(f"{out}.{ps.rank}", "w"))
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
