@@ -5,6 +5,7 @@
 #include <cstring>
 #include <fstream>
 #include <iomanip>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -52,6 +53,50 @@ int get_work(Context *ctx, int idx, double **out)
     return OGL_OK;
 }
 
+// One NCCL communicator per (process, unique id), shared by every context
+// created with that id -- as all fields share MPI_COMM_WORLD in the reference
+// (ExecutorHandler.H:140-144).  Calls are serialised by the caller, so sharing
+// it across the contexts' streams is safe.
+struct SharedComm {
+    ncclComm_t comm = nullptr;
+    int refs = 0;
+};
+static std::mutex g_comm_mutex;
+static std::map<std::string, SharedComm> g_comms;
+
+static int acquire_comm(const void *id_bytes, int n_ranks, int rank, ncclComm_t *out,
+                        std::string *key, std::string *err)
+{
+    std::lock_guard<std::mutex> lock(g_comm_mutex);
+    key->assign(static_cast<const char *>(id_bytes), OGL_NCCL_ID_BYTES);
+    auto it = g_comms.find(*key);
+    if (it == g_comms.end()) {
+        ncclUniqueId id;
+        std::memcpy(&id, id_bytes, sizeof(id));
+        ncclComm_t comm = nullptr;
+        ncclResult_t r = ncclCommInitRank(&comm, n_ranks, id, rank);
+        if (r != ncclSuccess) {
+            *err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r);
+            return OGL_ERR_NCCL;
+        }
+        it = g_comms.emplace(*key, SharedComm{comm, 0}).first;
+    }
+    it->second.refs++;
+    *out = it->second.comm;
+    return OGL_OK;
+}
+
+static void release_comm(const std::string &key)
+{
+    std::lock_guard<std::mutex> lock(g_comm_mutex);
+    auto it = g_comms.find(key);
+    if (it == g_comms.end()) return;
+    if (--it->second.refs == 0) {
+        ncclCommDestroy(it->second.comm);
+        g_comms.erase(it);
+    }
+}
+
 static void destroy(Context *c)
 {
     if (!c) return;
@@ -59,7 +104,7 @@ static void destroy(Context *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm) release_comm(c->comm_key);
     void *ptrs[] = {c->d_rows,       c->d_cols,       c->d_map,        c->d_row_ptrs,
                     c->d_send_idxs,  c->d_send_buf,   c->d_recv_buf,   c->d_nl_rows,
                     c->d_nl_cols,    c->d_nl_map,     c->d_nl_row_ids, c->d_nl_row_ptrs,
@@ -183,11 +228,12 @@ int ogl_ctx_create(int device_id, int rank, int n_ranks, const void *nccl_id, vo
     cudaMemset(c->d_ticket, 0, sizeof(unsigned int));
     std::memset(c->h_state, 0, 3 * sizeof(SolveState));
     if (n_ranks > 1) {
-        ncclUniqueId id;
-        std::memcpy(&id, nccl_id, sizeof(id));
-        ncclResult_t r = ncclCommInitRank(&c->comm, n_ranks, id, rank);
-        if (r != ncclSuccess)
-            return bail(OGL_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+        std::string err;
+        const int rc = ogl::acquire_comm(nccl_id, n_ranks, rank, &c->comm, &c->comm_key, &err);
+        if (rc != OGL_OK) {
+            c->comm = nullptr;
+            return bail(rc, err);
+        }
     }
     *out = c;
     return OGL_OK;
@@ -220,6 +266,9 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->use_graph = value != 0;
     } else if (k == "profile_stride") {
         ctx->profile_stride = value < 0 ? 0 : value;
+    } else if (k == "tma_stages") {
+        if (value < 1 || value > 4) return fail(ctx, OGL_ERR_INVALID, "tma_stages in [1,4]");
+        ctx->tma_stages = value;
     } else if (k == "stream_ctas") {
         if (value < 0 || value > 65535) return fail(ctx, OGL_ERR_INVALID, "stream_ctas in [0,65535]");
         ctx->stream_ctas = value;
@@ -248,6 +297,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "profile_stride") *value = ctx->profile_stride;
     else if (k == "blas1_blocks") *value = ctx->blas1_blocks;
     else if (k == "stream_ctas") *value = ctx->stream_ctas;
+    else if (k == "tma_stages") *value = ctx->tma_stages;
     else if (k == "max_row_len") *value = ctx->max_row_len;
     else if (k == "max_block_nnz") *value = ctx->max_block_nnz;
     else if (k == "launches") *value = ctx->launches;

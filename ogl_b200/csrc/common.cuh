@@ -86,7 +86,8 @@ struct Context {
     cudaStream_t comm_stream = nullptr;  // halo exchange
     cudaEvent_t ev_pack = nullptr, ev_recv = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;           // shared per (process, unique id), see capi.cu
+    std::string comm_key;
     std::string error;
 
     // options
@@ -96,6 +97,7 @@ struct Context {
     int64_t profile_stride = 0;  // sample SpMV launch durations every k-th iteration
     int64_t blas1_blocks = kNumSM * kBlas1BlocksPerSM;
     int64_t stream_ctas = 0;     // persistent SpMV grid (0 = 8 CTAs per SM)
+    int64_t tma_stages = 3;      // shared-memory ring depth of the TMA SpMV
 
     // local pattern (a4/a5) -- resident across solves
     label n = 0, n_faces = 0, n_local_iface = 0;

@@ -119,6 +119,208 @@ k_spmv_stream(const SpmvK a)
                                            a.inline_epi != 0, a.ea);
 }
 
+// ---------------------------------------------------------------------------
+// Variant 4: TMA-fed persistent pipeline.
+//
+// One producer lane per CTA walks the CTA's row blocks ahead of the consumers
+// and issues three 1-D bulk copies (cp.async.bulk, the TMA engine) per block --
+// values, columns, row pointers -- into a ring of kStages shared-memory stages;
+// completion is tracked by an mbarrier per stage (expect_tx / complete_tx).
+// The 8 consumer warps never wait on HBM: they wait on the stage's mbarrier,
+// gather x (L1/L2), overwrite the staged values with the products in place,
+// meet at a named barrier, add each row's products left to right (same order
+// as the stream kernel => bit-identical results), and hand the stage back
+// through a second mbarrier.  The matrix stream carries an L2 evict-first
+// policy so that x keeps its place in the 126 MB L2.
+// ---------------------------------------------------------------------------
+namespace tma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes,
+                                          uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void consumer_sync()
+{
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+}  // namespace tma
+
+constexpr int kTmaThreads = kStreamThreads + 32;   // 8 consumer warps + 1 producer warp
+constexpr int kTmaMaxStages = 4;
+
+struct TmaHdr {
+    label s, e, s_al, r0, nr, pad0, pad1, pad2;
+};
+
+template <bool ADV, int NRED>
+__global__ void __launch_bounds__(kTmaThreads)
+k_spmv_tma(const SpmvK a, const int cap, const int stages)
+{
+    if (a.guard_done && a.state->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // carve: [vals | cols | row ptrs] per stage, then headers, then barriers
+    const size_t vals_bytes = (size_t)cap * sizeof(double);
+    const size_t cols_bytes = (size_t)cap * sizeof(label);
+    const size_t rp_bytes_max = (size_t)(kRowsPerBlock + 4) * sizeof(label);
+    const size_t stage_bytes = vals_bytes + cols_bytes + rp_bytes_max;
+    TmaHdr *hdr = reinterpret_cast<TmaHdr *>(smem_raw + stage_bytes * stages);
+    uint64_t *full = reinterpret_cast<uint64_t *>(hdr + kTmaMaxStages);
+    uint64_t *empty = full + kTmaMaxStages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int st = 0; st < stages; ++st) {
+            tma::mbar_init(&full[st], 1);
+            tma::mbar_init(&empty[st], kStreamThreads / 32);
+        }
+        tma::fence_barrier_init();
+        tma::fence_proxy_async();
+    }
+    __syncthreads();
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+
+    if (warp == kStreamThreads / 32) {
+        // ===== producer: one lane feeds the ring =====
+        if (lane == 0) {
+            const uint64_t pol = tma::policy_evict_first();
+            int i = 0;
+            for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x, ++i) {
+                const int st = i % stages;
+                const uint32_t round = (uint32_t)(i / stages);
+                if (round > 0) tma::mbar_wait(&empty[st], (round - 1) & 1);
+                const label r0 = rb * kRowsPerBlock;
+                const label nr = min((label)kRowsPerBlock, a.n - r0);
+                const label s = __ldg(&a.row_ptrs[r0]);
+                const label e = __ldg(&a.row_ptrs[r0 + nr]);
+                const label s_al = s & ~3;                  // 32 B (values) / 16 B (columns) aligned
+                const label cnt = ((e + 3) & ~3) - s_al;
+                const uint32_t rp_bytes = (uint32_t)(((nr + 1) * sizeof(label) + 15) & ~15u);
+                unsigned char *base = smem_raw + stage_bytes * st;
+                hdr[st].s = s;
+                hdr[st].e = e;
+                hdr[st].s_al = s_al;
+                hdr[st].r0 = r0;
+                hdr[st].nr = nr;
+                const uint32_t bytes = (uint32_t)cnt * 12u + rp_bytes;
+                tma::mbar_expect_tx(&full[st], bytes);
+                if (cnt > 0) {
+                    tma::bulk_load(base, a.vals + s_al, (uint32_t)cnt * 8u, &full[st], pol);
+                    tma::bulk_load(base + vals_bytes, a.cols + s_al, (uint32_t)cnt * 4u, &full[st], pol);
+                }
+                tma::bulk_load(base + vals_bytes + cols_bytes, a.row_ptrs + r0, rp_bytes, &full[st], pol);
+            }
+        }
+    } else {
+        // ===== consumers: 256 threads =====
+        int i = 0;
+        for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x, ++i) {
+            const int st = i % stages;
+            const uint32_t round = (uint32_t)(i / stages);
+            tma::mbar_wait(&full[st], round & 1);
+            unsigned char *base = smem_raw + stage_bytes * st;
+            double *v = reinterpret_cast<double *>(base);
+            const label *c = reinterpret_cast<const label *>(base + vals_bytes);
+            const label *rp = reinterpret_cast<const label *>(base + vals_bytes + cols_bytes);
+            const label s = hdr[st].s, e = hdr[st].e, s_al = hdr[st].s_al;
+            const label r0 = hdr[st].r0, nr = hdr[st].nr;
+            const label off = s - s_al, len = e - s;
+            // products in place: v[k] <- v[k] * x[c[k]]
+            label k = tid;
+            for (; k + 3 * kStreamThreads < len; k += 4 * kStreamThreads) {
+                double xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xv[u] = __ldg(&a.x[c[off + k + u * kStreamThreads]]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const label q = off + k + u * kStreamThreads;
+                    v[q] = prod_of(v[q], xv[u], a.alpha, ADV);
+                }
+            }
+            for (; k < len; k += kStreamThreads) {
+                const label q = off + k;
+                v[q] = prod_of(v[q], __ldg(&a.x[c[q]]), a.alpha, ADV);
+            }
+            tma::consumer_sync();
+            if (tid < nr) {
+                const label row = r0 + tid;
+                double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+                const label qe = rp[tid + 1] - s_al;
+                for (label q = rp[tid] - s_al; q < qe; ++q) sum = __dadd_rn(sum, v[q]);
+                a.y[row] = sum;
+                if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
+                if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+            }
+            // generic-proxy writes to the stage must be ordered before the next
+            // bulk copy (async proxy) overwrites it
+            tma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty[st]);
+        }
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
 template <bool ADV, int NRED>
 __global__ void __launch_bounds__(256) k_spmv_scalar(const SpmvK a)
 {
@@ -271,7 +473,7 @@ int spmv_setup(Context *ctx)
 
 static int pick_variant(const Context *ctx)
 {
-    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 3) return (int)ctx->spmv_variant;
+    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 4) return (int)ctx->spmv_variant;
     const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
     const double mean_len = ctx->n > 0 ? (double)ctx->nnz / ctx->n : 0.0;
     // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
@@ -336,6 +538,38 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 8;
         const int grid = nblk < cap ? nblk : (int)cap;
         DISPATCH(k_spmv_stream, grid, kStreamThreads, smem);
+    } else if (variant == 4) {
+        const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
+        k.n_row_blocks = nblk;
+        const int stages = (int)ctx->tma_stages;
+        const int cap = (int)(((ctx->max_block_nnz + 3) & ~(int64_t)3) + 4);
+        const size_t stage_bytes = (size_t)cap * 12 + (size_t)(kRowsPerBlock + 4) * sizeof(label);
+        const size_t smem = stage_bytes * stages + sizeof(TmaHdr) * kTmaMaxStages +
+                            2 * sizeof(uint64_t) * kTmaMaxStages + 128;
+        if (smem > 227 * 1024)
+            return fail(ctx, OGL_ERR_UNSUPPORTED, "row blocks too long for the TMA SpMV pipeline");
+        // resident CTAs per SM for this shared-memory footprint -> persistent grid
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 2048 / kTmaThreads) per_sm = 2048 / kTmaThreads;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t want = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * per_sm;
+        const int grid = nblk < want ? nblk : (int)want;
+#define TMA_LAUNCH(A, R)                                                                      \
+    do {                                                                                      \
+        cudaFuncSetAttribute(k_spmv_tma<A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                             (int)smem);                                                      \
+        k_spmv_tma<A, R><<<grid, kTmaThreads, smem, st>>>(k, cap, stages);                   \
+    } while (0)
+        if (sa.advanced) {
+            if (nred == 0) TMA_LAUNCH(true, 0);
+            else if (nred == 1) TMA_LAUNCH(true, 1);
+            else TMA_LAUNCH(true, 2);
+        } else {
+            if (nred == 0) TMA_LAUNCH(false, 0);
+            else if (nred == 1) TMA_LAUNCH(false, 1);
+            else TMA_LAUNCH(false, 2);
+        }
+#undef TMA_LAUNCH
     } else if (variant == 2) {
         const int grid = (ctx->n + 255) / 256;
         DISPATCH(k_spmv_scalar, grid, 256, 0);

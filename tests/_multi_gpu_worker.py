@@ -19,7 +19,8 @@ CASES = {
     "pressure_cg_bj4": (lambda p: cases.pressure_3d(12, p), "GKOCG", "BJ", 4, 1e-9),
     "momentum_bicgstab": (lambda p: cases.momentum_3d(14, p), "GKOBiCGStab", "BJ", 1, 1e-10),
     "channel_gmres": (lambda p: cases.channel((16, 8, 8), p), "GKOGMRES", "BJ", 1, 1e-8),
-    "cavity_cg_none": (lambda p: cases.cavity_2d(p), "GKOCG", "none", 1, 1e-8),
+    # all-Neumann + one reference cell: nearly singular, so solve tighter than the L2 bar
+    "cavity_cg_none": (lambda p: cases.cavity_2d(p), "GKOCG", "none", 1, 1e-11),
 }
 
 
