@@ -32,6 +32,8 @@ namespace ogl {
 constexpr int kRowsPerBlock = 256;
 constexpr int kStreamThreads = 256;
 constexpr int kStreamSmemMax = 96 * 1024;
+constexpr int kBatch = 8;            // entries per thread requested at once (7-pt rows: 7)
+constexpr int kStreamCtasPerSM = 5;  // <= 51 registers per thread
 
 struct SpmvK {
     const label *row_ptrs;
@@ -60,7 +62,7 @@ __device__ __forceinline__ double prod_of(double v, double xv, double alpha, boo
 }
 
 template <bool ADV, int NRED>
-__global__ void __launch_bounds__(kStreamThreads, 8)
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSM)
 k_spmv_stream(const SpmvK a)
 {
     if (a.guard_done && a.state->done) return;
@@ -82,25 +84,32 @@ k_spmv_stream(const SpmvK a)
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
         }
-        // ---- stream the slice: coalesced value/column loads, gathered x
-        label k = s + tid;
-        for (; k + 3 * kStreamThreads < e; k += 4 * kStreamThreads) {
-            label c[4];
-            double v[4], xv[4];
+        // ---- stream the slice: coalesced value/column loads, gathered x.
+        // All of a thread's entries of the slice are requested in ONE batch
+        // (kBatch independent loads of columns, of values, then of x), so a row
+        // block costs one HBM round trip plus one L2 round trip instead of one
+        // pair per entry.
+        const label len = e - s;
+        for (label base = 0; base < len; base += kBatch * kStreamThreads) {
+            label c[kBatch];
+            double v[kBatch], xv[kBatch];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) c[u] = __ldcs(&a.cols[k + u * kStreamThreads]);
+            for (int u = 0; u < kBatch; ++u) {
+                const label q = base + tid + u * kStreamThreads;
+                c[u] = q < len ? __ldcs(&a.cols[s + q]) : -1;
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = __ldcs(&a.vals[k + u * kStreamThreads]);
+            for (int u = 0; u < kBatch; ++u) {
+                const label q = base + tid + u * kStreamThreads;
+                v[u] = q < len ? __ldcs(&a.vals[s + q]) : 0.0;
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xv[u] = __ldg(&a.x[c[u]]);
+            for (int u = 0; u < kBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                prod[k - s + u * kStreamThreads] = prod_of(v[u], xv[u], a.alpha, ADV);
-        }
-        for (; k < e; k += kStreamThreads) {
-            const label c = __ldcs(&a.cols[k]);
-            const double v = __ldcs(&a.vals[k]);
-            prod[k - s] = prod_of(v, __ldg(&a.x[c]), a.alpha, ADV);
+            for (int u = 0; u < kBatch; ++u) {
+                const label q = base + tid + u * kStreamThreads;
+                if (q < len) prod[q] = prod_of(v[u], xv[u], a.alpha, ADV);
+            }
         }
         __syncthreads();
         // ---- one thread per row: left-to-right sum of its products
@@ -269,6 +278,7 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
                 tma::bulk_load(base + vals_bytes + cols_bytes, a.row_ptrs + r0, rp_bytes, &full[st], pol);
             }
         }
+        __syncwarp();   // reconverge the producer warp before the block-wide reduction
     } else {
         // ===== consumers: 256 threads =====
         int i = 0;
@@ -283,21 +293,20 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
             const label s = hdr[st].s, e = hdr[st].e, s_al = hdr[st].s_al;
             const label r0 = hdr[st].r0, nr = hdr[st].nr;
             const label off = s - s_al, len = e - s;
-            // products in place: v[k] <- v[k] * x[c[k]]
-            label k = tid;
-            for (; k + 3 * kStreamThreads < len; k += 4 * kStreamThreads) {
-                double xv[4];
+            // products in place: v[k] <- v[k] * x[c[k]]; all x gathers of the
+            // thread are in flight together (one L2 round trip per row block)
+            for (label base = 0; base < len; base += kBatch * kStreamThreads) {
+                double xv[kBatch];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) xv[u] = __ldg(&a.x[c[off + k + u * kStreamThreads]]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const label q = off + k + u * kStreamThreads;
-                    v[q] = prod_of(v[q], xv[u], a.alpha, ADV);
+                for (int u = 0; u < kBatch; ++u) {
+                    const label q = base + tid + u * kStreamThreads;
+                    xv[u] = q < len ? __ldg(&a.x[c[off + q]]) : 0.0;
                 }
-            }
-            for (; k < len; k += kStreamThreads) {
-                const label q = off + k;
-                v[q] = prod_of(v[q], __ldg(&a.x[c[q]]), a.alpha, ADV);
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const label q = base + tid + u * kStreamThreads;
+                    if (q < len) v[off + q] = prod_of(v[off + q], xv[u], a.alpha, ADV);
+                }
             }
             tma::consumer_sync();
             if (tid < nr) {
@@ -535,7 +544,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         }
         const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
         k.n_row_blocks = nblk;
-        const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 8;
+        const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
         const int grid = nblk < cap ? nblk : (int)cap;
         DISPATCH(k_spmv_stream, grid, kStreamThreads, smem);
     } else if (variant == 4) {

@@ -156,6 +156,17 @@ def test_graph_and_stream_paths_agree(ctx):
         assert n_it == res[0][0] and np.array_equal(x, res[0][1])
 
 
+def test_cg_with_every_spmv_kernel(ctx, oracle):
+    s = cases.pressure_3d(20)[0]
+    outs = []
+    for variant in (1, 2, 3, 4):
+        ctx.set_option("spmv_variant", variant)
+        r, o, x = check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", tolerance=1e-9)
+        outs.append(r.n_iterations)
+    ctx.set_option("spmv_variant", 0)
+    assert max(outs) - min(outs) <= ITER_TOL
+
+
 def test_full_size_pressure_solve_properties(ctx):
     # BASELINE configs[1]: 100^3 GKOCG + BJ; oracle-free properties at full size
     s = cases.pressure_3d(100)[0]

@@ -28,9 +28,10 @@ def main():
         nnz = ctx.nnz
         b_spmv = 12 * nnz + 4 * (s.n + 1) + 16 * s.n
         b_pcg = 12 * nnz + 4 * (s.n + 1) + 96 * s.n
-        for variant, ctas in itertools.product((1, 2, 4), (0, 148 * 4, 148 * 6, 148 * 12, 148 * 16)):
-            if variant == 2 and ctas:
+        for variant, ctas, stages in itertools.product((1, 4), (0, 148 * 3, 148 * 4, 148 * 6, 148 * 8), (2, 3)):
+            if variant == 1 and stages != 3:
                 continue
+            ctx.set_option("tma_stages", stages)
             try:
                 ctx.set_option("spmv_variant", variant)
                 ctx.set_option("stream_ctas", ctas)
@@ -40,13 +41,13 @@ def main():
             reps = 100
             t0 = ctx.spmv_bench(reps, False) / reps * 1e3
             t1 = ctx.spmv_bench(reps, True) / reps * 1e3
-            row = dict(n=n, variant=variant, ctas=ctas, spmv_us=round(t0, 2), fused_us=round(t1, 2),
+            row = dict(n=n, variant=variant, ctas=ctas, stages=stages, spmv_us=round(t0, 2), fused_us=round(t1, 2),
                        spmv_gbs=round(b_spmv / t0 / 1e3, 1), fused_gbs=round(b_spmv / t1 / 1e3, 1))
             print(json.dumps(row), flush=True)
             out.append(row)
         ctx.set_option("spmv_variant", 0)
         ctx.set_option("stream_ctas", 0)
-        for blocks, graph, chunk in itertools.product((148 * 2, 148 * 4, 148 * 8), (1, 0), (16, 64)):
+        for blocks, graph, chunk in itertools.product((148 * 4,), (1,), (16,)):
             ctx.set_option("blas1_blocks", blocks)
             ctx.set_option("use_graph", graph)
             ctx.set_option("chunk_iters", chunk)
