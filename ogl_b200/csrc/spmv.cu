@@ -34,6 +34,7 @@ constexpr int kStreamThreads = 256;
 constexpr int kStreamSmemMax = 96 * 1024;
 constexpr int kBatch = 8;            // entries per thread requested at once (7-pt rows: 7)
 constexpr int kStreamCtasPerSM = 5;  // <= 51 registers per thread
+constexpr int kMaxTilesPerCta = 1024; // row-block extents cached in shared memory
 
 struct SpmvK {
     const label *row_ptrs;
@@ -71,18 +72,35 @@ k_spmv_stream(const SpmvK a)
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
-    // persistent CTAs: a fixed grid (8 per SM) walks the row blocks, so a fused
-    // reduction leaves gridDim.x partials whatever the matrix size
-    for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x) {
+    // persistent CTAs: a fixed grid walks the row blocks, so a fused reduction
+    // leaves gridDim.x partials whatever the matrix size.  The extents of all of
+    // this CTA's row blocks are fetched once up front (otherwise every block
+    // starts with a dependent round trip for row_ptrs[r0]).
+    __shared__ label ext[2 * kMaxTilesPerCta];
+    {
+        int i = tid;
+        for (label rb = blockIdx.x + (label)tid * gridDim.x; rb < a.n_row_blocks && i < kMaxTilesPerCta;
+             rb += (label)kStreamThreads * gridDim.x, i += kStreamThreads) {
+            const label r0 = rb * kRowsPerBlock;
+            ext[2 * i] = __ldg(&a.row_ptrs[r0]);
+            ext[2 * i + 1] = __ldg(&a.row_ptrs[min(r0 + (label)kRowsPerBlock, a.n)]);
+        }
+    }
+    __syncthreads();
+    int it = 0;
+    for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x, ++it) {
         const label r0 = rb * kRowsPerBlock;
         const label nr = min((label)kRowsPerBlock, a.n - r0);
-        const label s = __ldg(&a.row_ptrs[r0]);
-        const label e = __ldg(&a.row_ptrs[r0 + nr]);
-        // row extents of "my" row: issued early, consumed after the barrier
+        const label s = it < kMaxTilesPerCta ? ext[2 * it] : __ldg(&a.row_ptrs[r0]);
+        const label e = it < kMaxTilesPerCta ? ext[2 * it + 1] : __ldg(&a.row_ptrs[r0 + nr]);
+        // per-row operands of "my" row: issued early, consumed after the barrier
         label rs = 0, re = 0;
+        double dw = 0.0, yin = 0.0;
         if (tid < nr) {
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
+            if (NRED >= 1) dw = a.dot_with[r0 + tid];
+            if (ADV) yin = a.y_in[r0 + tid];
         }
         // ---- stream the slice: coalesced value/column loads, gathered x.
         // All of a thread's entries of the slice are requested in ONE batch
@@ -115,10 +133,10 @@ k_spmv_stream(const SpmvK a)
         // ---- one thread per row: left-to-right sum of its products
         if (tid < nr) {
             const label row = r0 + tid;
-            double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+            double sum = ADV ? __dmul_rn(a.beta, yin) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
             a.y[row] = sum;
-            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
             if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
         }
         __syncthreads();   // prod is overwritten by the next row block
@@ -242,6 +260,18 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
         tma::fence_barrier_init();
         tma::fence_proxy_async();
     }
+    // extents of this CTA's row blocks, fetched once by all threads: the single
+    // producer lane must not pay a global round trip per block
+    __shared__ label ext[2 * kMaxTilesPerCta];
+    {
+        int i = tid;
+        for (label rb = blockIdx.x + (label)tid * gridDim.x; rb < a.n_row_blocks && i < kMaxTilesPerCta;
+             rb += (label)kTmaThreads * gridDim.x, i += kTmaThreads) {
+            const label r0 = rb * kRowsPerBlock;
+            ext[2 * i] = __ldg(&a.row_ptrs[r0]);
+            ext[2 * i + 1] = __ldg(&a.row_ptrs[min(r0 + (label)kRowsPerBlock, a.n)]);
+        }
+    }
     __syncthreads();
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
@@ -258,8 +288,8 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
                 if (round > 0) tma::mbar_wait(&empty[st], (round - 1) & 1);
                 const label r0 = rb * kRowsPerBlock;
                 const label nr = min((label)kRowsPerBlock, a.n - r0);
-                const label s = __ldg(&a.row_ptrs[r0]);
-                const label e = __ldg(&a.row_ptrs[r0 + nr]);
+                const label s = i < kMaxTilesPerCta ? ext[2 * i] : __ldg(&a.row_ptrs[r0]);
+                const label e = i < kMaxTilesPerCta ? ext[2 * i + 1] : __ldg(&a.row_ptrs[r0 + nr]);
                 const label s_al = s & ~3;                  // 32 B (values) / 16 B (columns) aligned
                 const label cnt = ((e + 3) & ~3) - s_al;
                 const uint32_t rp_bytes = (uint32_t)(((nr + 1) * sizeof(label) + 15) & ~15u);
@@ -293,6 +323,11 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
             const label s = hdr[st].s, e = hdr[st].e, s_al = hdr[st].s_al;
             const label r0 = hdr[st].r0, nr = hdr[st].nr;
             const label off = s - s_al, len = e - s;
+            double dw = 0.0, yin = 0.0;
+            if (tid < nr) {
+                if (NRED >= 1) dw = a.dot_with[r0 + tid];
+                if (ADV) yin = a.y_in[r0 + tid];
+            }
             // products in place: v[k] <- v[k] * x[c[k]]; all x gathers of the
             // thread are in flight together (one L2 round trip per row block)
             for (label base = 0; base < len; base += kBatch * kStreamThreads) {
@@ -311,11 +346,11 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
             tma::consumer_sync();
             if (tid < nr) {
                 const label row = r0 + tid;
-                double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+                double sum = ADV ? __dmul_rn(a.beta, yin) : 0.0;
                 const label qe = rp[tid + 1] - s_al;
                 for (label q = rp[tid] - s_al; q < qe; ++q) sum = __dadd_rn(sum, v[q]);
                 a.y[row] = sum;
-                if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
+                if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
                 if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
             }
             // generic-proxy writes to the stage must be ordered before the next

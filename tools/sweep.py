@@ -28,7 +28,7 @@ def main():
         nnz = ctx.nnz
         b_spmv = 12 * nnz + 4 * (s.n + 1) + 16 * s.n
         b_pcg = 12 * nnz + 4 * (s.n + 1) + 96 * s.n
-        for variant, ctas, stages in itertools.product((1, 4), (0, 148 * 3, 148 * 4, 148 * 6, 148 * 8), (2, 3)):
+        for variant, ctas, stages in itertools.product((1, 4), (0, 148 * 3, 148 * 4, 148 * 5), (2, 3, 4)):
             if variant == 1 and stages != 3:
                 continue
             ctx.set_option("tma_stages", stages)
