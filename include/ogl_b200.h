@@ -191,6 +191,10 @@ int ogl_spmv_bench(ogl_ctx *ctx, int32_t reps, int fused_dot, float *ms);
  * (roofline measurement of the whole iteration), timed with CUDA events. */
 int ogl_pcg_bench(ogl_ctx *ctx, int32_t iters, float *ms);
 int ogl_synchronize(ogl_ctx *ctx);
+/* HBM calibration kernels (roofline context for the numbers above), timed with
+ * CUDA events; *gbs = bytes moved / time.  mode 0: copy (read + write, 128-bit),
+ * 1: read-only sum, 2: read-only 8 B + 4 B streams (values + columns like CSR). */
+int ogl_membench(ogl_ctx *ctx, int mode, int64_t n_doubles, int32_t reps, double *gbs);
 
 /* ---- Matrix-Market export ---------------------------------------
  * replaces export_mtx / export_vec (common/common.C:31-58,

@@ -197,6 +197,11 @@ class Context:
         self._check(self.lib.ogl_pcg_bench(self.h, iters, C.byref(ms)))
         return ms.value
 
+    def membench(self, mode: int, n_doubles: int = 1 << 27, reps: int = 10) -> float:
+        g = C.c_double(0)
+        self._check(self.lib.ogl_membench(self.h, mode, n_doubles, reps, C.byref(g)))
+        return g.value
+
     def synchronize(self):
         self._check(self.lib.ogl_synchronize(self.h))
 

@@ -131,6 +131,43 @@ static void destroy(Context *c)
 
 using namespace ogl;
 
+namespace {
+
+__global__ void __launch_bounds__(256, 8) k_mb_copy(const double2 *__restrict__ in,
+                                                    double2 *__restrict__ out, int64_t n2)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+
+__global__ void __launch_bounds__(256, 8) k_mb_read(const double2 *__restrict__ in, int64_t n2,
+                                                    double *sink)
+{
+    double acc = 0.0;
+#pragma unroll 4
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = in[i];
+        acc += v.x + v.y;
+    }
+    if (acc == 1.2345e-300) *sink = acc;
+}
+
+__global__ void __launch_bounds__(256, 8) k_mb_read2(const double *__restrict__ a,
+                                                     const int *__restrict__ b, int64_t n,
+                                                     double *sink)
+{
+    double acc = 0.0;
+#pragma unroll 4
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        acc += a[i] + (double)b[i];
+    if (acc == 1.2345e-300) *sink = acc;
+}
+
+}  // namespace
+
 #define CHECK_CTX(ctx)                                                      \
     do {                                                                    \
         if (!(ctx)) {                                                       \
@@ -526,6 +563,45 @@ int ogl_pcg_bench(ogl_ctx *ctx, int32_t iters, float *ms)
     ogl_solve_result r;
     OGL_TRY(solve(ctx, &p, &r));
     *ms = (float)(r.solve_us * 1e-3);
+    return OGL_OK;
+}
+
+int ogl_membench(ogl_ctx *ctx, int mode, int64_t n_doubles, int32_t reps, double *gbs)
+{
+    CHECK_CTX(ctx);
+    if (mode < 0 || mode > 2 || n_doubles < 1024 || reps < 1 || !gbs)
+        return fail(ctx, OGL_ERR_INVALID, "ogl_membench: bad arguments");
+    double *a = nullptr, *b = nullptr;
+    OGL_TRY(dev_alloc(ctx, &a, (size_t)n_doubles));
+    OGL_TRY(dev_alloc(ctx, &b, (size_t)n_doubles));
+    cudaMemsetAsync(a, 0, sizeof(double) * n_doubles, ctx->stream);
+    cudaMemsetAsync(b, 0, sizeof(double) * n_doubles, ctx->stream);
+    const int grid = kNumSM * 8;
+    double bytes = 0;
+    for (int r = -2; r < reps; ++r) {
+        if (r == 0) cudaEventRecord(ctx->ev_t0, ctx->stream);
+        if (mode == 0) {
+            k_mb_copy<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const double2 *>(a),
+                                                     reinterpret_cast<double2 *>(b), n_doubles / 2);
+            bytes = 16.0 * (double)(n_doubles / 2) * 2;
+        } else if (mode == 1) {
+            k_mb_read<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const double2 *>(a),
+                                                     n_doubles / 2, b);
+            bytes = 16.0 * (double)(n_doubles / 2);
+        } else {
+            k_mb_read2<<<grid, 256, 0, ctx->stream>>>(a, reinterpret_cast<const int *>(b), n_doubles,
+                                                      b + n_doubles / 2 + 8);
+            bytes = 12.0 * (double)n_doubles;
+        }
+    }
+    cudaEventRecord(ctx->ev_t1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1);
+    cudaFree(a);
+    cudaFree(b);
+    if (e != cudaSuccess) return fail(ctx, OGL_ERR_CUDA, std::string("membench: ") + cudaGetErrorString(e));
+    *gbs = bytes * reps / (ms * 1e-3) / 1e9;
     return OGL_OK;
 }
 

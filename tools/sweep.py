@@ -26,6 +26,9 @@ def main():
         ctx.vector_fill(L.OGL_VEC_X, 0.0)
         ctx.precond_setup(L.OGL_PRECOND_BJ, 1)
         nnz = ctx.nnz
+        print(json.dumps(dict(n=n, hbm_copy_gbs=round(ctx.membench(0), 1),
+                              hbm_read_gbs=round(ctx.membench(1), 1),
+                              hbm_read_8p4_gbs=round(ctx.membench(2), 1))), flush=True)
         b_spmv = 12 * nnz + 4 * (s.n + 1) + 16 * s.n
         b_pcg = 12 * nnz + 4 * (s.n + 1) + 96 * s.n
         for variant, ctas, stages in itertools.product((1, 4), (0, 148 * 3, 148 * 4, 148 * 5), (2, 3, 4)):
