@@ -106,6 +106,7 @@ struct Context {
     label *d_rows = nullptr, *d_cols = nullptr, *d_map = nullptr, *d_row_ptrs = nullptr;
     label max_row_len = 0;
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
+    int64_t max_warp_nnz = 0;    // warp-tile kernel: max nnz of 32 consecutive rows
 
     // partition (a6/a11)
     bool have_partition = false;

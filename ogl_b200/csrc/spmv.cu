@@ -72,35 +72,18 @@ k_spmv_stream(const SpmvK a)
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
-    // persistent CTAs: a fixed grid walks the row blocks, so a fused reduction
-    // leaves gridDim.x partials whatever the matrix size.  The extents of all of
-    // this CTA's row blocks are fetched once up front (otherwise every block
-    // starts with a dependent round trip for row_ptrs[r0]).
-    __shared__ label ext[2 * kMaxTilesPerCta];
-    {
-        int i = tid;
-        for (label rb = blockIdx.x + (label)tid * gridDim.x; rb < a.n_row_blocks && i < kMaxTilesPerCta;
-             rb += (label)kStreamThreads * gridDim.x, i += kStreamThreads) {
-            const label r0 = rb * kRowsPerBlock;
-            ext[2 * i] = __ldg(&a.row_ptrs[r0]);
-            ext[2 * i + 1] = __ldg(&a.row_ptrs[min(r0 + (label)kRowsPerBlock, a.n)]);
-        }
-    }
-    __syncthreads();
-    int it = 0;
-    for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x, ++it) {
+    // persistent CTAs: a fixed grid (8 per SM) walks the row blocks, so a fused
+    // reduction leaves gridDim.x partials whatever the matrix size
+    for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x) {
         const label r0 = rb * kRowsPerBlock;
         const label nr = min((label)kRowsPerBlock, a.n - r0);
-        const label s = it < kMaxTilesPerCta ? ext[2 * it] : __ldg(&a.row_ptrs[r0]);
-        const label e = it < kMaxTilesPerCta ? ext[2 * it + 1] : __ldg(&a.row_ptrs[r0 + nr]);
-        // per-row operands of "my" row: issued early, consumed after the barrier
+        const label s = __ldg(&a.row_ptrs[r0]);
+        const label e = __ldg(&a.row_ptrs[r0 + nr]);
+        // row extents of "my" row: issued early, consumed after the barrier
         label rs = 0, re = 0;
-        double dw = 0.0, yin = 0.0;
         if (tid < nr) {
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
-            if (NRED >= 1) dw = a.dot_with[r0 + tid];
-            if (ADV) yin = a.y_in[r0 + tid];
         }
         // ---- stream the slice: coalesced value/column loads, gathered x.
         // All of a thread's entries of the slice are requested in ONE batch
@@ -133,10 +116,10 @@ k_spmv_stream(const SpmvK a)
         // ---- one thread per row: left-to-right sum of its products
         if (tid < nr) {
             const label row = r0 + tid;
-            double sum = ADV ? __dmul_rn(a.beta, yin) : 0.0;
+            double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
             a.y[row] = sum;
-            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
             if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
         }
         __syncthreads();   // prod is overwritten by the next row block
@@ -365,6 +348,94 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
                                            a.inline_epi != 0, a.ea);
 }
 
+// ---------------------------------------------------------------------------
+// Variant 5: warp-synchronous stream.  Same arithmetic as variant 1, but the
+// unit of work is one WARP x 32 rows: no CTA-wide barrier, so the 40 resident
+// warps of an SM drift apart and overlap each other's load / gather / add
+// phases; the row pointers of the NEXT tile are prefetched while the current
+// one is processed, so a tile costs one HBM round trip (columns + values, all
+// requested at once) plus one L2 round trip (x).
+// ---------------------------------------------------------------------------
+constexpr int kWarpRows = 32;
+constexpr int kWarpCtaThreads = 128;   // 4 independent warps per CTA
+constexpr int kWarpCtasPerSM = 8;      // 32 warps per SM, <= 64 registers per thread
+
+template <bool ADV, int NRED>
+__global__ void __launch_bounds__(kWarpCtaThreads, kWarpCtasPerSM)
+k_spmv_warp(const SpmvK a, const int warp_cap)
+{
+    if (a.guard_done && a.state->done) return;
+    extern __shared__ double prod_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *prod = prod_all + (size_t)warp * warp_cap;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    const label n_tiles = (a.n + kWarpRows - 1) / kWarpRows;
+    const label stride = gridDim.x * (kWarpCtaThreads / 32);
+    label tile = blockIdx.x * (kWarpCtaThreads / 32) + warp;
+    // row pointers of the first tile
+    label rs = 0, re = 0;
+    if (tile < n_tiles) {
+        const label row = min(tile * kWarpRows + lane, a.n - 1);
+        rs = __ldg(&a.row_ptrs[row]);
+        re = __ldg(&a.row_ptrs[row + 1]);
+    }
+    for (; tile < n_tiles; tile += stride) {
+        const label r0 = tile * kWarpRows;
+        const label nr = min((label)kWarpRows, a.n - r0);
+        const label s = __shfl_sync(0xffffffffu, rs, 0);
+        const label e = __shfl_sync(0xffffffffu, re, nr - 1);
+        const label my_rs = rs, my_re = re;
+        // prefetch the next tile's row pointers
+        const label nxt = tile + stride;
+        if (nxt < n_tiles) {
+            const label row = min(nxt * kWarpRows + lane, a.n - 1);
+            rs = __ldg(&a.row_ptrs[row]);
+            re = __ldg(&a.row_ptrs[row + 1]);
+        }
+        double dw = 0.0, yin = 0.0;
+        if (lane < nr) {
+            if (NRED >= 1) dw = a.dot_with[r0 + lane];
+            if (ADV) yin = a.y_in[r0 + lane];
+        }
+        const label len = e - s;
+        for (label base = 0; base < len; base += kBatch * 32) {
+            label c[kBatch];
+            double v[kBatch], xv[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const label q = base + lane + u * 32;
+                c[u] = q < len ? __ldcs(&a.cols[s + q]) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const label q = base + lane + u * 32;
+                v[u] = q < len ? __ldcs(&a.vals[s + q]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const label q = base + lane + u * 32;
+                if (q < len) prod[q] = prod_of(v[u], xv[u], a.alpha, ADV);
+            }
+        }
+        __syncwarp();
+        if (lane < nr) {
+            double sum = ADV ? __dmul_rn(a.beta, yin) : 0.0;
+            for (label q = my_rs - s; q < my_re - s; ++q) sum = __dadd_rn(sum, prod[q]);
+            a.y[r0 + lane] = sum;
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
+            if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+        }
+        __syncwarp();
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
 template <bool ADV, int NRED>
 __global__ void __launch_bounds__(256) k_spmv_scalar(const SpmvK a)
 {
@@ -461,12 +532,13 @@ __global__ void __launch_bounds__(256) k_spmv_nonlocal(const NonLocalK a)
                                            a.inline_epi != 0, a.ea, /*accumulate=*/true);
 }
 
-__global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int *out)
+__global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int rows_per_block,
+                                int *out)
 {
     const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t r0 = b * kRowsPerBlock;
+    const int64_t r0 = b * rows_per_block;
     if (r0 < n) {
-        const int64_t r1 = r0 + kRowsPerBlock < n ? r0 + kRowsPerBlock : n;
+        const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
         atomicMax(out, row_ptrs[r1] - row_ptrs[r0]);
     }
 }
@@ -493,19 +565,25 @@ int spmv_setup(Context *ctx)
 {
     // largest slice any kRowsPerBlock-row CTA would have to park in shared memory
     int *d_max = nullptr;
-    OGL_CUDA(ctx, cudaMalloc(&d_max, sizeof(int)));
-    cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream);
+    OGL_CUDA(ctx, cudaMalloc(&d_max, 2 * sizeof(int)));
+    cudaMemsetAsync(d_max, 0, 2 * sizeof(int), ctx->stream);
     const int64_t nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
-    if (nblk > 0)
+    const int64_t nwt = (ctx->n + kWarpRows - 1) / kWarpRows;
+    if (nblk > 0) {
         k_block_nnz_max<<<(int)((nblk + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->n, ctx->d_row_ptrs, d_max);
-    int mx = 0;
-    cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+            ctx->n, ctx->d_row_ptrs, kRowsPerBlock, d_max);
+        k_block_nnz_max<<<(int)((nwt + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->n, ctx->d_row_ptrs, kWarpRows, d_max + 1);
+    }
+    int mx2[2] = {0, 0};
+    int &mx = mx2[0];
+    cudaMemcpyAsync(mx2, d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_max);
     if (e != cudaSuccess)
         return fail(ctx, OGL_ERR_CUDA, std::string("spmv_setup: ") + cudaGetErrorString(e));
     ctx->max_block_nnz = mx;
+    ctx->max_warp_nnz = mx2[1];
     // reduction scratch sized for the largest grid any kernel of the library uses
     int64_t max_grid = nblk;
     const int64_t vec_grid = ((int64_t)ctx->n * 32 + 255) / 256;
@@ -517,7 +595,7 @@ int spmv_setup(Context *ctx)
 
 static int pick_variant(const Context *ctx)
 {
-    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 4) return (int)ctx->spmv_variant;
+    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 5) return (int)ctx->spmv_variant;
     const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
     const double mean_len = ctx->n > 0 ? (double)ctx->nnz / ctx->n : 0.0;
     // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
@@ -582,6 +660,34 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
         const int grid = nblk < cap ? nblk : (int)cap;
         DISPATCH(k_spmv_stream, grid, kStreamThreads, smem);
+    } else if (variant == 5) {
+        const int warp_cap = (int)((ctx->max_warp_nnz + 1) & ~(int64_t)1);
+        const size_t smem = (size_t)warp_cap * sizeof(double) * (kWarpCtaThreads / 32);
+        if (smem > (size_t)kStreamSmemMax)
+            return fail(ctx, OGL_ERR_UNSUPPORTED, "rows too long for the warp-tile SpMV");
+        static bool attr5 = false;
+        if (!attr5) {
+            cudaFuncSetAttribute(k_spmv_warp<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_warp<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_warp<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_warp<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_warp<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_warp<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            attr5 = true;
+        }
+        const int64_t n_tiles = (ctx->n + kWarpRows - 1) / kWarpRows;
+        const int64_t need = (n_tiles + (kWarpCtaThreads / 32) - 1) / (kWarpCtaThreads / 32);
+        const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kWarpCtasPerSM;
+        const int grid = (int)(need < cap ? need : cap);
+        if (sa.advanced) {
+            if (nred == 0) k_spmv_warp<true, 0><<<grid, kWarpCtaThreads, smem, st>>>(k, warp_cap);
+            else if (nred == 1) k_spmv_warp<true, 1><<<grid, kWarpCtaThreads, smem, st>>>(k, warp_cap);
+            else k_spmv_warp<true, 2><<<grid, kWarpCtaThreads, smem, st>>>(k, warp_cap);
+        } else {
+            if (nred == 0) k_spmv_warp<false, 0><<<grid, kWarpCtaThreads, smem, st>>>(k, warp_cap);
+            else if (nred == 1) k_spmv_warp<false, 1><<<grid, kWarpCtaThreads, smem, st>>>(k, warp_cap);
+            else k_spmv_warp<false, 2><<<grid, kWarpCtaThreads, smem, st>>>(k, warp_cap);
+        }
     } else if (variant == 4) {
         const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
         k.n_row_blocks = nblk;

@@ -31,8 +31,10 @@ def main():
                               hbm_read_8p4_gbs=round(ctx.membench(2), 1))), flush=True)
         b_spmv = 12 * nnz + 4 * (s.n + 1) + 16 * s.n
         b_pcg = 12 * nnz + 4 * (s.n + 1) + 96 * s.n
-        for variant, ctas, stages in itertools.product((1, 4), (0, 148 * 3, 148 * 4, 148 * 5), (2, 3, 4)):
-            if variant == 1 and stages != 3:
+        for variant, ctas, stages in itertools.product((1, 5, 4), (0, 148 * 4, 148 * 6, 148 * 8), (2, 3)):
+            if variant != 4 and stages != 3:
+                continue
+            if variant == 4 and ctas > 148 * 4:
                 continue
             ctx.set_option("tma_stages", stages)
             try:
