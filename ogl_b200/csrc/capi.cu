@@ -303,6 +303,8 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->use_graph = value != 0;
     } else if (k == "profile_stride") {
         ctx->profile_stride = value < 0 ? 0 : value;
+    } else if (k == "tile_blocked") {
+        ctx->tile_blocked = value != 0;
     } else if (k == "tma_stages") {
         if (value < 1 || value > 4) return fail(ctx, OGL_ERR_INVALID, "tma_stages in [1,4]");
         ctx->tma_stages = value;
@@ -335,6 +337,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "blas1_blocks") *value = ctx->blas1_blocks;
     else if (k == "stream_ctas") *value = ctx->stream_ctas;
     else if (k == "tma_stages") *value = ctx->tma_stages;
+    else if (k == "tile_blocked") *value = ctx->tile_blocked;
     else if (k == "max_row_len") *value = ctx->max_row_len;
     else if (k == "max_block_nnz") *value = ctx->max_block_nnz;
     else if (k == "launches") *value = ctx->launches;

@@ -33,6 +33,7 @@ constexpr int kRowsPerBlock = 256;
 constexpr int kStreamThreads = 256;
 constexpr int kStreamSmemMax = 96 * 1024;
 constexpr int kBatch = 8;            // entries per thread requested at once (7-pt rows: 7)
+constexpr int kBatchStream = 7;      // stream kernel: 48-register budget (5 CTAs per SM)
 constexpr int kStreamCtasPerSM = 5;  // <= 51 registers per thread
 constexpr int kMaxTilesPerCta = 1024; // row-block extents cached in shared memory
 
@@ -45,6 +46,7 @@ struct SpmvK {
     double *y;
     label n;
     label n_row_blocks;   // stream kernel: ceil(n / kRowsPerBlock)
+    int blocked;          // 1: each CTA walks a CONTIGUOUS range of tiles (x reuse in L1)
     double alpha, beta;
     const double *dot_with;
     double *partials;
@@ -62,6 +64,24 @@ __device__ __forceinline__ double prod_of(double v, double xv, double alpha, boo
     return adv ? __dmul_rn(__dmul_rn(alpha, v), xv) : __dmul_rn(v, xv);
 }
 
+
+// tile range of a persistent CTA (or warp): strided over the grid, or one
+// contiguous chunk per worker so that consecutive tiles reuse x lines in L1
+__device__ __forceinline__ void tile_range(int blocked, label worker, label n_workers,
+                                           label n_tiles, label &first, label &last, label &step)
+{
+    if (blocked) {
+        const label per = (n_tiles + n_workers - 1) / n_workers;
+        first = worker * per;
+        last = min(first + per, n_tiles);
+        step = 1;
+    } else {
+        first = worker;
+        last = n_tiles;
+        step = n_workers;
+    }
+}
+
 template <bool ADV, int NRED>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSM)
 k_spmv_stream(const SpmvK a)
@@ -74,7 +94,9 @@ k_spmv_stream(const SpmvK a)
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
     // persistent CTAs: a fixed grid (8 per SM) walks the row blocks, so a fused
     // reduction leaves gridDim.x partials whatever the matrix size
-    for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x) {
+    label t_first, t_last, t_step;
+    tile_range(a.blocked, blockIdx.x, gridDim.x, a.n_row_blocks, t_first, t_last, t_step);
+    for (label rb = t_first; rb < t_last; rb += t_step) {
         const label r0 = rb * kRowsPerBlock;
         const label nr = min((label)kRowsPerBlock, a.n - r0);
         const label s = __ldg(&a.row_ptrs[r0]);
@@ -87,27 +109,27 @@ k_spmv_stream(const SpmvK a)
         }
         // ---- stream the slice: coalesced value/column loads, gathered x.
         // All of a thread's entries of the slice are requested in ONE batch
-        // (kBatch independent loads of columns, of values, then of x), so a row
+        // (kBatchStream independent loads of columns, of values, then of x), so a row
         // block costs one HBM round trip plus one L2 round trip instead of one
         // pair per entry.
         const label len = e - s;
-        for (label base = 0; base < len; base += kBatch * kStreamThreads) {
-            label c[kBatch];
-            double v[kBatch], xv[kBatch];
+        for (label base = 0; base < len; base += kBatchStream * kStreamThreads) {
+            label c[kBatchStream];
+            double v[kBatchStream], xv[kBatchStream];
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
+            for (int u = 0; u < kBatchStream; ++u) {
                 const label q = base + tid + u * kStreamThreads;
                 c[u] = q < len ? __ldcs(&a.cols[s + q]) : -1;
             }
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
+            for (int u = 0; u < kBatchStream; ++u) {
                 const label q = base + tid + u * kStreamThreads;
                 v[u] = q < len ? __ldcs(&a.vals[s + q]) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+            for (int u = 0; u < kBatchStream; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
+            for (int u = 0; u < kBatchStream; ++u) {
                 const label q = base + tid + u * kStreamThreads;
                 if (q < len) prod[q] = prod_of(v[u], xv[u], a.alpha, ADV);
             }
@@ -246,10 +268,12 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
     // extents of this CTA's row blocks, fetched once by all threads: the single
     // producer lane must not pay a global round trip per block
     __shared__ label ext[2 * kMaxTilesPerCta];
+    label t_first, t_last, t_step;
+    tile_range(a.blocked, blockIdx.x, gridDim.x, a.n_row_blocks, t_first, t_last, t_step);
     {
         int i = tid;
-        for (label rb = blockIdx.x + (label)tid * gridDim.x; rb < a.n_row_blocks && i < kMaxTilesPerCta;
-             rb += (label)kTmaThreads * gridDim.x, i += kTmaThreads) {
+        for (label rb = t_first + (label)tid * t_step; rb < t_last && i < kMaxTilesPerCta;
+             rb += (label)kTmaThreads * t_step, i += kTmaThreads) {
             const label r0 = rb * kRowsPerBlock;
             ext[2 * i] = __ldg(&a.row_ptrs[r0]);
             ext[2 * i + 1] = __ldg(&a.row_ptrs[min(r0 + (label)kRowsPerBlock, a.n)]);
@@ -265,7 +289,7 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
         if (lane == 0) {
             const uint64_t pol = tma::policy_evict_first();
             int i = 0;
-            for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x, ++i) {
+            for (label rb = t_first; rb < t_last; rb += t_step, ++i) {
                 const int st = i % stages;
                 const uint32_t round = (uint32_t)(i / stages);
                 if (round > 0) tma::mbar_wait(&empty[st], (round - 1) & 1);
@@ -295,7 +319,7 @@ k_spmv_tma(const SpmvK a, const int cap, const int stages)
     } else {
         // ===== consumers: 256 threads =====
         int i = 0;
-        for (label rb = blockIdx.x; rb < a.n_row_blocks; rb += gridDim.x, ++i) {
+        for (label rb = t_first; rb < t_last; rb += t_step, ++i) {
             const int st = i % stages;
             const uint32_t round = (uint32_t)(i / stages);
             tma::mbar_wait(&full[st], round & 1);
@@ -372,16 +396,17 @@ k_spmv_warp(const SpmvK a, const int warp_cap)
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
     const label n_tiles = (a.n + kWarpRows - 1) / kWarpRows;
-    const label stride = gridDim.x * (kWarpCtaThreads / 32);
-    label tile = blockIdx.x * (kWarpCtaThreads / 32) + warp;
+    label tile, t_last, stride;
+    tile_range(a.blocked, blockIdx.x * (kWarpCtaThreads / 32) + warp,
+               gridDim.x * (kWarpCtaThreads / 32), n_tiles, tile, t_last, stride);
     // row pointers of the first tile
     label rs = 0, re = 0;
-    if (tile < n_tiles) {
+    if (tile < t_last) {
         const label row = min(tile * kWarpRows + lane, a.n - 1);
         rs = __ldg(&a.row_ptrs[row]);
         re = __ldg(&a.row_ptrs[row + 1]);
     }
-    for (; tile < n_tiles; tile += stride) {
+    for (; tile < t_last; tile += stride) {
         const label r0 = tile * kWarpRows;
         const label nr = min((label)kWarpRows, a.n - r0);
         const label s = __shfl_sync(0xffffffffu, rs, 0);
@@ -389,7 +414,7 @@ k_spmv_warp(const SpmvK a, const int warp_cap)
         const label my_rs = rs, my_re = re;
         // prefetch the next tile's row pointers
         const label nxt = tile + stride;
-        if (nxt < n_tiles) {
+        if (nxt < t_last) {
             const label row = min(nxt * kWarpRows + lane, a.n - 1);
             rs = __ldg(&a.row_ptrs[row]);
             re = __ldg(&a.row_ptrs[row + 1]);
@@ -617,6 +642,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.y = sa.y;
     k.n = ctx->n;
     k.n_row_blocks = 0;
+    k.blocked = ctx->tile_blocked ? 1 : 0;
     k.alpha = sa.alpha;
     k.beta = sa.beta;
     k.dot_with = sa.dot_with;

@@ -31,11 +31,10 @@ def main():
                               hbm_read_8p4_gbs=round(ctx.membench(2), 1))), flush=True)
         b_spmv = 12 * nnz + 4 * (s.n + 1) + 16 * s.n
         b_pcg = 12 * nnz + 4 * (s.n + 1) + 96 * s.n
-        for variant, ctas, stages in itertools.product((1, 5, 4), (0, 148 * 4, 148 * 6, 148 * 8), (2, 3)):
+        for variant, ctas, stages, blocked in itertools.product((1, 5, 4), (0,), (2, 3), (0, 1)):
             if variant != 4 and stages != 3:
                 continue
-            if variant == 4 and ctas > 148 * 4:
-                continue
+            ctx.set_option("tile_blocked", blocked)
             ctx.set_option("tma_stages", stages)
             try:
                 ctx.set_option("spmv_variant", variant)
@@ -46,7 +45,7 @@ def main():
             reps = 100
             t0 = ctx.spmv_bench(reps, False) / reps * 1e3
             t1 = ctx.spmv_bench(reps, True) / reps * 1e3
-            row = dict(n=n, variant=variant, ctas=ctas, stages=stages, spmv_us=round(t0, 2), fused_us=round(t1, 2),
+            row = dict(n=n, variant=variant, blocked=blocked, stages=stages, spmv_us=round(t0, 2), fused_us=round(t1, 2),
                        spmv_gbs=round(b_spmv / t0 / 1e3, 1), fused_gbs=round(b_spmv / t1 / 1e3, 1))
             print(json.dumps(row), flush=True)
             out.append(row)
