@@ -98,7 +98,7 @@ struct Context {
     int64_t blas1_blocks = kNumSM * kBlas1BlocksPerSM;
     int64_t stream_ctas = 0;     // persistent SpMV grid (0 = 8 CTAs per SM)
     int64_t tma_stages = 3;      // shared-memory ring depth of the TMA SpMV
-    int64_t tile_blocked = 1;    // persistent SpMV: contiguous tile range per CTA
+    int64_t tile_blocked = 0;    // persistent SpMV: 1 = contiguous tile range per CTA (measured slower)
 
     // local pattern (a4/a5) -- resident across solves
     label n = 0, n_faces = 0, n_local_iface = 0;
