@@ -207,6 +207,7 @@ def run_gpu(args):
     ctx.partition_create(n, *host.create_communication_pattern(s))
     ctx.nonlocal_pattern(host.collect_cells_on_non_local_interface(s))
     nnz, n_halo = ctx.nnz, ctx.n_halo
+    p2p_active = bool(ctx.get_option("p2p_active"))
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
     h_diag, h_upper, h_b, h_x0 = pin(s.diag), pin(s.upper), pin(s.source), pin(s.psi)
     h_if = pin(host.collect_interface_coeffs(s, True))
@@ -320,6 +321,9 @@ def run_gpu(args):
                         "(BASELINE configs[1])",
             "rows_per_gpu": n, "nnz_per_gpu": nnz, "halo_per_gpu": n_halo,
             "decomposition": list(procs_for(n_gpus)),
+            "comm": ("none" if n_gpus == 1 else
+                     ("peer-memory windows over NVLink (P2P stores + in-kernel all-reduce)"
+                      if p2p_active else "NCCL send/recv + allreduce")),
             "iterations_per_solve": iters_res / args.steps,
             "l2": "working set ~%.0f MB vs 126 MB L2; 512 MB written between steps to flush L2; "
                   "inside a solve the iterations reuse whatever L2 keeps (that is the workload)"

@@ -104,6 +104,7 @@ static void destroy(Context *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    comm_teardown(c);
     if (c->comm) release_comm(c->comm_key);
     void *ptrs[] = {c->d_rows,       c->d_cols,       c->d_map,        c->d_row_ptrs,
                     c->d_send_idxs,  c->d_send_buf,   c->d_recv_buf,   c->d_nl_rows,
@@ -303,6 +304,9 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->use_graph = value != 0;
     } else if (k == "profile_stride") {
         ctx->profile_stride = value < 0 ? 0 : value;
+    } else if (k == "comm_mode") {
+        if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "comm_mode in {0,1,2}");
+        ctx->comm_mode = value;   // takes effect at the next ogl_partition_create / solve
     } else if (k == "tile_blocked") {
         ctx->tile_blocked = value != 0;
     } else if (k == "tma_stages") {
@@ -338,6 +342,8 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "stream_ctas") *value = ctx->stream_ctas;
     else if (k == "tma_stages") *value = ctx->tma_stages;
     else if (k == "tile_blocked") *value = ctx->tile_blocked;
+    else if (k == "comm_mode") *value = ctx->comm_mode;
+    else if (k == "p2p_active") *value = use_p2p(ctx) ? 1 : 0;
     else if (k == "max_row_len") *value = ctx->max_row_len;
     else if (k == "max_block_nnz") *value = ctx->max_block_nnz;
     else if (k == "launches") *value = ctx->launches;

@@ -1,15 +1,26 @@
-// Multi-GPU plumbing: one process (rank) per GPU, NCCL over NVLink/NVSwitch
-// (SURVEY.md section 8e).  Replaces, on this path, Ginkgo's
-// distributed::Matrix::communicate + MPI_Allreduce calls:
-//   halo exchange   MPI_Ineighbor_alltoallv of gathered boundary values
-//                   -> pack kernel + grouped ncclSend/ncclRecv on a side stream,
-//                      overlapped with the interior (local-block) SpMV
-//   reductions      MPI_Allreduce(SUM) of 1 scalar, 2-3 times per iteration
-//                   -> one ncclAllReduce of the packed scalars, in place in the
-//                      device-resident SolveState
-// The partition itself (who sends what to whom) is OGL's
-// create_communication_pattern (HostMatrix/HostMatrix.C:251-306) fed through
-// PartitionInitFunctor (DevicePersistent/Partition/Partition.H:57-70).
+// Multi-GPU plumbing: one process (rank) per GPU.
+//
+// Replaces, on this path, Ginkgo's distributed::Matrix::communicate
+// (MPI_Ineighbor_alltoallv of gathered boundary values, overlapped with the
+// local SpMV) and the MPI_Allreduce behind every distributed dot / norm.  The
+// partition (who sends what to whom) is OGL's create_communication_pattern
+// (HostMatrix/HostMatrix.C:251-306) fed through PartitionInitFunctor
+// (DevicePersistent/Partition/Partition.H:57-70).
+//
+// Two data paths:
+//   comm_mode 2 (default when every peer is reachable over NVLink P2P):
+//     peer-memory windows (reduce.cuh).  The pack kernel stores boundary values
+//     straight into the neighbours' receive buffers; reducing kernels all-reduce
+//     their partial sums through the peers' mailboxes in their own last block.
+//     No NCCL call, no extra launch per iteration; the stores travel while the
+//     local-block SpMV runs.
+//   comm_mode 1: NCCL -- grouped ncclSend/ncclRecv on a side stream overlapped
+//     with the local SpMV, ncclAllReduce of the packed scalars in place in the
+//     device-resident SolveState, then a one-thread epilogue kernel.
+// NCCL is also what bootstraps the windows (all-gather of the IPC handles and
+// of each rank's neighbour directory) and sums the global size.
+#include <cstring>
+
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -25,7 +36,207 @@ __global__ void k_pack(label n_send, const label *__restrict__ idx,
     if (k < n_send) buf[k] = x[idx[k]];
 }
 
+// P2P pack: x[send_idxs[k]] goes directly into the receive buffer of the
+// neighbour that owns block k; the last block raises the neighbours' data flags.
+__global__ void __launch_bounds__(256)
+k_pack_p2p(label n_send, const label *__restrict__ idx, const double *__restrict__ x,
+           CommDev *c, SolveState *state, int guard_done)
+{
+    if (guard_done && state->done) return;
+    __shared__ bool is_last;
+    const unsigned long long seq = c->halo_seq + 1;
+    const int parity = (int)(seq & 1ull);
+    // flow control: the buffer of this parity was last used by exchange seq-2;
+    // wait until every neighbour has acknowledged consuming it
+    if (seq > 2 && threadIdx.x < c->n_targets) {
+        if (!wait_flag(&c->my_ack_flag[threadIdx.x], seq - 2)) state->comm_error = 1;
+    }
+    __syncthreads();
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_send) {
+        int t = 0;
+        while (k >= c->send_offs[t + 1]) ++t;
+        double *dst = c->peer_recv[t] + (size_t)parity * c->peer_recv_stride[t] + (k - c->send_offs[t]);
+        const double v = x[idx[k]];
+        asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(&c->pack_ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    if (threadIdx.x < c->n_targets) st_flag(c->peer_data_flag[threadIdx.x], seq);
+    if (threadIdx.x == 0) {
+        c->halo_seq = seq;
+        c->pack_ticket = 0u;
+    }
+}
+
+struct Directory {
+    int n_targets;
+    int n_halo;
+    int target_ids[kMaxTargets];
+    int send_offs[kMaxTargets + 1];
+    long long off_mbox, off_data_flag, off_ack_flag, off_recv;   // bytes inside the window
+    cudaIpcMemHandle_t handle;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 }  // namespace
+
+static void p2p_teardown(Context *ctx)
+{
+    for (void *p : ctx->peer_windows)
+        if (p) cudaIpcCloseMemHandle(p);
+    ctx->peer_windows.clear();
+    if (ctx->d_window) cudaFree(ctx->d_window);
+    ctx->d_window = nullptr;
+    if (ctx->d_commdev) cudaFree(ctx->d_commdev);
+    ctx->d_commdev = nullptr;
+    ctx->p2p_ready = false;
+}
+
+void comm_teardown(Context *ctx) { p2p_teardown(ctx); }
+
+// Build the peer-memory windows.  Collective.  Returns OGL_OK with
+// ctx->p2p_ready == false when the topology does not allow it (caller falls
+// back to NCCL).
+static int p2p_setup(Context *ctx)
+{
+    p2p_teardown(ctx);
+    if (ctx->n_ranks > kMaxPeers || ctx->n_targets > kMaxTargets) return OGL_OK;
+    const int R = ctx->n_ranks;
+    // ---- my window
+    Directory mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.n_targets = ctx->n_targets;
+    mine.n_halo = ctx->n_send;
+    for (int t = 0; t < ctx->n_targets; ++t) mine.target_ids[t] = ctx->target_ids[t];
+    for (int t = 0; t <= ctx->n_targets; ++t) mine.send_offs[t] = ctx->send_offs[t];
+    size_t off = 0;
+    mine.off_mbox = (long long)off;
+    off = align_up(off + sizeof(double) * 2 * R * kSlot, 256);
+    mine.off_data_flag = (long long)off;
+    off = align_up(off + sizeof(unsigned long long) * kMaxTargets, 256);
+    mine.off_ack_flag = (long long)off;
+    off = align_up(off + sizeof(unsigned long long) * kMaxTargets, 256);
+    mine.off_recv = (long long)off;
+    off = align_up(off + sizeof(double) * 2 * (size_t)(ctx->n_send > 0 ? ctx->n_send : 1), 256);
+    ctx->window_bytes = off;
+    int ok_local = 1;
+    if (cudaMalloc(&ctx->d_window, off) != cudaSuccess) ok_local = 0;
+    if (ok_local) cudaMemset(ctx->d_window, 0, off);
+    if (ok_local && cudaIpcGetMemHandle(&mine.handle, ctx->d_window) != cudaSuccess) ok_local = 0;
+    cudaGetLastError();
+    // ---- all-gather the directories (and whether everyone got this far)
+    Directory *d_all = nullptr;
+    OGL_TRY(dev_alloc(ctx, &d_all, (size_t)R));
+    int *d_ok = nullptr;
+    OGL_TRY(dev_alloc(ctx, &d_ok, 1));
+    cudaMemcpyAsync(d_all + ctx->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_ok, &ok_local, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r1 = ncclAllGather(d_all + ctx->rank, d_all, sizeof(Directory), ncclChar, ctx->comm,
+                                    ctx->stream);
+    ncclResult_t r2 = ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, ctx->comm, ctx->stream);
+    std::vector<Directory> all(R);
+    int ok_all = 0;
+    cudaMemcpyAsync(all.data(), d_all, sizeof(Directory) * R, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&ok_all, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_all);
+    cudaFree(d_ok);
+    if (r1 != ncclSuccess || r2 != ncclSuccess)
+        return fail(ctx, OGL_ERR_NCCL, "window bootstrap: NCCL all-gather failed");
+    if (e != cudaSuccess)
+        return fail(ctx, OGL_ERR_CUDA, std::string("window bootstrap: ") + cudaGetErrorString(e));
+    // ---- map the peers' windows
+    int mapped = ok_all;
+    ctx->peer_windows.assign(R, nullptr);
+    if (mapped) {
+        for (int q = 0; q < R && mapped; ++q) {
+            if (q == ctx->rank) continue;
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                mapped = 0;
+                break;
+            }
+            ctx->peer_windows[q] = p;
+        }
+    }
+    // everyone must agree before the first kernel relies on it
+    int *d_flag = nullptr;
+    OGL_TRY(dev_alloc(ctx, &d_flag, 1));
+    cudaMemcpyAsync(d_flag, &mapped, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r3 = ncclAllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, ctx->comm, ctx->stream);
+    int mapped_all = 0;
+    cudaMemcpyAsync(&mapped_all, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_flag);
+    if (r3 != ncclSuccess || e != cudaSuccess)
+        return fail(ctx, OGL_ERR_NCCL, "window bootstrap: agreement all-reduce failed");
+    if (!mapped_all) {
+        p2p_teardown(ctx);
+        return OGL_OK;   // NCCL path
+    }
+    // ---- device-side description
+    CommDev h;
+    std::memset(&h, 0, sizeof(h));
+    h.rank = ctx->rank;
+    h.n_ranks = R;
+    h.n_targets = ctx->n_targets;
+    auto base_of = [&](int q) -> char * {
+        return static_cast<char *>(q == ctx->rank ? ctx->d_window : ctx->peer_windows[q]);
+    };
+    for (int q = 0; q < R; ++q) h.mbox[q] = reinterpret_cast<double *>(base_of(q) + all[q].off_mbox);
+    for (int t = 0; t <= ctx->n_targets; ++t) h.send_offs[t] = ctx->send_offs[t];
+    for (int t = 0; t < ctx->n_targets; ++t) {
+        const int q = ctx->target_ids[t];
+        const Directory &dq = all[q];
+        int u = -1;
+        for (int k = 0; k < dq.n_targets; ++k)
+            if (dq.target_ids[k] == ctx->rank) u = k;
+        if (u < 0 || dq.send_offs[u + 1] - dq.send_offs[u] != ctx->target_sizes[t]) {
+            p2p_teardown(ctx);
+            return fail(ctx, OGL_ERR_INVALID,
+                        "neighbour lists of the ranks are not symmetric (processor patches)");
+        }
+        // my values land in the neighbour's recv block reserved for me: same offset
+        // as the neighbour's own send block towards me (blocked by ascending rank)
+        h.peer_recv[t] = reinterpret_cast<double *>(base_of(q) + dq.off_recv) + dq.send_offs[u];
+        h.peer_recv_stride[t] = dq.n_halo > 0 ? dq.n_halo : 1;
+        h.peer_data_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_data_flag) + u;
+        h.peer_ack_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_ack_flag) + u;
+    }
+    char *me = static_cast<char *>(ctx->d_window);
+    h.my_data_flag = reinterpret_cast<unsigned long long *>(me + mine.off_data_flag);
+    h.my_ack_flag = reinterpret_cast<unsigned long long *>(me + mine.off_ack_flag);
+    h.my_recv = reinterpret_cast<double *>(me + mine.off_recv);
+    h.my_recv_stride = ctx->n_send > 0 ? ctx->n_send : 1;
+    OGL_TRY(dev_alloc(ctx, &ctx->d_commdev, 1));
+    OGL_CUDA(ctx, cudaMemcpy(ctx->d_commdev, &h, sizeof(h), cudaMemcpyHostToDevice));
+    // nobody may touch a window before every rank has finished zeroing/mapping
+    int *d_bar = nullptr;
+    OGL_TRY(dev_alloc(ctx, &d_bar, 1));
+    cudaMemsetAsync(d_bar, 0, sizeof(int), ctx->stream);
+    ncclResult_t r4 = ncclAllReduce(d_bar, d_bar, 1, ncclInt, ncclSum, ctx->comm, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_bar);
+    if (r4 != ncclSuccess || e != cudaSuccess)
+        return fail(ctx, OGL_ERR_NCCL, "window bootstrap: final barrier failed");
+    ctx->p2p_ready = true;
+    return OGL_OK;
+}
+
+bool use_p2p(const Context *ctx)
+{
+    return ctx->n_ranks > 1 && ctx->p2p_ready && ctx->comm_mode != 1;
+}
 
 int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,
                      const label *target_sizes, const label *send_idxs)
@@ -74,22 +285,32 @@ int partition_create(Context *ctx, label n_local, label n_targets, const label *
         if (e != cudaSuccess)
             return fail(ctx, OGL_ERR_CUDA, std::string("partition: ") + cudaGetErrorString(e));
         ctx->global_n = h;
+        if (ctx->comm_mode != 1) OGL_TRY(p2p_setup(ctx));
     }
     ctx->have_partition = true;
+    if (ctx->graph_exec) {
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+    }
     return OGL_OK;
 }
 
-int halo_begin(Context *ctx, const double *x)
+int halo_begin(Context *ctx, const double *x, bool guard_done)
 {
     if (ctx->n_send == 0) return OGL_OK;
+    if (ctx->n_ranks == 1)
+        return fail(ctx, OGL_ERR_INVALID, "halo exchange requested on a single rank");
+    if (use_p2p(ctx)) {
+        k_pack_p2p<<<(ctx->n_send + 255) / 256, 256, 0, ctx->stream>>>(
+            ctx->n_send, ctx->d_send_idxs, x, ctx->d_commdev, ctx->d_state, guard_done ? 1 : 0);
+        ctx->launches++;
+        OGL_CUDA(ctx, cudaGetLastError());
+        return OGL_OK;
+    }
     k_pack<<<(ctx->n_send + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_send, ctx->d_send_idxs, x,
                                                               ctx->d_send_buf);
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
-    if (ctx->n_ranks == 1) {
-        // no peers (cannot happen with a valid partition): loop back for safety
-        return fail(ctx, OGL_ERR_INVALID, "halo exchange requested on a single rank");
-    }
     OGL_CUDA(ctx, cudaEventRecord(ctx->ev_pack, ctx->stream));
     OGL_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_pack, 0));
     OGL_NCCL(ctx, ncclGroupStart());
@@ -110,21 +331,22 @@ int halo_begin(Context *ctx, const double *x)
 
 int halo_end(Context *ctx)
 {
-    if (ctx->n_send == 0) return OGL_OK;
+    if (ctx->n_send == 0 || use_p2p(ctx)) return OGL_OK;   // P2P: the consumer kernel waits on flags
     OGL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_recv, 0));
     return OGL_OK;
 }
 
 int allreduce_red(Context *ctx, int count)
 {
-    if (ctx->n_ranks == 1) return OGL_OK;
+    if (ctx->n_ranks == 1 || use_p2p(ctx)) return OGL_OK;
     double *red = &ctx->d_state->red[0];
     OGL_NCCL(ctx, ncclAllReduce(red, red, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     return OGL_OK;
 }
 
-// y = A x through the distributed operator: halo exchange on the side stream
-// while the local block runs, then the non-local block on the received values.
+// y = A x through the distributed operator: boundary values travel to the
+// neighbours while the local block runs, then the non-local block is applied
+// to the received values (and finishes the fused reductions).
 int dist_spmv(Context *ctx, const SpmvArgs &a)
 {
     if (ctx->n_ranks == 1) {
@@ -136,14 +358,15 @@ int dist_spmv(Context *ctx, const SpmvArgs &a)
     }
     if (ctx->n_halo != ctx->n_send)
         return fail(ctx, OGL_ERR_INVALID, "halo pattern and partition disagree on the halo size");
-    OGL_TRY(halo_begin(ctx, a.x));
+    OGL_TRY(halo_begin(ctx, a.x, a.guard_done));
     SpmvArgs s = a;
     s.inline_epi = false;
     s.epi = EPI_NONE;
     OGL_TRY(spmv_local(ctx, s));
     OGL_TRY(halo_end(ctx));
+    const bool p2p = use_p2p(ctx);
     OGL_TRY(spmv_nonlocal(ctx, ctx->d_recv_buf, a.y, a.advanced ? a.alpha : 1.0, a.dot_with,
-                          a.nred, a.guard_done, EPI_NONE, false));
+                          a.nred, a.guard_done, p2p ? a.epi : EPI_NONE, p2p));
     if (a.nred > 0) OGL_TRY(finish_reduction(ctx, a.nred, a.epi, a.guard_done));
     return OGL_OK;
 }

@@ -13,6 +13,8 @@
 
 namespace ogl {
 
+struct CommDev;
+
 using label = int32_t;
 using scalar = double;
 
@@ -44,6 +46,7 @@ struct SolveState {
     // --- GMRES
     int restart_iter, final_iter, krylov_dim, need_restart;
     double res_norm2;
+    int comm_error, pad2;   // peer synchronisation timed out (multi-GPU)
 };
 
 struct DeviceBuffer {
@@ -116,6 +119,14 @@ struct Context {
     std::vector<label> target_ids, target_sizes, send_offs;
     label *d_send_idxs = nullptr;
     double *d_send_buf = nullptr, *d_recv_buf = nullptr;
+
+    // peer-memory window (multi-GPU P2P path, comm.cu)
+    int64_t comm_mode = 0;        // 0 auto, 1 NCCL send/recv + allreduce, 2 peer-memory (P2P)
+    bool p2p_ready = false;
+    void *d_window = nullptr;     // my window (exported through CUDA IPC)
+    size_t window_bytes = 0;
+    std::vector<void *> peer_windows;   // opened IPC mappings, by rank (nullptr for self)
+    struct CommDev *d_commdev = nullptr;
 
     // non-local pattern (a7)
     label n_halo = 0;
@@ -224,7 +235,7 @@ int spmv_setup(Context *ctx);
 // comm.cu ------------------------------------------------------------------------
 int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,
                      const label *target_sizes, const label *send_idxs);
-int halo_begin(Context *ctx, const double *x);                    // pack + send/recv on comm stream
+int halo_begin(Context *ctx, const double *x, bool guard_done);   // pack (+ NCCL send/recv)
 int halo_end(Context *ctx);                                       // compute stream waits for recv
 int allreduce_red(Context *ctx, int count);                      // state->red[0..count) summed over ranks
 int dist_spmv(Context *ctx, const SpmvArgs &a);                   // halo + local + non-local
@@ -232,7 +243,9 @@ int dist_spmv(Context *ctx, const SpmvArgs &a);                   // halo + loca
 // precond.cu ---------------------------------------------------------------------
 int precond_setup(Context *ctx, int kind, label mbs);
 int precond_apply(Context *ctx, const double *r, double *z, const double *dot_with,
-                  int red_base, bool guard_done, int epi, bool inline_epi);
+                  int red_base, bool guard_done, int epi, bool inline_epi, int ar_count);
+bool use_p2p(const Context *ctx);
+void comm_teardown(Context *ctx);
 
 // solver.cu ----------------------------------------------------------------------
 int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res);

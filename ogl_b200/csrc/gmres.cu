@@ -24,7 +24,8 @@
 namespace ogl {
 
 int precond_apply(Context *ctx, const double *r, double *z, const double *dot_with,
-                  int red_base, bool guard_done, int epi, bool inline_epi);
+                  int red_base, bool guard_done, int epi, bool inline_epi, int ar_count);
+bool use_p2p(const Context *ctx);
 
 namespace {
 
@@ -234,7 +235,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     int64_t g64 = ((int64_t)n + kT - 1) / kT;
     if (g64 > ctx->blas1_blocks) g64 = ctx->blas1_blocks;
     const int grid = (int)(g64 < 1 ? 1 : g64);
-    auto base = [&]() {
+    auto base = [&](int ar_count = 0) {
         GmK a;
         std::memset(&a, 0, sizeof(a));
         a.n = n;
@@ -242,7 +243,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
         a.partials = ctx->d_partials;
         a.ticket = ctx->d_ticket;
         a.inline_epi = 0;
-        a.ea = ea;
+        a.ea = make_epi_args(ctx, ar_count);
         a.d = d;
         return a;
     };
@@ -268,7 +269,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
         ctx->launches += 2;
         const double *add = tmp;
         if (pk != 0) {
-            OGL_TRY(precond_apply(ctx, tmp, pv, nullptr, 0, guard, EPI_NONE, false));
+            OGL_TRY(precond_apply(ctx, tmp, pv, nullptr, 0, guard, EPI_NONE, false, 0));
             add = pv;
         }
         GmK b = base();
@@ -301,7 +302,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
                 s.beta = 1.0;
                 s.guard_done = true;
                 OGL_TRY(dist_spmv(ctx, s));
-                GmK a = base();
+                GmK a = base(2);
                 a.in0 = residual;
                 k_gmres_norms<<<grid, kT, 0, st>>>(a, 1);
                 ctx->launches++;
@@ -321,7 +322,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
                 ctx->launches++;
                 y = pv;
             } else if (pk == 2) {
-                OGL_TRY(precond_apply(ctx, vj, pv, nullptr, 0, true, EPI_NONE, false));
+                OGL_TRY(precond_apply(ctx, vj, pv, nullptr, 0, true, EPI_NONE, false, 0));
                 y = pv;
             }
             {
@@ -335,7 +336,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
                 OGL_TRY(dist_spmv(ctx, s));
             }
             for (int k = 0; k <= ri; ++k) {
-                GmK a = base();
+                GmK a = base(1);
                 a.ri = ri;
                 a.k = k;
                 a.in0 = V + (size_t)k * n;
@@ -384,6 +385,8 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     res->n_iterations = hs.iter;
     res->solve_us = ms * 1e3;
     res->kernel_launches = ctx->launches - launches0;
+    if (hs.comm_error)
+        return fail(ctx, OGL_ERR_NCCL, "peer synchronisation timed out (a rank left the solve?)");
     if (!hs.done)
         return fail(ctx, OGL_ERR_CUDA, "GMRES loop ended without the criterion firing");
     return OGL_OK;

@@ -260,7 +260,7 @@ int precond_setup(Context *ctx, int kind, label mbs)
 }
 
 int precond_apply(Context *ctx, const double *r, double *z, const double *dot_with,
-                  int red_base, bool guard_done, int epi, bool inline_epi)
+                  int red_base, bool guard_done, int epi, bool inline_epi, int ar_count)
 {
     if (ctx->precond_kind == OGL_PRECOND_NONE || ctx->n == 0) {
         if (r != z)
@@ -285,7 +285,7 @@ int precond_apply(Context *ctx, const double *r, double *z, const double *dot_wi
     a.epi = epi;
     a.inline_epi = inline_epi ? 1 : 0;
     a.guard_done = guard_done ? 1 : 0;
-    a.ea = make_epi_args(ctx);
+    a.ea = make_epi_args(ctx, dot_with ? ar_count : 0);
     int grid = (ctx->n + 255) / 256;
     if (grid > ctx->blas1_blocks) grid = (int)ctx->blas1_blocks;
     const bool scalar = ctx->max_block_size == 1;

@@ -62,14 +62,54 @@ __device__ __forceinline__ bool criterion_check(SolveState *s, double norm1,
     return stop;
 }
 
+// ---- peer-memory communication window (multi-GPU, one process per GPU) --------
+// Every rank exposes one device allocation ("window") to its peers through CUDA
+// IPC over NVLink/NVSwitch.  Kernels write straight into the peers' windows:
+//   * all-reduce: the last block of a reducing kernel stores its partial sums
+//     into slot[my rank] of EVERY rank's mailbox, waits until all slots of its
+//     own mailbox carry the current sequence stamp and adds them in rank order
+//     (identical order on every rank => bit-identical, deterministic results);
+//   * halo exchange: the pack kernel stores x[send_idxs] directly into the
+//     neighbours' receive buffers and raises a per-neighbour flag; the kernel
+//     that consumes the halo waits for the flags and acknowledges afterwards.
+// Buffers are double-buffered by sequence parity; acknowledgements give flow
+// control for back-to-back exchanges.  No NCCL call and no extra kernel launch
+// is needed per iteration, so a chunk of iterations replays as one CUDA graph.
+constexpr int kMaxPeers = 8;       // ranks per NVSwitch domain
+constexpr int kMaxTargets = 32;    // neighbour ranks of one rank
+constexpr int kSlot = kMaxReduce + 1;   // payload + stamp
+constexpr long long kSpinCycles = 6000000000LL;   // ~3 s: fail loudly instead of hanging
+
+struct CommDev {
+    int rank, n_ranks, n_targets, pad;
+    // all-reduce mailboxes: mbox[r] = rank r's mailbox base, [2][n_ranks][kSlot] doubles
+    double *mbox[kMaxPeers];
+    unsigned long long ar_seq;          // device-side sequence counters
+    unsigned long long halo_seq;
+    unsigned int pack_ticket, nl_ticket;
+    // halo exchange, per neighbour t
+    int send_offs[kMaxTargets + 1];
+    double *peer_recv[kMaxTargets];           // neighbour's recv block for me, parity 0
+    long long peer_recv_stride[kMaxTargets];  // doubles between the neighbour's two parity buffers
+    unsigned long long *peer_data_flag[kMaxTargets];  // neighbour's data flag for me
+    unsigned long long *peer_ack_flag[kMaxTargets];   // neighbour's ack flag for me
+    unsigned long long *my_data_flag;         // [n_targets] raised by neighbours
+    unsigned long long *my_ack_flag;          // [n_targets] raised by neighbours
+    double *my_recv;                          // [2][n_halo]
+    long long my_recv_stride;
+};
+
 // extra scalars some epilogues need
 struct EpiArgs {
     double inv_n_local;   // 1 / n_local
     double weight;        // n_local / n_global
     double *history;
+    CommDev *comm;        // peer-memory window (nullptr: single rank or NCCL path)
+    int ar_count;         // leading state->red[] slots to all-reduce in this launch (0: none)
+    int ar_after_epi;     // 1: run the epilogue on the local sums first (mean)
 };
 
-EpiArgs make_epi_args(Context *ctx);
+EpiArgs make_epi_args(Context *ctx, int ar_count = 0, bool ar_after_epi = false);
 
 __device__ __forceinline__ void run_epilogue(int epi, SolveState *s, const EpiArgs &a)
 {
@@ -167,6 +207,65 @@ __device__ __forceinline__ void block_sum(double (&v)[NRED], double *sm)
     }
 }
 
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *p >= want; false on timeout
+__device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long want)
+{
+    const long long t0 = clock64();
+    while (ld_flag(p) < want) {
+        if (clock64() - t0 > kSpinCycles) return false;
+    }
+    return true;
+}
+
+// All-reduce (sum) of state->red[0..count) over the ranks through the peers'
+// mailboxes.  Called by ALL threads of ONE block per rank (the last block of a
+// reducing kernel); state->red must already hold the local sums.
+__device__ __forceinline__ void p2p_allreduce(SolveState *s, int count, CommDev *c)
+{
+    __shared__ unsigned long long seq_sh;
+    if (threadIdx.x == 0) seq_sh = ++c->ar_seq;
+    __syncthreads();
+    const unsigned long long seq = seq_sh;
+    const int parity = (int)(seq & 1ull);
+    const int t = threadIdx.x;
+    if (t < c->n_ranks) {
+        // my partial sums -> slot[my rank] of rank t's mailbox
+        double *box = c->mbox[t] + ((size_t)(parity * c->n_ranks + c->rank)) * kSlot;
+        for (int j = 0; j < count; ++j)
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(box + j), "d"(s->red[j]) : "memory");
+        st_flag(reinterpret_cast<unsigned long long *>(box + kMaxReduce), seq);
+        // wait for rank t's contribution in my own mailbox
+        const double *mine = c->mbox[c->rank] + ((size_t)(parity * c->n_ranks + t)) * kSlot;
+        if (!wait_flag(reinterpret_cast<const unsigned long long *>(mine + kMaxReduce), seq))
+            s->comm_error = 1;
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double *base = c->mbox[c->rank] + (size_t)parity * c->n_ranks * kSlot;
+        for (int j = 0; j < count; ++j) {
+            double acc = 0.0;
+            for (int r = 0; r < c->n_ranks; ++r) {
+                double v;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(base + (size_t)r * kSlot + j) : "memory");
+                acc += v;   // rank order: the same on every rank
+            }
+            s->red[j] = acc;
+        }
+        if (s->comm_error) s->done = 1;
+    }
+    __syncthreads();
+}
+
 // Grid-wide deterministic reduction + optional inline epilogue.
 // All threads of all blocks call this exactly once per kernel.
 // red_base: first slot of state->red the sums go to.
@@ -208,7 +307,16 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
             state->red[red_base + j] = accumulate ? state->red[red_base + j] + acc[j] : acc[j];
         }
         *ticket = 0u;
-        if (inline_epi && epi != EPI_NONE) run_epilogue(epi, state, ea);
+    }
+    const bool ar = ea.comm != nullptr && ea.ar_count > 0;   // block-uniform
+    if (ar && !ea.ar_after_epi) {
+        __syncthreads();
+        p2p_allreduce(state, ea.ar_count, ea.comm);
+    }
+    if (threadIdx.x == 0 && inline_epi && epi != EPI_NONE) run_epilogue(epi, state, ea);
+    if (ar && ea.ar_after_epi) {
+        __syncthreads();
+        p2p_allreduce(state, ea.ar_count, ea.comm);
     }
 }
 

@@ -22,7 +22,7 @@
 namespace ogl {
 
 int precond_apply(Context *ctx, const double *r, double *z, const double *dot_with,
-                  int red_base, bool guard_done, int epi, bool inline_epi);
+                  int red_base, bool guard_done, int epi, bool inline_epi, int ar_count);
 int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res);
 
 namespace {
@@ -264,7 +264,11 @@ __global__ void k_epilogue(SolveState *state, int epi, EpiArgs ea, int guard_don
 
 // ---------------------------------------------------------------------------
 
-static VecK base_args(Context *ctx, int epi, bool guard)
+bool use_p2p(const Context *ctx);
+
+// ar_count: how many leading state->red[] slots this launch all-reduces on the
+// peer-memory path before its epilogue (ignored on one rank / the NCCL path)
+static VecK base_args(Context *ctx, int epi, bool guard, int ar_count = 0)
 {
     VecK a;
     std::memset(&a, 0, sizeof(a));
@@ -273,9 +277,9 @@ static VecK base_args(Context *ctx, int epi, bool guard)
     a.partials = ctx->d_partials;
     a.ticket = ctx->d_ticket;
     a.epi = epi;
-    a.inline_epi = ctx->n_ranks == 1 ? 1 : 0;
+    a.inline_epi = (ctx->n_ranks == 1 || use_p2p(ctx)) ? 1 : 0;
     a.guard_done = guard ? 1 : 0;
-    a.ea = make_epi_args(ctx);
+    a.ea = make_epi_args(ctx, ar_count);
     return a;
 }
 
@@ -291,7 +295,7 @@ static int vec_grid(const Context *ctx)
 // scalar epilogue in a one-thread kernel (one rank: already done in-kernel)
 int finish_reduction(Context *ctx, int count, int epi, bool guard)
 {
-    if (ctx->n_ranks == 1) return OGL_OK;
+    if (ctx->n_ranks == 1 || use_p2p(ctx)) return OGL_OK;   // done inside the kernel
     OGL_TRY(allreduce_red(ctx, count));
     if (epi != EPI_NONE) {
         k_epilogue<<<1, 1, 0, ctx->stream>>>(ctx->d_state, epi, make_epi_args(ctx), guard ? 1 : 0);
@@ -342,6 +346,7 @@ int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, dou
     {
         VecK a = base_args(ctx, EPI_MEAN_LOCAL, false);
         a.inline_epi = 1;   // the local transform always runs in-kernel
+        a.ea = make_epi_args(ctx, 1, /*ar_after_epi=*/true);
         a.in0 = ctx->d_x;
         LAUNCH(k_sum, a);
         if (ctx->n_ranks > 1) OGL_TRY(allreduce_red(ctx, 1));
@@ -365,7 +370,8 @@ int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, dou
         s.beta = 1.0;
         OGL_TRY(dist_spmv(ctx, s));
     }
-    VecK a = base_args(ctx, (pk == 2 && mode == 0) ? EPI_NONE : epi, false);
+    const bool defer = (pk == 2 && mode == 0);   // block Jacobi finishes <r,z> afterwards
+    VecK a = base_args(ctx, defer ? EPI_NONE : epi, false, defer ? 0 : 3);
     a.in0 = r;
     a.in1 = ctx->d_b;
     a.in2 = w;
@@ -377,7 +383,7 @@ int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, dou
         else if (pk == 1) LAUNCH((k_init_norms<1, 0>), a);
         else {
             LAUNCH((k_init_norms<2, 0>), a);
-            OGL_TRY(precond_apply(ctx, r, z, r, 0, false, epi, ctx->n_ranks == 1));
+            OGL_TRY(precond_apply(ctx, r, z, r, 0, false, epi, ctx->n_ranks == 1 || use_p2p(ctx), 3));
         }
     } else if (mode == 1) {
         LAUNCH((k_init_norms<0, 1>), a);
@@ -409,7 +415,7 @@ static int cg_iteration(Context *ctx, double *r, double *z, double *p, double *q
         OGL_TRY(dist_spmv(ctx, s));
     }
     {
-        VecK a = base_args(ctx, pk == 2 ? EPI_NONE : EPI_CG_RHO_CHECK, true);
+        VecK a = base_args(ctx, pk == 2 ? EPI_NONE : EPI_CG_RHO_CHECK, true, pk == 2 ? 0 : 2);
         a.in0 = p;
         a.in1 = q;
         a.in2 = ctx->d_inv_diag;
@@ -420,7 +426,8 @@ static int cg_iteration(Context *ctx, double *r, double *z, double *p, double *q
         else if (pk == 1) LAUNCH(k_cg_xr<1>, a);
         else {
             LAUNCH(k_cg_xr<2>, a);
-            OGL_TRY(precond_apply(ctx, r, z, r, 0, true, EPI_CG_RHO_CHECK, ctx->n_ranks == 1));
+            OGL_TRY(precond_apply(ctx, r, z, r, 0, true, EPI_CG_RHO_CHECK,
+                                  ctx->n_ranks == 1 || use_p2p(ctx), 2));
         }
     }
     return finish_reduction(ctx, 2, EPI_CG_RHO_CHECK, true);
@@ -439,7 +446,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         a.out1 = y;
         if (pk == 1) LAUNCH(k_bicg_step1<1>, a);
         else LAUNCH(k_bicg_step1<0>, a);
-        if (pk == 2) OGL_TRY(precond_apply(ctx, p, y, nullptr, 0, true, EPI_NONE, false));
+        if (pk == 2) OGL_TRY(precond_apply(ctx, p, y, nullptr, 0, true, EPI_NONE, false, 0));
     }
     const double *yy = pk == 0 ? p : y;
     {
@@ -453,7 +460,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         OGL_TRY(dist_spmv(ctx, sa));
     }
     {
-        VecK a = base_args(ctx, EPI_BICG_CHECK_S, true);
+        VecK a = base_args(ctx, EPI_BICG_CHECK_S, true, 2);
         a.in0 = r;
         a.in1 = v;
         a.in2 = ctx->d_inv_diag;
@@ -462,7 +469,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         if (pk == 1) LAUNCH(k_bicg_step2<1>, a);
         else LAUNCH(k_bicg_step2<0>, a);
         OGL_TRY(finish_reduction(ctx, 2, EPI_BICG_CHECK_S, true));
-        if (pk == 2) OGL_TRY(precond_apply(ctx, s, z, nullptr, 0, true, EPI_NONE, false));
+        if (pk == 2) OGL_TRY(precond_apply(ctx, s, z, nullptr, 0, true, EPI_NONE, false, 0));
     }
     const double *zz = pk == 0 ? s : z;
     {
@@ -476,7 +483,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         OGL_TRY(dist_spmv(ctx, sa));
     }
     {
-        VecK a = base_args(ctx, EPI_BICG_RHO_CHECK, true);
+        VecK a = base_args(ctx, EPI_BICG_RHO_CHECK, true, 2);
         a.in0 = s;
         a.in1 = t;
         a.in2 = yy;
@@ -531,7 +538,8 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
 {
     const int chunk = (int)(ctx->chunk_iters < 1 ? 1 : ctx->chunk_iters);
     cudaStream_t st = ctx->stream;
-    const bool graph_ok = ctx->use_graph && ctx->n_ranks == 1 && ctx->profile_stride == 0;
+    const bool graph_ok = ctx->use_graph && (ctx->n_ranks == 1 || use_p2p(ctx)) &&
+                          ctx->profile_stride == 0;
     const int64_t sig = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^
                         ((int64_t)chunk << 32) ^ (int64_t)ctx->n ^ (ctx->spmv_variant << 56);
     if (graph_ok && (!ctx->graph_exec || ctx->graph_sig != sig)) {
@@ -652,6 +660,8 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     // the L1 norm rides inside the fused update kernel: no separate evaluation
     res->resnorm_us = 0.0;
     res->kernel_launches = ctx->launches - launches0;
+    if (hs.comm_error)
+        return fail(ctx, OGL_ERR_NCCL, "peer synchronisation timed out (a rank left the solve?)");
     if (!hs.done)
         return fail(ctx, OGL_ERR_CUDA, "solver loop ended without the criterion firing");
     return OGL_OK;

@@ -535,6 +535,19 @@ template <int NRED>
 __global__ void __launch_bounds__(256) k_spmv_nonlocal(const NonLocalK a)
 {
     if (a.guard_done && a.state->done) return;
+    const double *recv = a.recv;
+    CommDev *c = a.ea.comm;
+    unsigned long long seq = 0;
+    if (c != nullptr && c->n_targets > 0) {
+        // peer-memory path: the neighbours' pack kernels store into my window;
+        // wait for their data flags of the current exchange
+        seq = c->halo_seq;
+        if (threadIdx.x < c->n_targets) {
+            if (!wait_flag(&c->my_data_flag[threadIdx.x], seq)) a.state->comm_error = 1;
+        }
+        __syncthreads();
+        recv = c->my_recv + (size_t)(seq & 1ull) * c->my_recv_stride;
+    }
     const label u = blockIdx.x * blockDim.x + threadIdx.x;
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
@@ -543,14 +556,35 @@ __global__ void __launch_bounds__(256) k_spmv_nonlocal(const NonLocalK a)
         const label row = a.row_ids[u];
         const double y_old = a.y[row];
         double acc = y_old;
-        for (label q = a.row_ptrs[u]; q < a.row_ptrs[u + 1]; ++q)
-            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(a.alpha, a.vals[q]), a.recv[a.cols[q]]));
+        for (label q = a.row_ptrs[u]; q < a.row_ptrs[u + 1]; ++q) {
+            double h;
+            if (c != nullptr)
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.cols[q]) : "memory");
+            else
+                h = recv[a.cols[q]];
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(a.alpha, a.vals[q]), h));
+        }
         a.y[row] = acc;
         if (NRED >= 1) {
             const double d = a.dot_with[row];
             red[0] = __dmul_rn(d, acc) - __dmul_rn(d, y_old);
         }
         if (NRED >= 2) red[1] = __dmul_rn(acc, acc) - __dmul_rn(y_old, y_old);
+    }
+    if (c != nullptr && c->n_targets > 0) {
+        // acknowledge: this rank is done reading the buffer of exchange `seq`
+        __shared__ bool last_nl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int tk = atomicAdd(&c->nl_ticket, 1u);
+            last_nl = (tk == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last_nl) {
+            if (threadIdx.x < c->n_targets) st_flag(c->peer_ack_flag[threadIdx.x], seq);
+            if (threadIdx.x == 0) c->nl_ticket = 0u;
+        }
     }
     if (NRED > 0)
         grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
@@ -576,13 +610,19 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const
 
 }  // namespace
 
-EpiArgs make_epi_args(Context *ctx)
+bool use_p2p(const Context *ctx);
+
+EpiArgs make_epi_args(Context *ctx, int ar_count, bool ar_after_epi)
 {
     EpiArgs ea;
     ea.inv_n_local = ctx->n > 0 ? 1.0 / (double)ctx->n : 0.0;
     const double g = (double)(ctx->global_n > 0 ? ctx->global_n : ctx->n);
     ea.weight = g > 0 ? (double)ctx->n / g : 0.0;
     ea.history = ctx->d_history;
+    const bool p2p = use_p2p(ctx);
+    ea.comm = p2p ? ctx->d_commdev : nullptr;
+    ea.ar_count = p2p ? ar_count : 0;
+    ea.ar_after_epi = ar_after_epi ? 1 : 0;
     return ea;
 }
 
@@ -652,7 +692,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.epi = sa.epi;
     k.inline_epi = sa.inline_epi ? 1 : 0;
     k.guard_done = sa.guard_done ? 1 : 0;
-    k.ea = make_epi_args(ctx);
+    k.ea = make_epi_args(ctx, 0);
     const int nred = sa.nred;
     if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
     const int variant = pick_variant(ctx);
@@ -763,7 +803,10 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
                   const double *dot_with, int nred, bool guard_done, int epi,
                   bool inline_epi)
 {
-    if (ctx->n_nl_rows == 0) return OGL_OK;
+    const bool p2p = use_p2p(ctx);
+    // peer-memory path: this launch also carries the all-reduce of the fused
+    // sums (and the flag handshake), so it runs even without halo rows
+    if (ctx->n_nl_rows == 0 && !(p2p && (nred > 0 || ctx->n_targets > 0))) return OGL_OK;
     NonLocalK k;
     k.n_rows = ctx->n_nl_rows;
     k.row_ids = ctx->d_nl_row_ids;
@@ -780,8 +823,9 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
     k.epi = epi;
     k.inline_epi = inline_epi ? 1 : 0;
     k.guard_done = guard_done ? 1 : 0;
-    k.ea = make_epi_args(ctx);
-    const int grid = (ctx->n_nl_rows + 255) / 256;
+    k.ea = make_epi_args(ctx, nred);
+    int grid = (ctx->n_nl_rows + 255) / 256;
+    if (grid < 1) grid = 1;
     if (nred == 0) k_spmv_nonlocal<0><<<grid, 256, 0, ctx->stream>>>(k);
     else if (nred == 1) k_spmv_nonlocal<1><<<grid, 256, 0, ctx->stream>>>(k);
     else k_spmv_nonlocal<2><<<grid, 256, 0, ctx->stream>>>(k);

@@ -29,11 +29,14 @@ def main():
     ps = init_from_env("nccl")
     db = ObjectRegistry()
     results = {}
-    for name, (builder, solver, precond, mbs, tol) in CASES.items():
+    # every case on both data paths: peer-memory windows (default) and NCCL
+    for name, (builder, solver, precond, mbs, tol), mode in (
+            (n, c, m) for n, c in CASES.items() for m in (0, 1)):
         s = builder(procs)[ps.rank]
         controls = {"solver": solver, "executor": "cuda", "tolerance": tol, "relTol": 0.0,
-                    "adaptMinIter": False, "krylovDim": 30,
+                    "adaptMinIter": False, "krylovDim": 30, "comm_mode": mode,
                     "preconditioner": {"preconditioner": precond, "maxBlockSize": mbs}}
+        name = f"{name}@{mode}"
         sol = lduMatrix_solver_New(name, s, controls, db, ps)
         psi = s.psi.copy()
         perf = sol.solve(psi, s.source)
@@ -41,7 +44,8 @@ def main():
         y = sol.ctx.spmv(x)
         results[name] = {"iters": perf.n_iterations, "init": perf.initial_residual,
                          "final": perf.final_residual, "x": psi.tolist(), "y": y.tolist(),
-                         "global_n": sol.ctx.partition_sizes()[1]}
+                         "global_n": sol.ctx.partition_sizes()[1],
+                         "p2p": sol.ctx.get_option("p2p_active")}
     json.dump(results, open(f"{out}.{ps.rank}", "w"))
     import torch.distributed as dist
     dist.barrier()

@@ -42,7 +42,10 @@ def test_decomposed_solves_match_oracle(oracle, tmp_path, procs):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     res = [json.load(open(f"{out}.{r}")) for r in range(world)]
-    for name, (builder, solver, precond, mbs, tol) in CASES.items():
+    assert res[0]["pressure_cg@0"]["p2p"] == 1, "peer-memory path not active on an NVLink box"
+    assert res[0]["pressure_cg@1"]["p2p"] == 0
+    for name, (builder, solver, precond, mbs, tol) in (
+            (f"{n}@{m}", c) for n, c in CASES.items() for m in (0, 1)):
         systems = builder(procs)
         asms = [oracle.assemble(s) for s in systems]
         o = oracle.solve(asms, solver, precond, max_block_size=mbs, tolerance=tol, krylov_dim=30)
