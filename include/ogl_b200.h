@@ -195,6 +195,10 @@ int ogl_synchronize(ogl_ctx *ctx);
  * CUDA events; *gbs = bytes moved / time.  mode 0: copy (read + write, 128-bit),
  * 1: read-only sum, 2: read-only 8 B + 4 B streams (values + columns like CSR). */
 int ogl_membench(ogl_ctx *ctx, int mode, int64_t n_doubles, int32_t reps, double *gbs);
+/* Peer-memory primitives (multi-GPU, collective): mode 0 one all-reduce per
+ * launch, 1 `reps` all-reduces inside one launch (device-side latency), 2 one
+ * halo exchange (pack + consume) per repetition; *us = time per repetition. */
+int ogl_commbench(ogl_ctx *ctx, int mode, int32_t reps, double *us);
 
 /* ---- Matrix-Market export ---------------------------------------
  * replaces export_mtx / export_vec (common/common.C:31-58,

@@ -202,6 +202,11 @@ class Context:
         self._check(self.lib.ogl_membench(self.h, mode, n_doubles, reps, C.byref(g)))
         return g.value
 
+    def commbench(self, mode: int, reps: int = 200) -> float:
+        u = C.c_double(0)
+        self._check(self.lib.ogl_commbench(self.h, mode, reps, C.byref(u)))
+        return u.value
+
     def synchronize(self):
         self._check(self.lib.ogl_synchronize(self.h))
 

@@ -91,10 +91,10 @@ static void release_comm(const std::string &key)
     std::lock_guard<std::mutex> lock(g_comm_mutex);
     auto it = g_comms.find(key);
     if (it == g_comms.end()) return;
-    if (--it->second.refs == 0) {
-        ncclCommDestroy(it->second.comm);
-        g_comms.erase(it);
-    }
+    // the communicator stays cached for the life of the process: an NCCL unique
+    // id cannot be used for a second ncclCommInitRank, and later contexts (new
+    // fields, new time steps) arrive with the same id
+    if (it->second.refs > 0) --it->second.refs;
 }
 
 static void destroy(Context *c)
@@ -612,6 +612,14 @@ int ogl_membench(ogl_ctx *ctx, int mode, int64_t n_doubles, int32_t reps, double
     if (e != cudaSuccess) return fail(ctx, OGL_ERR_CUDA, std::string("membench: ") + cudaGetErrorString(e));
     *gbs = bytes * reps / (ms * 1e-3) / 1e9;
     return OGL_OK;
+}
+
+int ogl_commbench(ogl_ctx *ctx, int mode, int32_t reps, double *us)
+{
+    CHECK_CTX(ctx);
+    if (mode < 0 || mode > 2 || reps < 1 || !us) return fail(ctx, OGL_ERR_INVALID, "bad arguments");
+    if (!ctx->have_partition) return fail(ctx, OGL_ERR_INVALID, "no partition");
+    return comm_bench(ctx, mode, reps, us);
 }
 
 int ogl_synchronize(ogl_ctx *ctx)

@@ -60,15 +60,16 @@ k_pack_p2p(label n_send, const label *__restrict__ idx, const double *__restrict
         const double v = x[idx[k]];
         asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
     }
-    __threadfence_system();
+    // one system-scope fence per block (cumulative over the block's stores after
+    // the barrier) instead of one per thread: membar.sys is the expensive part
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int tk = atomicAdd(&c->pack_ticket, 1u);
         is_last = (tk == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return;
-    __threadfence_system();
     if (threadIdx.x < c->n_targets) st_flag(c->peer_data_flag[threadIdx.x], seq);
     if (threadIdx.x == 0) {
         c->halo_seq = seq;
@@ -230,6 +231,56 @@ static int p2p_setup(Context *ctx)
     if (r4 != ncclSuccess || e != cudaSuccess)
         return fail(ctx, OGL_ERR_NCCL, "window bootstrap: final barrier failed");
     ctx->p2p_ready = true;
+    return OGL_OK;
+}
+
+namespace {
+
+// reps all-reduces inside ONE launch: pure device-side latency of the primitive
+__global__ void k_ar_loop(SolveState *state, CommDev *c, int reps)
+{
+    for (int i = 0; i < reps; ++i) {
+        if (threadIdx.x == 0) state->red[0] = 1.0;
+        __syncthreads();
+        p2p_allreduce(state, 1, c);
+    }
+}
+
+// one all-reduce per launch
+__global__ void k_ar_once(SolveState *state, CommDev *c)
+{
+    if (threadIdx.x == 0) state->red[0] = 1.0;
+    __syncthreads();
+    p2p_allreduce(state, 1, c);
+}
+
+}  // namespace
+
+int comm_bench(Context *ctx, int mode, int reps, double *us)
+{
+    if (!use_p2p(ctx)) return fail(ctx, OGL_ERR_INVALID, "comm_bench needs the peer-memory path");
+    cudaStream_t st = ctx->stream;
+    double *x = nullptr;
+    OGL_TRY(get_work(ctx, 2, &x));
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) cudaEventRecord(ctx->ev_t0, st);
+        const int n = pass == 0 ? 3 : reps;
+        if (mode == 0) {
+            for (int i = 0; i < n; ++i) k_ar_once<<<1, 32, 0, st>>>(ctx->d_state, ctx->d_commdev);
+        } else if (mode == 1) {
+            k_ar_loop<<<1, 32, 0, st>>>(ctx->d_state, ctx->d_commdev, n);
+        } else {
+            for (int i = 0; i < n; ++i) {
+                OGL_TRY(halo_begin(ctx, x, false));
+                OGL_TRY(spmv_nonlocal(ctx, ctx->d_recv_buf, x, 0.0, nullptr, 0, false, EPI_NONE, true));
+            }
+        }
+    }
+    cudaEventRecord(ctx->ev_t1, st);
+    OGL_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1);
+    *us = ms * 1e3 / reps;
     return OGL_OK;
 }
 

@@ -246,6 +246,7 @@ int precond_apply(Context *ctx, const double *r, double *z, const double *dot_wi
                   int red_base, bool guard_done, int epi, bool inline_epi, int ar_count);
 bool use_p2p(const Context *ctx);
 void comm_teardown(Context *ctx);
+int comm_bench(Context *ctx, int mode, int reps, double *us);
 
 // solver.cu ----------------------------------------------------------------------
 int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res);
