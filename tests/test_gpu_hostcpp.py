@@ -1,0 +1,85 @@
+"""-m gpu: the C++ plugin layer (lduMatrix::solver::New -> GKO* -> lduLduBase ->
+HostMatrixWrapper -> C ABI) against the oracle, read like the reference would
+be driven by OpenFOAM."""
+import numpy as np
+import pytest
+
+from foam_harness import FoamCase, FoamFatalError
+from gpu_helpers import rel_l2
+from ogl_b200 import cases
+
+pytestmark = pytest.mark.gpu
+
+BASE = {"executor": "cuda", "relTol": 0.0, "adaptMinIter": False}
+
+
+@pytest.mark.parametrize("builder,solver,precond,tol", [
+    (lambda: cases.pressure_3d(20)[0], "GKOCG", "BJ", 1e-9),
+    (lambda: cases.pressure_3d(16)[0], "GKOCG", "none", 1e-9),
+    (lambda: cases.pressure_3d(16)[0], "GKOCG", {"preconditioner": "BJ", "maxBlockSize": 4}, 1e-9),
+    (lambda: cases.momentum_3d(16)[0], "GKOBiCGStab", "BJ", 1e-10),
+    (lambda: cases.channel((16, 8, 8), (1, 1, 1))[0], "GKOGMRES", "BJ", 1e-8),
+])
+def test_plugin_solve_matches_oracle(oracle, builder, solver, precond, tol):
+    s = builder()
+    c = FoamCase(s)
+    try:
+        controls = dict(BASE, solver=solver, preconditioner=precond, tolerance=tol, krylovDim=30)
+        psi, name, r0, r1, it = c.solve("f", controls, s.psi, s.source)
+        pname = precond if isinstance(precond, str) else precond["preconditioner"]
+        mbs = 1 if isinstance(precond, str) else precond["maxBlockSize"]
+        assert name == f"{pname}cuda{solver}"
+        o = oracle.solve([oracle.assemble(s)], solver, pname, max_block_size=mbs, tolerance=tol,
+                         krylov_dim=30)
+        assert abs(it - o.n_iterations) <= 2
+        assert rel_l2(psi, o.x[0]) <= 1e-8
+        assert r0 == pytest.approx(o.init_residual, rel=1e-10) and r1 < tol
+    finally:
+        c.close()
+
+
+def test_time_steps_reuse_the_registry(oracle):
+    s = cases.pressure_3d(16)[0]
+    c = FoamCase(s)
+    try:
+        controls = dict(BASE, solver="GKOCG", preconditioner="BJ", tolerance=1e-9)
+        psi1, *_ , it1 = c.solve("p", controls, s.psi, s.source)
+        n_objects = c.registry_size()
+        # second time step: new coefficients (scaled matrix), new rhs; initial guess is the
+        # previous DEVICE solution whatever psi says (updateInitGuess false)
+        s2 = cases.pressure_3d(16)[0]
+        s2.diag, s2.upper = 2.0 * s.diag, 2.0 * s.upper
+        c.set_coeffs(s2)
+        psi2, _, _, _, it2 = c.solve("p", controls, np.full(s.n, 7.0), 3.0 * s.source)
+        assert c.registry_size() == n_objects          # nothing re-created
+        a = oracle.assemble(s2)
+        a.b = 3.0 * a.b
+        a.x = psi1.copy()
+        o = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-9)
+        assert abs(it2 - o.n_iterations) <= 2 and rel_l2(psi2, o.x[0]) <= 1e-8
+        # updateInitGuess true: psi is uploaded again
+        psi3, _, _, _, it3 = c.solve("p", dict(controls, updateInitGuess=True), np.zeros(s.n),
+                                     3.0 * s.source)
+        a.x = np.zeros(s.n)
+        o3 = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-9)
+        assert abs(it3 - o3.n_iterations) <= 2 and rel_l2(psi3, o3.x[0]) <= 1e-8
+    finally:
+        c.close()
+
+
+def test_unsupported_interfaces_and_preconditioners():
+    s = cases.channel((8, 4, 4), (1, 1, 1))[0]
+    s.interfaces[-1].kind = "cyclicAMI"
+    c = FoamCase(s)
+    try:
+        with pytest.raises(FoamFatalError, match="CyclicAMIFvPatch"):
+            c.solve("p", dict(BASE, solver="GKOCG", preconditioner="BJ"), s.psi, s.source)
+    finally:
+        c.close()
+    s = cases.pressure_3d(6)[0]
+    c = FoamCase(s)
+    try:
+        with pytest.raises(FoamFatalError, match="does not support the preconditioner: ILU"):
+            c.solve("p", dict(BASE, solver="GKOCG", preconditioner="ILU"), s.psi, s.source)
+    finally:
+        c.close()
