@@ -79,7 +79,7 @@ class FoamCase:
         return lib().foamshim_registry_size(self.h)
 
     def solve(self, field, controls, psi, source):
-        psi = np.ascontiguousarray(psi, np.float64)
+        psi = np.array(psi, dtype=np.float64)   # copy: the caller's psi stays untouched
         src = np.ascontiguousarray(source, np.float64)
         name = C.create_string_buffer(128)
         a, b, it = C.c_double(0), C.c_double(0), C.c_int(0)
