@@ -160,6 +160,22 @@ __global__ void k_compact_heads(label n, const label *__restrict__ rows,
     if (i == 0) row_ptrs[n_unique] = n;
 }
 
+// first row group whose row is >= tile * rows_per_tile (row_ids ascending)
+__global__ void k_tile_nl_ptr(label n_tiles, label rows_per_tile, label n_groups,
+                              const label *__restrict__ row_ids, label *tile_ptr)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    const int64_t want = t * rows_per_tile;
+    label lo = 0, hi = n_groups;
+    while (lo < hi) {
+        const label mid = (lo + hi) >> 1;
+        if (row_ids[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_ptr[t] = lo;
+}
+
 // coefficient gather (HostMatrix.C:685-703 row_gather + CsrMatrixWrapper.H:123-135
 // value copy, fused): vals[k] = scaling * staging[map[k]], the local interface
 // segment negated (HostMatrix.C:204).
@@ -343,6 +359,12 @@ int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
     OGL_TRY(dev_alloc(ctx, &ctx->d_nl_row_ids, n_halo));
     OGL_TRY(dev_alloc(ctx, &ctx->d_nl_row_ptrs, (size_t)n_halo + 1));
     ctx->have_nonlocal = true;
+    {
+        // per-tile ranges of the halo rows for the halo-fused stream SpMV (256-row tiles)
+        const label n_tiles = (ctx->n + 255) / 256;
+        OGL_TRY(dev_alloc(ctx, &ctx->d_tile_nl_ptr, (size_t)n_tiles + 1));
+        OGL_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_nl_ptr, 0, sizeof(label) * ((size_t)n_tiles + 1), st));
+    }
     if (n_halo == 0) return OGL_OK;
 
     label *d_keys = nullptr, *d_iota = nullptr, *d_head = nullptr, *d_scan = nullptr;
@@ -400,6 +422,11 @@ int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
     k_compact_heads<<<grid_for(n_halo), kThreads, 0, st>>>(
         n_halo, ctx->d_nl_rows, d_head, d_scan, ctx->d_nl_row_ids, ctx->d_nl_row_ptrs,
         ctx->n_nl_rows);
+    {
+        const label n_tiles = (ctx->n + 255) / 256;
+        k_tile_nl_ptr<<<grid_for((int64_t)n_tiles + 1), kThreads, 0, st>>>(
+            n_tiles, 256, ctx->n_nl_rows, ctx->d_nl_row_ids, ctx->d_tile_nl_ptr);
+    }
     e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess)

@@ -307,6 +307,8 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     } else if (k == "comm_mode") {
         if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "comm_mode in {0,1,2}");
         ctx->comm_mode = value;   // takes effect at the next ogl_partition_create / solve
+    } else if (k == "fused_halo") {
+        ctx->fused_halo = value != 0;
     } else if (k == "tile_blocked") {
         ctx->tile_blocked = value != 0;
     } else if (k == "tma_stages") {
@@ -343,6 +345,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "tma_stages") *value = ctx->tma_stages;
     else if (k == "tile_blocked") *value = ctx->tile_blocked;
     else if (k == "comm_mode") *value = ctx->comm_mode;
+    else if (k == "fused_halo") *value = ctx->fused_halo;
     else if (k == "p2p_active") *value = use_p2p(ctx) ? 1 : 0;
     else if (k == "max_row_len") *value = ctx->max_row_len;
     else if (k == "max_block_nnz") *value = ctx->max_block_nnz;

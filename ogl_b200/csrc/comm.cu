@@ -77,6 +77,28 @@ k_pack_p2p(label n_send, const label *__restrict__ idx, const double *__restrict
     }
 }
 
+// Stores only: the consumer kernel (halo-fused stream SpMV) publishes the
+// exchange on entry -- the kernel boundary orders these stores before its flag.
+__global__ void __launch_bounds__(256)
+k_pack_stores(label n_send, const label *__restrict__ idx, const double *__restrict__ x,
+              CommDev *c, SolveState *state, int guard_done)
+{
+    if (guard_done && state->done) return;
+    const unsigned long long seq = c->halo_seq + 1;
+    const int parity = (int)(seq & 1ull);
+    if (seq > 2 && threadIdx.x < c->n_targets) {
+        if (!wait_flag(&c->my_ack_flag[threadIdx.x], seq - 2)) state->comm_error = 1;
+    }
+    __syncthreads();
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_send) {
+        int t = 0;
+        while (k >= c->send_offs[t + 1]) ++t;
+        double *dst = c->peer_recv[t] + (size_t)parity * c->peer_recv_stride[t] + (k - c->send_offs[t]);
+        *dst = x[idx[k]];   // weak, coalesced per warp; published by the next kernel's release
+    }
+}
+
 struct Directory {
     int n_targets;
     int n_halo;
@@ -284,6 +306,22 @@ int comm_bench(Context *ctx, int mode, int reps, double *us)
     return OGL_OK;
 }
 
+// the halo-fused stream kernel needs the peer-memory path and SpMV variant 1
+bool fused_halo_ok(const Context *ctx)
+{
+    return use_p2p(ctx) && spmv_variant_in_use(ctx) == 1 && ctx->fused_halo != 0;
+}
+
+int pack_stores(Context *ctx, const double *x, bool guard_done)
+{
+    if (ctx->n_send == 0) return OGL_OK;
+    k_pack_stores<<<(ctx->n_send + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->n_send, ctx->d_send_idxs, x, ctx->d_commdev, ctx->d_state, guard_done ? 1 : 0);
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    return OGL_OK;
+}
+
 bool use_p2p(const Context *ctx)
 {
     return ctx->n_ranks > 1 && ctx->p2p_ready && ctx->comm_mode != 1;
@@ -409,6 +447,14 @@ int dist_spmv(Context *ctx, const SpmvArgs &a)
     }
     if (ctx->n_halo != ctx->n_send)
         return fail(ctx, OGL_ERR_INVALID, "halo pattern and partition disagree on the halo size");
+    if (fused_halo_ok(ctx)) {
+        // one kernel: local block + halo rows + all-reduce of the fused sums + epilogue
+        if (!a.halo_stored) OGL_TRY(pack_stores(ctx, a.x, a.guard_done));
+        SpmvArgs s = a;
+        s.inline_epi = true;
+        s.fused_halo = true;
+        return spmv_local(ctx, s);
+    }
     OGL_TRY(halo_begin(ctx, a.x, a.guard_done));
     SpmvArgs s = a;
     s.inline_epi = false;

@@ -122,6 +122,7 @@ struct Context {
 
     // peer-memory window (multi-GPU P2P path, comm.cu)
     int64_t comm_mode = 0;        // 0 auto, 1 NCCL send/recv + allreduce, 2 peer-memory (P2P)
+    int64_t fused_halo = 1;       // P2P: apply the non-local block inside the stream SpMV
     bool p2p_ready = false;
     void *d_window = nullptr;     // my window (exported through CUDA IPC)
     size_t window_bytes = 0;
@@ -135,6 +136,7 @@ struct Context {
     // CSR-like grouping of the non-local entries by row (rows touching the halo)
     label n_nl_rows = 0;
     label *d_nl_row_ids = nullptr, *d_nl_row_ptrs = nullptr;
+    label *d_tile_nl_ptr = nullptr;   // range of each 256-row tile in the row groups
 
     // values (a8/a9)
     bool have_values = false;
@@ -225,6 +227,8 @@ struct SpmvArgs {
     bool guard_done = false;            // early-exit when state->done
     int epi = 0;                        // scalar epilogue after the reduction (reduce.cuh)
     bool inline_epi = true;             // run it inside the kernel (single rank)
+    bool fused_halo = false;            // stream kernel applies the non-local block itself (P2P)
+    bool halo_stored = false;           // boundary values already stored by the previous kernel
 };
 int spmv_local(Context *ctx, const SpmvArgs &a);
 int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
@@ -247,6 +251,9 @@ int precond_apply(Context *ctx, const double *r, double *z, const double *dot_wi
 bool use_p2p(const Context *ctx);
 void comm_teardown(Context *ctx);
 int comm_bench(Context *ctx, int mode, int reps, double *us);
+int spmv_variant_in_use(const Context *ctx);
+bool fused_halo_ok(const Context *ctx);
+int pack_stores(Context *ctx, const double *x, bool guard_done);
 
 // solver.cu ----------------------------------------------------------------------
 int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res);

@@ -38,6 +38,9 @@ struct VecK {
     EpiArgs ea;
     const double *in0, *in1, *in2, *in3, *in4, *in5;
     double *out0, *out1, *out2, *out3;
+    const label *send_idx;   // fused halo pack (multi-GPU peer-memory path)
+    label n_send;
+    int pack;
 };
 
 #define GRID_STRIDE(i, n)                                                             \
@@ -101,14 +104,37 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_init_norms(const VecK
     grid_reduce<3>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
 }
 
-// cg::step_1   in0 = z (or r when unpreconditioned), out0 = p
-// 128-bit loads/stores (two rows per thread and trip), 8 CTAs of 256 threads per SM
+// cg::step_1   in0 = z (or r when unpreconditioned), in1 = p (previous), out0 = p (new)
+// Out of place (two p buffers alternate), so that on several GPUs the same
+// launch can ALSO compute the new p of the boundary cells and store it straight
+// into the neighbours' halo buffers (peer memory): no pack kernel, and the
+// stores are on their way before the SpMV starts.
+// 128-bit loads/stores (two rows per thread and trip).
 __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
 {
     if (a.guard_done && a.state->done) return;
     const bool p_is_z = a.state->flag_p_is_z != 0;
     const double t = a.state->coef_p;
+    if (a.pack) {
+        CommDev *c = a.ea.comm;
+        const unsigned long long seq = c->halo_seq + 1;
+        const int parity = (int)(seq & 1ull);
+        if (seq > 2 && threadIdx.x < c->n_targets) {
+            if (!wait_flag(&c->my_ack_flag[threadIdx.x], seq - 2)) a.state->comm_error = 1;
+        }
+        __syncthreads();
+        GRID_STRIDE(k, a.n_send) {
+            const label cell = a.send_idx[k];
+            const double z = a.in0[cell];
+            const double v = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.in1[cell]));
+            int tg = 0;
+            while (k >= c->send_offs[tg + 1]) ++tg;
+            double *dst = c->peer_recv[tg] + (size_t)parity * c->peer_recv_stride[tg] + (k - c->send_offs[tg]);
+            *dst = v;   // published by the SpMV kernel's release on entry
+        }
+    }
     const double2 *__restrict__ z2 = reinterpret_cast<const double2 *>(a.in0);
+    const double2 *__restrict__ po2 = reinterpret_cast<const double2 *>(a.in1);
     double2 *__restrict__ p2 = reinterpret_cast<double2 *>(a.out0);
     const int64_t n2 = a.n >> 1;
 #pragma unroll 2
@@ -116,7 +142,7 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
         const double2 z = z2[i];
         double2 p = z;
         if (!p_is_z) {
-            const double2 po = p2[i];
+            const double2 po = po2[i];
             p.x = __dadd_rn(z.x, __dmul_rn(t, po.x));
             p.y = __dadd_rn(z.y, __dmul_rn(t, po.y));
         }
@@ -125,7 +151,7 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
     if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = a.n - 1;
         const double z = a.in0[i];
-        a.out0[i] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.out0[i]));
+        a.out0[i] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.in1[i]));
     }
 }
 
@@ -394,14 +420,20 @@ int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, dou
     return finish_reduction(ctx, 3, epi, false);
 }
 
-static int cg_iteration(Context *ctx, double *r, double *z, double *p, double *q)
+static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old, double *p,
+                        double *q)
 {
     const int pk = pk_of(ctx);
     const double *zz = pk == 0 ? r : z;
+    const bool pack = fused_halo_ok(ctx) && ctx->n_send > 0;
     {
         VecK a = base_args(ctx, EPI_NONE, true);
         a.in0 = zz;
+        a.in1 = p_old;
         a.out0 = p;
+        a.send_idx = ctx->d_send_idxs;
+        a.n_send = ctx->n_send;
+        a.pack = pack ? 1 : 0;
         LAUNCH(k_cg_p, a);
     }
     {
@@ -412,6 +444,7 @@ static int cg_iteration(Context *ctx, double *r, double *z, double *p, double *q
         s.nred = 1;
         s.guard_done = true;
         s.epi = EPI_CG_BETA;
+        s.halo_stored = pack;
         OGL_TRY(dist_spmv(ctx, s));
     }
     {
@@ -536,7 +569,10 @@ int init_state(Context *ctx, const ogl_solve_params *p)
 template <typename F>
 static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F enqueue)
 {
-    const int chunk = (int)(ctx->chunk_iters < 1 ? 1 : ctx->chunk_iters);
+    // an even number of iterations per chunk: CG alternates two p buffers and a
+    // replayed chunk must end where it started
+    int chunk = (int)(ctx->chunk_iters < 1 ? 1 : ctx->chunk_iters);
+    chunk += chunk & 1;
     cudaStream_t st = ctx->stream;
     const bool graph_ok = ctx->use_graph && (ctx->n_ranks == 1 || use_p2p(ctx)) &&
                           ctx->profile_stride == 0;
@@ -619,10 +655,17 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     w = q;      // w and tmp are only live during the prologue
     tmp = pv;
     if (p->solver == OGL_SOLVER_CG) {
+        double *pv2;
+        OGL_TRY(get_work(ctx, 9, &pv2));
         OGL_TRY(solve_prologue(ctx, 0, r, z, nullptr, w, tmp, EPI_INIT_CHECK));
         OGL_CUDA(ctx, cudaMemsetAsync(pv, 0, sizeof(double) * ctx->n, st));
-        OGL_TRY(run_chunks(ctx, OGL_SOLVER_CG, p->max_iter,
-                           [&]() { return cg_iteration(ctx, r, z, pv, q); }));
+        OGL_CUDA(ctx, cudaMemsetAsync(pv2, 0, sizeof(double) * ctx->n, st));
+        int flip = 0;   // the two p buffers alternate; a chunk holds an even number of iterations
+        OGL_TRY(run_chunks(ctx, OGL_SOLVER_CG, p->max_iter, [&]() {
+            double *p_old = flip ? pv2 : pv, *p_new = flip ? pv : pv2;
+            flip ^= 1;
+            return cg_iteration(ctx, r, z, p_old, p_new, q);
+        }));
     } else {
         double *rr, *v, *s, *t, *y;
         OGL_TRY(get_work(ctx, 4, &rr));

@@ -47,6 +47,10 @@ struct SpmvK {
     label n;
     label n_row_blocks;   // stream kernel: ceil(n / kRowsPerBlock)
     int blocked;          // 1: each CTA walks a CONTIGUOUS range of tiles (x reuse in L1)
+    // halo-fused stream kernel (multi-GPU, peer-memory path): non-local rows grouped by tile
+    const label *tile_nl_ptr;   // [n_row_blocks + 1] range of each tile in the non-local row groups
+    const label *nl_row_ids, *nl_row_ptrs, *nl_cols;
+    const double *nl_vals;
     double alpha, beta;
     const double *dot_with;
     double *partials;
@@ -82,13 +86,30 @@ __device__ __forceinline__ void tile_range(int blocked, label worker, label n_wo
     }
 }
 
-template <bool ADV, int NRED>
+// HALO (multi-GPU, peer-memory path): the kernel is the whole distributed
+// operator.  The boundary values were stored into the neighbours' windows by
+// the PREVIOUS kernel on the stream (the fused p-update or k_pack_stores); block
+// 0 publishes them (data flags) on entry, tiles that own halo rows wait for the
+// neighbours' flags -- which arrive while interior tiles are being processed --
+// and add the non-local entries after the local row sums (Ginkgo's order:
+// local apply, then `y += A_nl * recv`).  The last CTA acknowledges the
+// exchange; the fused sums are all-reduced in grid_reduce's last block.
+template <bool ADV, int NRED, bool HALO>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSM)
 k_spmv_stream(const SpmvK a)
 {
     if (a.guard_done && a.state->done) return;
     extern __shared__ double prod[];
     const int tid = threadIdx.x;
+    CommDev *c = HALO ? a.ea.comm : nullptr;
+    unsigned long long seq = 0;
+    const double *recv = nullptr;
+    bool halo_ready = false;
+    if (HALO) {
+        seq = c->halo_seq + 1;
+        if (blockIdx.x == 0 && tid < c->n_targets) st_flag(c->peer_data_flag[tid], seq);
+        recv = c->my_recv + (size_t)(seq & 1ull) * c->my_recv_stride;
+    }
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
@@ -144,7 +165,57 @@ k_spmv_stream(const SpmvK a)
             if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
             if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
         }
+        if (HALO) {
+            const label h0 = a.tile_nl_ptr[rb], h1 = a.tile_nl_ptr[rb + 1];
+            if (h1 > h0) {   // block-uniform: this tile owns rows that touch the halo
+                if (!halo_ready) {
+                    if (tid < c->n_targets && !wait_flag(&c->my_data_flag[tid], seq))
+                        a.state->comm_error = 1;
+                    halo_ready = true;
+                }
+                __syncthreads();   // neighbours' data visible; this tile's y written
+                for (label u = h0 + tid; u < h1; u += kStreamThreads) {
+                    const label row = a.nl_row_ids[u];
+                    const double y_old = a.y[row];
+                    double acc = y_old;
+                    for (label q = a.nl_row_ptrs[u]; q < a.nl_row_ptrs[u + 1]; ++q) {
+                        double h;
+                        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
+                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
+                    }
+                    a.y[row] = acc;
+                    if (NRED >= 1) {
+                        const double d = a.dot_with[row];
+                        red[0] = __dadd_rn(red[0], __dmul_rn(d, acc) - __dmul_rn(d, y_old));
+                    }
+                    if (NRED >= 2)
+                        red[1] = __dadd_rn(red[1], __dmul_rn(acc, acc) - __dmul_rn(y_old, y_old));
+                }
+            }
+        }
         __syncthreads();   // prod is overwritten by the next row block
+    }
+    if (HALO) {
+        // the last CTA to get here closes the exchange: acknowledge to the
+        // neighbours (their buffer of this parity may be reused) and advance seq
+        __shared__ bool last_cta;
+        if (tid == 0) {
+            __threadfence();
+            last_cta = (atomicAdd(&c->nl_ticket, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last_cta) {
+            if (tid < c->n_targets) {
+                // a CTA without halo tiles has not waited: make sure the exchange is complete
+                if (!wait_flag(&c->my_data_flag[tid], seq)) a.state->comm_error = 1;
+                st_flag(c->peer_ack_flag[tid], seq);
+            }
+            if (tid == 0) {
+                c->halo_seq = seq;
+                c->nl_ticket = 0u;
+            }
+        }
+        __syncthreads();
     }
     if (NRED > 0)
         grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
@@ -658,6 +729,7 @@ int spmv_setup(Context *ctx)
     return OGL_OK;
 }
 
+int spmv_variant_in_use(const Context *ctx);
 static int pick_variant(const Context *ctx)
 {
     if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 5) return (int)ctx->spmv_variant;
@@ -667,6 +739,8 @@ static int pick_variant(const Context *ctx)
     if (smem <= (size_t)kStreamSmemMax && mean_len <= 48.0) return 1;
     return mean_len >= 16.0 ? 3 : 2;
 }
+
+int spmv_variant_in_use(const Context *ctx) { return pick_variant(ctx); }
 
 int spmv_local(Context *ctx, const SpmvArgs &sa)
 {
@@ -683,6 +757,9 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.n = ctx->n;
     k.n_row_blocks = 0;
     k.blocked = ctx->tile_blocked ? 1 : 0;
+    k.tile_nl_ptr = nullptr;
+    k.nl_row_ids = k.nl_row_ptrs = k.nl_cols = nullptr;
+    k.nl_vals = nullptr;
     k.alpha = sa.alpha;
     k.beta = sa.beta;
     k.dot_with = sa.dot_with;
@@ -713,19 +790,44 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(k_spmv_stream<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_stream<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_stream<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_stream<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_stream<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_stream<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+#define SET_ATTR(A, R)                                                                             \
+    cudaFuncSetAttribute(k_spmv_stream<A, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                         kStreamSmemMax);                                                          \
+    cudaFuncSetAttribute(k_spmv_stream<A, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                         kStreamSmemMax);
+            SET_ATTR(false, 0) SET_ATTR(false, 1) SET_ATTR(false, 2)
+            SET_ATTR(true, 0) SET_ATTR(true, 1) SET_ATTR(true, 2)
+#undef SET_ATTR
             attr_set = true;
         }
         const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
         k.n_row_blocks = nblk;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
         const int grid = nblk < cap ? nblk : (int)cap;
-        DISPATCH(k_spmv_stream, grid, kStreamThreads, smem);
+#define STREAM_LAUNCH(H)                                                                          \
+    do {                                                                                          \
+        if (sa.advanced) {                                                                        \
+            if (nred == 0) k_spmv_stream<true, 0, H><<<grid, kStreamThreads, smem, st>>>(k);      \
+            else if (nred == 1) k_spmv_stream<true, 1, H><<<grid, kStreamThreads, smem, st>>>(k); \
+            else k_spmv_stream<true, 2, H><<<grid, kStreamThreads, smem, st>>>(k);                \
+        } else {                                                                                  \
+            if (nred == 0) k_spmv_stream<false, 0, H><<<grid, kStreamThreads, smem, st>>>(k);     \
+            else if (nred == 1) k_spmv_stream<false, 1, H><<<grid, kStreamThreads, smem, st>>>(k);\
+            else k_spmv_stream<false, 2, H><<<grid, kStreamThreads, smem, st>>>(k);               \
+        }                                                                                         \
+    } while (0)
+        if (sa.fused_halo) {
+            k.tile_nl_ptr = ctx->d_tile_nl_ptr;
+            k.nl_row_ids = ctx->d_nl_row_ids;
+            k.nl_row_ptrs = ctx->d_nl_row_ptrs;
+            k.nl_cols = ctx->d_nl_cols;
+            k.nl_vals = ctx->d_nl_vals;
+            k.ea = make_epi_args(ctx, nred);
+            STREAM_LAUNCH(true);
+        } else {
+            STREAM_LAUNCH(false);
+        }
+#undef STREAM_LAUNCH
     } else if (variant == 5) {
         const int warp_cap = (int)((ctx->max_warp_nnz + 1) & ~(int64_t)1);
         const size_t smem = (size_t)warp_cap * sizeof(double) * (kWarpCtaThreads / 32);

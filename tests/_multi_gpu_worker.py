@@ -29,12 +29,14 @@ def main():
     ps = init_from_env("nccl")
     db = ObjectRegistry()
     results = {}
-    # every case on both data paths: peer-memory windows (default) and NCCL
+    # every case on the three data paths: 0 peer-memory windows with the halo fused into
+    # the SpMV (default), 1 NCCL, 2 peer-memory windows with separate pack / non-local kernels
     for name, (builder, solver, precond, mbs, tol), mode in (
-            (n, c, m) for n, c in CASES.items() for m in (0, 1)):
+            (n, c, m) for n, c in CASES.items() for m in (0, 1, 2)):
         s = builder(procs)[ps.rank]
         controls = {"solver": solver, "executor": "cuda", "tolerance": tol, "relTol": 0.0,
-                    "adaptMinIter": False, "krylovDim": 30, "comm_mode": mode,
+                    "adaptMinIter": False, "krylovDim": 30, "comm_mode": 1 if mode == 1 else 0,
+                    "fused_halo": 0 if mode == 2 else 1,
                     "preconditioner": {"preconditioner": precond, "maxBlockSize": mbs}}
         name = f"{name}@{mode}"
         sol = lduMatrix_solver_New(name, s, controls, db, ps)

@@ -43,9 +43,9 @@ def test_decomposed_solves_match_oracle(oracle, tmp_path, procs):
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     res = [json.load(open(f"{out}.{r}")) for r in range(world)]
     assert res[0]["pressure_cg@0"]["p2p"] == 1, "peer-memory path not active on an NVLink box"
-    assert res[0]["pressure_cg@1"]["p2p"] == 0
+    assert res[0]["pressure_cg@1"]["p2p"] == 0 and res[0]["pressure_cg@2"]["p2p"] == 1
     for name, (builder, solver, precond, mbs, tol) in (
-            (f"{n}@{m}", c) for n, c in CASES.items() for m in (0, 1)):
+            (f"{n}@{m}", c) for n, c in CASES.items() for m in (0, 1, 2)):
         systems = builder(procs)
         asms = [oracle.assemble(s) for s in systems]
         o = oracle.solve(asms, solver, precond, max_block_size=mbs, tolerance=tol, krylov_dim=30)
