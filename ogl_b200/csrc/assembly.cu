@@ -176,6 +176,12 @@ __global__ void k_tile_nl_ptr(label n_tiles, label rows_per_tile, label n_groups
     tile_ptr[t] = lo;
 }
 
+__global__ void k_nl_rowmask(label n_groups, const label *__restrict__ row_ids, unsigned int *mask)
+{
+    const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u < n_groups) atomicOr(&mask[row_ids[u] >> 5], 1u << (row_ids[u] & 31));
+}
+
 // coefficient gather (HostMatrix.C:685-703 row_gather + CsrMatrixWrapper.H:123-135
 // value copy, fused): vals[k] = scaling * staging[map[k]], the local interface
 // segment negated (HostMatrix.C:204).
@@ -364,6 +370,9 @@ int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
         const label n_tiles = (ctx->n + 255) / 256;
         OGL_TRY(dev_alloc(ctx, &ctx->d_tile_nl_ptr, (size_t)n_tiles + 1));
         OGL_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_nl_ptr, 0, sizeof(label) * ((size_t)n_tiles + 1), st));
+        const size_t words = (size_t)n_tiles * 8 + 8;
+        OGL_TRY(dev_alloc(ctx, &ctx->d_nl_rowmask, words));
+        OGL_CUDA(ctx, cudaMemsetAsync(ctx->d_nl_rowmask, 0, sizeof(unsigned int) * words, st));
     }
     if (n_halo == 0) return OGL_OK;
 
@@ -426,6 +435,8 @@ int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
         const label n_tiles = (ctx->n + 255) / 256;
         k_tile_nl_ptr<<<grid_for((int64_t)n_tiles + 1), kThreads, 0, st>>>(
             n_tiles, 256, ctx->n_nl_rows, ctx->d_nl_row_ids, ctx->d_tile_nl_ptr);
+        k_nl_rowmask<<<grid_for(ctx->n_nl_rows), kThreads, 0, st>>>(ctx->n_nl_rows, ctx->d_nl_row_ids,
+                                                                   ctx->d_nl_rowmask);
     }
     e = cudaStreamSynchronize(st);
     cleanup();

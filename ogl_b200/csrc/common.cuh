@@ -137,6 +137,7 @@ struct Context {
     label n_nl_rows = 0;
     label *d_nl_row_ids = nullptr, *d_nl_row_ptrs = nullptr;
     label *d_tile_nl_ptr = nullptr;   // range of each 256-row tile in the row groups
+    unsigned int *d_nl_rowmask = nullptr;   // bit per row: owns non-local entries
 
     // values (a8/a9)
     bool have_values = false;

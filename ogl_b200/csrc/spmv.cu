@@ -49,6 +49,7 @@ struct SpmvK {
     int blocked;          // 1: each CTA walks a CONTIGUOUS range of tiles (x reuse in L1)
     // halo-fused stream kernel (multi-GPU, peer-memory path): non-local rows grouped by tile
     const label *tile_nl_ptr;   // [n_row_blocks + 1] range of each tile in the non-local row groups
+    const unsigned int *nl_rowmask;   // bit r set: row r owns non-local entries
     const label *nl_row_ids, *nl_row_ptrs, *nl_cols;
     const double *nl_vals;
     double alpha, beta;
@@ -128,6 +129,29 @@ k_spmv_stream(const SpmvK a)
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
         }
+        // HALO: does my row own non-local entries, and which row group is it?
+        // (bit mask over the rows + the tile's first group: O(1), 32 B per tile)
+        label my_group = -1;
+        if (HALO) {
+            const label h0 = __ldg(&a.tile_nl_ptr[rb]), h1 = __ldg(&a.tile_nl_ptr[rb + 1]);
+            if (h1 > h0) {   // block-uniform
+                if (!halo_ready) {
+                    // first tile with halo rows: the neighbours' data must have landed
+                    // (the barrier after the product phase makes every thread wait on it)
+                    if (tid < c->n_targets && !wait_flag(&c->my_data_flag[tid], seq))
+                        a.state->comm_error = 1;
+                    halo_ready = true;
+                }
+                const int w = tid >> 5, lane = tid & 31;
+                const unsigned int *mk = a.nl_rowmask + (size_t)rb * (kRowsPerBlock / 32);
+                const unsigned int mine = __ldg(&mk[w]);
+                if ((mine >> lane) & 1u) {
+                    label before = __popc(mine & ((1u << lane) - 1u));
+                    for (int j = 0; j < w; ++j) before += __popc(__ldg(&mk[j]));
+                    my_group = h0 + before;
+                }
+            }
+        }
         // ---- stream the slice: coalesced value/column loads, gathered x.
         // All of a thread's entries of the slice are requested in ONE batch
         // (kBatchStream independent loads of columns, of values, then of x), so a row
@@ -161,37 +185,17 @@ k_spmv_stream(const SpmvK a)
             const label row = r0 + tid;
             double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
+            if (HALO && my_group >= 0) {
+                // y += A_nl * recv for this row, entry by entry after the local sum
+                for (label q = a.nl_row_ptrs[my_group]; q < a.nl_row_ptrs[my_group + 1]; ++q) {
+                    double h;
+                    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
+                    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
+                }
+            }
             a.y[row] = sum;
             if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
             if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
-        }
-        if (HALO) {
-            const label h0 = a.tile_nl_ptr[rb], h1 = a.tile_nl_ptr[rb + 1];
-            if (h1 > h0) {   // block-uniform: this tile owns rows that touch the halo
-                if (!halo_ready) {
-                    if (tid < c->n_targets && !wait_flag(&c->my_data_flag[tid], seq))
-                        a.state->comm_error = 1;
-                    halo_ready = true;
-                }
-                __syncthreads();   // neighbours' data visible; this tile's y written
-                for (label u = h0 + tid; u < h1; u += kStreamThreads) {
-                    const label row = a.nl_row_ids[u];
-                    const double y_old = a.y[row];
-                    double acc = y_old;
-                    for (label q = a.nl_row_ptrs[u]; q < a.nl_row_ptrs[u + 1]; ++q) {
-                        double h;
-                        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
-                        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
-                    }
-                    a.y[row] = acc;
-                    if (NRED >= 1) {
-                        const double d = a.dot_with[row];
-                        red[0] = __dadd_rn(red[0], __dmul_rn(d, acc) - __dmul_rn(d, y_old));
-                    }
-                    if (NRED >= 2)
-                        red[1] = __dadd_rn(red[1], __dmul_rn(acc, acc) - __dmul_rn(y_old, y_old));
-                }
-            }
         }
         __syncthreads();   // prod is overwritten by the next row block
     }
@@ -758,6 +762,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.n_row_blocks = 0;
     k.blocked = ctx->tile_blocked ? 1 : 0;
     k.tile_nl_ptr = nullptr;
+    k.nl_rowmask = nullptr;
     k.nl_row_ids = k.nl_row_ptrs = k.nl_cols = nullptr;
     k.nl_vals = nullptr;
     k.alpha = sa.alpha;
@@ -818,6 +823,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     } while (0)
         if (sa.fused_halo) {
             k.tile_nl_ptr = ctx->d_tile_nl_ptr;
+            k.nl_rowmask = ctx->d_nl_rowmask;
             k.nl_row_ids = ctx->d_nl_row_ids;
             k.nl_row_ptrs = ctx->d_nl_row_ptrs;
             k.nl_cols = ctx->d_nl_cols;
