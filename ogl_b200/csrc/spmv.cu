@@ -36,6 +36,7 @@ constexpr int kBatch = 8;            // entries per thread requested at once (7-
 constexpr int kBatchStream = 7;      // stream kernel: 48-register budget (5 CTAs per SM)
 constexpr int kStreamCtasPerSM = 5;  // <= 51 registers per thread
 constexpr int kMaxTilesPerCta = 1024; // row-block extents cached in shared memory
+constexpr int kHaloEarly = 3;         // halo products of a row prefetched with the tile's loads
 
 struct SpmvK {
     const label *row_ptrs;
@@ -105,11 +106,16 @@ k_spmv_stream(const SpmvK a)
     CommDev *c = HALO ? a.ea.comm : nullptr;
     unsigned long long seq = 0;
     const double *recv = nullptr;
-    bool halo_ready = false;
     if (HALO) {
         seq = c->halo_seq + 1;
         if (blockIdx.x == 0 && tid < c->n_targets) st_flag(c->peer_data_flag[tid], seq);
         recv = c->my_recv + (size_t)(seq & 1ull) * c->my_recv_stride;
+        // The neighbours stored their boundary values during THEIR previous kernel
+        // and publish them on entry of this one, so this wait is the rank skew plus
+        // one NVLink flag latency; afterwards halo operands can be prefetched with
+        // the rest of a tile's loads.
+        if (tid < c->n_targets && !wait_flag(&c->my_data_flag[tid], seq)) a.state->comm_error = 1;
+        __syncthreads();
     }
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
@@ -129,26 +135,32 @@ k_spmv_stream(const SpmvK a)
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
         }
-        // HALO: does my row own non-local entries, and which row group is it?
-        // (bit mask over the rows + the tile's first group: O(1), 32 B per tile)
-        label my_group = -1;
+        // HALO: does my row own non-local entries?  (bit mask over the rows + the
+        // tile's first row group: O(1), 32 B per tile.)  Its first kHaloEarly
+        // products are fetched NOW, together with the tile's own loads, and added
+        // after the local row sum; otherwise one or two threads per tile would
+        // serialise three dependent L2 round trips behind the tile barrier.
+        label hq = 0, hqe = 0;
+        double hp[kHaloEarly];
         if (HALO) {
             const label h0 = __ldg(&a.tile_nl_ptr[rb]), h1 = __ldg(&a.tile_nl_ptr[rb + 1]);
             if (h1 > h0) {   // block-uniform
-                if (!halo_ready) {
-                    // first tile with halo rows: the neighbours' data must have landed
-                    // (the barrier after the product phase makes every thread wait on it)
-                    if (tid < c->n_targets && !wait_flag(&c->my_data_flag[tid], seq))
-                        a.state->comm_error = 1;
-                    halo_ready = true;
-                }
                 const int w = tid >> 5, lane = tid & 31;
                 const unsigned int *mk = a.nl_rowmask + (size_t)rb * (kRowsPerBlock / 32);
                 const unsigned int mine = __ldg(&mk[w]);
                 if ((mine >> lane) & 1u) {
                     label before = __popc(mine & ((1u << lane) - 1u));
                     for (int j = 0; j < w; ++j) before += __popc(__ldg(&mk[j]));
-                    my_group = h0 + before;
+                    hq = __ldg(&a.nl_row_ptrs[h0 + before]);
+                    hqe = __ldg(&a.nl_row_ptrs[h0 + before + 1]);
+#pragma unroll
+                    for (int j = 0; j < kHaloEarly; ++j) {
+                        if (hq + j < hqe) {
+                            double h;
+                            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq + j])) : "memory");
+                            hp[j] = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq + j])), h);
+                        }
+                    }
                 }
             }
         }
@@ -185,9 +197,12 @@ k_spmv_stream(const SpmvK a)
             const label row = r0 + tid;
             double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
-            if (HALO && my_group >= 0) {
+            if (HALO && hqe > hq) {
                 // y += A_nl * recv for this row, entry by entry after the local sum
-                for (label q = a.nl_row_ptrs[my_group]; q < a.nl_row_ptrs[my_group + 1]; ++q) {
+#pragma unroll
+                for (int j = 0; j < kHaloEarly; ++j)
+                    if (hq + j < hqe) sum = __dadd_rn(sum, hp[j]);
+                for (label q = hq + kHaloEarly; q < hqe; ++q) {
                     double h;
                     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
                     sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
@@ -209,11 +224,7 @@ k_spmv_stream(const SpmvK a)
         }
         __syncthreads();
         if (last_cta) {
-            if (tid < c->n_targets) {
-                // a CTA without halo tiles has not waited: make sure the exchange is complete
-                if (!wait_flag(&c->my_data_flag[tid], seq)) a.state->comm_error = 1;
-                st_flag(c->peer_ack_flag[tid], seq);
-            }
+            if (tid < c->n_targets) st_flag(c->peer_ack_flag[tid], seq);
             if (tid == 0) {
                 c->halo_seq = seq;
                 c->nl_ticket = 0u;
