@@ -135,35 +135,8 @@ k_spmv_stream(const SpmvK a)
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
         }
-        // HALO: does my row own non-local entries?  (bit mask over the rows + the
-        // tile's first row group: O(1), 32 B per tile.)  Its first kHaloEarly
-        // products are fetched NOW, together with the tile's own loads, and added
-        // after the local row sum; otherwise one or two threads per tile would
-        // serialise three dependent L2 round trips behind the tile barrier.
         label hq = 0, hqe = 0;
         double hp[kHaloEarly];
-        if (HALO) {
-            const label h0 = __ldg(&a.tile_nl_ptr[rb]), h1 = __ldg(&a.tile_nl_ptr[rb + 1]);
-            if (h1 > h0) {   // block-uniform
-                const int w = tid >> 5, lane = tid & 31;
-                const unsigned int *mk = a.nl_rowmask + (size_t)rb * (kRowsPerBlock / 32);
-                const unsigned int mine = __ldg(&mk[w]);
-                if ((mine >> lane) & 1u) {
-                    label before = __popc(mine & ((1u << lane) - 1u));
-                    for (int j = 0; j < w; ++j) before += __popc(__ldg(&mk[j]));
-                    hq = __ldg(&a.nl_row_ptrs[h0 + before]);
-                    hqe = __ldg(&a.nl_row_ptrs[h0 + before + 1]);
-#pragma unroll
-                    for (int j = 0; j < kHaloEarly; ++j) {
-                        if (hq + j < hqe) {
-                            double h;
-                            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq + j])) : "memory");
-                            hp[j] = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq + j])), h);
-                        }
-                    }
-                }
-            }
-        }
         // ---- stream the slice: coalesced value/column loads, gathered x.
         // All of a thread's entries of the slice are requested in ONE batch
         // (kBatchStream independent loads of columns, of values, then of x), so a row
@@ -182,6 +155,49 @@ k_spmv_stream(const SpmvK a)
             for (int u = 0; u < kBatchStream; ++u) {
                 const label q = base + tid + u * kStreamThreads;
                 v[u] = q < len ? __ldcs(&a.vals[s + q]) : 0.0;
+            }
+            if (HALO && base == 0) {
+            // (issued after the tile's own column/value loads so that its dependent
+            // loads overlap their HBM latency)
+            // HALO: does my row own non-local entries?  (bit mask over the rows + the
+            // tile's first row group: O(1), 32 B per tile.)  Its first kHaloEarly
+            // products are fetched NOW, together with the tile's own loads, and added
+            // after the local row sum; otherwise one or two threads per tile would
+            // serialise three dependent L2 round trips behind the tile barrier.
+            {
+                // one load per lane: lanes 0..7 fetch the tile's 8 mask words, lanes 8/9 the
+                // tile's row-group range; everything else is shuffles and popcounts
+                const int w = tid >> 5, lane = tid & 31;
+                unsigned int word = 0;
+                if (lane < kRowsPerBlock / 32)
+                    word = __ldg(&a.nl_rowmask[(size_t)rb * (kRowsPerBlock / 32) + lane]);
+                else if (lane < kRowsPerBlock / 32 + 2)
+                    word = (unsigned int)__ldg(&a.tile_nl_ptr[rb + (lane - kRowsPerBlock / 32)]);
+                const label h0 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32);
+                const label h1 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32 + 1);
+                if (h1 > h0) {   // block-uniform
+                    const unsigned int mine = __shfl_sync(0xffffffffu, word, w);
+                    label before = 0;
+    #pragma unroll
+                    for (int j = 0; j < kRowsPerBlock / 32; ++j) {
+                        const unsigned int mj = __shfl_sync(0xffffffffu, word, j);
+                        if (j < w) before += __popc(mj);
+                    }
+                    if ((mine >> lane) & 1u) {
+                        before += __popc(mine & ((1u << lane) - 1u));
+                        hq = __ldg(&a.nl_row_ptrs[h0 + before]);
+                        hqe = __ldg(&a.nl_row_ptrs[h0 + before + 1]);
+    #pragma unroll
+                        for (int j = 0; j < kHaloEarly; ++j) {
+                            if (hq + j < hqe) {
+                                double h;
+                                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq + j])) : "memory");
+                                hp[j] = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq + j])), h);
+                            }
+                        }
+                    }
+                }
+            }
             }
 #pragma unroll
             for (int u = 0; u < kBatchStream; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
