@@ -295,7 +295,7 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     if (!key) return fail(ctx, OGL_ERR_INVALID, "null option key");
     const std::string k(key);
     if (k == "spmv_variant") {
-        if (value < 0 || value > 5) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,5]");
+        if (value < 0 || value > 6) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,6]");
         ctx->spmv_variant = value;
     } else if (k == "chunk_iters") {
         if (value < 1) return fail(ctx, OGL_ERR_INVALID, "chunk_iters >= 1");

@@ -254,6 +254,111 @@ k_spmv_stream(const SpmvK a)
 }
 
 // ---------------------------------------------------------------------------
+// Variant 6: software-pipelined stream.  Same tiles and arithmetic as variant 1,
+// but the (column, value) loads of the NEXT tile are issued -- into the very
+// registers the current tile has just finished with -- before the CTA goes
+// into its barrier / row-sum phase, and the next tile's extents one tile
+// earlier still.  The HBM stream of a CTA therefore never pauses while it
+// gathers x and adds rows: bytes in flight per SM stay at the level that
+// variant 1 only reaches during its load phase.
+// ---------------------------------------------------------------------------
+template <bool ADV, int NRED>
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSM)
+k_spmv_pipe(const SpmvK a)
+{
+    if (a.guard_done && a.state->done) return;
+    extern __shared__ double prod[];
+    const int tid = threadIdx.x;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    label rb, t_last, t_step;
+    tile_range(a.blocked, blockIdx.x, gridDim.x, a.n_row_blocks, rb, t_last, t_step);
+    label s = 0, e = 0;
+    if (rb < t_last) {
+        s = __ldg(&a.row_ptrs[rb * kRowsPerBlock]);
+        e = __ldg(&a.row_ptrs[min((rb + 1) * kRowsPerBlock, a.n)]);
+    }
+    label c[kBatchStream];
+    double v[kBatchStream];
+    // prologue: first batch of the first tile
+#pragma unroll
+    for (int u = 0; u < kBatchStream; ++u) {
+        const label q = tid + u * kStreamThreads;
+        c[u] = q < e - s ? __ldcs(&a.cols[s + q]) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatchStream; ++u) {
+        const label q = tid + u * kStreamThreads;
+        v[u] = q < e - s ? __ldcs(&a.vals[s + q]) : 0.0;
+    }
+    for (; rb < t_last; rb += t_step) {
+        const label r0 = rb * kRowsPerBlock;
+        const label nr = min((label)kRowsPerBlock, a.n - r0);
+        const label len = e - s;
+        // extents of the next tile: needed when this tile's products are parked
+        const label rbn = rb + t_step;
+        label s2 = 0, e2 = 0;
+        if (rbn < t_last) {
+            s2 = __ldg(&a.row_ptrs[rbn * kRowsPerBlock]);
+            e2 = __ldg(&a.row_ptrs[min((rbn + 1) * kRowsPerBlock, a.n)]);
+        }
+        label rs = 0, re = 0;
+        if (tid < nr) {
+            rs = __ldg(&a.row_ptrs[r0 + tid]);
+            re = __ldg(&a.row_ptrs[r0 + tid + 1]);
+        }
+        // ---- gather x for the batch already in registers, park the products
+        {
+            double xv[kBatchStream];
+#pragma unroll
+            for (int u = 0; u < kBatchStream; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < kBatchStream; ++u) {
+                const label q = tid + u * kStreamThreads;
+                if (q < len) prod[q] = prod_of(v[u], xv[u], a.alpha, ADV);
+            }
+        }
+        // ---- tiles longer than one batch: the rest without prefetch
+        for (label base = kBatchStream * kStreamThreads; base < len; base += kBatchStream * kStreamThreads) {
+#pragma unroll
+            for (int u = 0; u < kBatchStream; ++u) {
+                const label q = base + tid + u * kStreamThreads;
+                if (q < len)
+                    prod[q] = prod_of(__ldcs(&a.vals[s + q]), __ldg(&a.x[__ldcs(&a.cols[s + q])]), a.alpha, ADV);
+            }
+        }
+        // ---- prefetch the next tile's first batch into the freed registers
+#pragma unroll
+        for (int u = 0; u < kBatchStream; ++u) {
+            const label q = tid + u * kStreamThreads;
+            c[u] = q < e2 - s2 ? __ldcs(&a.cols[s2 + q]) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatchStream; ++u) {
+            const label q = tid + u * kStreamThreads;
+            v[u] = q < e2 - s2 ? __ldcs(&a.vals[s2 + q]) : 0.0;
+        }
+        __syncthreads();
+        // ---- one thread per row: left-to-right sum of its products
+        if (tid < nr) {
+            const label row = r0 + tid;
+            double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+            for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
+            a.y[row] = sum;
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
+            if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+        }
+        __syncthreads();   // prod is overwritten by the next row block
+        s = s2;
+        e = e2;
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
+// ---------------------------------------------------------------------------
 // Variant 4: TMA-fed persistent pipeline.
 //
 // One producer lane per CTA walks the CTA's row blocks ahead of the consumers
@@ -763,7 +868,7 @@ int spmv_setup(Context *ctx)
 int spmv_variant_in_use(const Context *ctx);
 static int pick_variant(const Context *ctx)
 {
-    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 5) return (int)ctx->spmv_variant;
+    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 6) return (int)ctx->spmv_variant;
     const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
     const double mean_len = ctx->n > 0 ? (double)ctx->nnz / ctx->n : 0.0;
     // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
@@ -861,6 +966,23 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
             STREAM_LAUNCH(false);
         }
 #undef STREAM_LAUNCH
+    } else if (variant == 6) {
+        const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
+        static bool attr6 = false;
+        if (!attr6) {
+            cudaFuncSetAttribute(k_spmv_pipe<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_pipe<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_pipe<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_pipe<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_pipe<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            cudaFuncSetAttribute(k_spmv_pipe<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+            attr6 = true;
+        }
+        const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
+        k.n_row_blocks = nblk;
+        const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
+        const int grid = nblk < cap ? nblk : (int)cap;
+        DISPATCH(k_spmv_pipe, grid, kStreamThreads, smem);
     } else if (variant == 5) {
         const int warp_cap = (int)((ctx->max_warp_nnz + 1) & ~(int64_t)1);
         const size_t smem = (size_t)warp_cap * sizeof(double) * (kWarpCtaThreads / 32);

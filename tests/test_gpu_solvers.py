@@ -160,7 +160,7 @@ def test_graph_and_stream_paths_agree(ctx):
 def test_cg_with_every_spmv_kernel(ctx, oracle):
     s = cases.pressure_3d(20)[0]
     outs = []
-    for variant in (1, 2, 3, 4, 5):
+    for variant in (1, 2, 3, 4, 5, 6):
         ctx.set_option("spmv_variant", variant)
         r, o, x = check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", tolerance=1e-9)
         outs.append(r.n_iterations)

@@ -31,10 +31,10 @@ def main():
                               hbm_read_8p4_gbs=round(ctx.membench(2), 1))), flush=True)
         b_spmv = 12 * nnz + 4 * (s.n + 1) + 16 * s.n
         b_pcg = 12 * nnz + 4 * (s.n + 1) + 96 * s.n
-        for variant, ctas, stages, blocked in itertools.product((1, 5, 4), (0,), (2, 3), (0, 1)):
-            if variant != 4 and stages != 3:
-                continue
+        for variant, ctas, stages, blocked in itertools.product((1, 6, 4), (0, 148 * 4), (2,), (0,)):
             ctx.set_option("tile_blocked", blocked)
+            if variant == 4 and ctas:
+                continue
             ctx.set_option("tma_stages", stages)
             try:
                 ctx.set_option("spmv_variant", variant)
