@@ -306,10 +306,11 @@ int comm_bench(Context *ctx, int mode, int reps, double *us)
     return OGL_OK;
 }
 
-// the halo-fused stream kernel needs the peer-memory path and SpMV variant 1
+// the halo-fused stream kernels need the peer-memory path and SpMV variant 1 or 6
 bool fused_halo_ok(const Context *ctx)
 {
-    return use_p2p(ctx) && spmv_variant_in_use(ctx) == 1 && ctx->fused_halo != 0;
+    const int v = spmv_variant_in_use(ctx);
+    return use_p2p(ctx) && (v == 1 || v == 6) && ctx->fused_halo != 0;
 }
 
 int pack_stores(Context *ctx, const double *x, bool guard_done)

@@ -262,13 +262,22 @@ k_spmv_stream(const SpmvK a)
 // gathers x and adds rows: bytes in flight per SM stay at the level that
 // variant 1 only reaches during its load phase.
 // ---------------------------------------------------------------------------
-template <bool ADV, int NRED>
+template <bool ADV, int NRED, bool HALO>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSM)
 k_spmv_pipe(const SpmvK a)
 {
     if (a.guard_done && a.state->done) return;
     extern __shared__ double prod[];
     const int tid = threadIdx.x;
+    // HALO (multi-GPU, peer-memory path): see k_spmv_stream
+    CommDev *cm = HALO ? a.ea.comm : nullptr;
+    unsigned long long seq = 0;
+    const double *recv = nullptr;
+    if (HALO) {
+        seq = cm->halo_seq + 1;
+        if (blockIdx.x == 0 && tid < cm->n_targets) st_flag(cm->peer_data_flag[tid], seq);
+        recv = cm->my_recv + (size_t)(seq & 1ull) * cm->my_recv_stride;
+    }
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
@@ -292,6 +301,12 @@ k_spmv_pipe(const SpmvK a)
         const label q = tid + u * kStreamThreads;
         v[u] = q < e - s ? __ldcs(&a.vals[s + q]) : 0.0;
     }
+    if (HALO) {
+        // the first tile's loads are in flight; now make sure the neighbours'
+        // boundary values (stored during their previous kernel) are published
+        if (tid < cm->n_targets && !wait_flag(&cm->my_data_flag[tid], seq)) a.state->comm_error = 1;
+        __syncthreads();
+    }
     for (; rb < t_last; rb += t_step) {
         const label r0 = rb * kRowsPerBlock;
         const label nr = min((label)kRowsPerBlock, a.n - r0);
@@ -307,6 +322,42 @@ k_spmv_pipe(const SpmvK a)
         if (tid < nr) {
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
+        }
+        // HALO: first kHaloEarly products of my row's non-local entries, fetched now
+        // (mask word / row-group range: one load per lane + shuffles, see k_spmv_stream)
+        label hq = 0, hqe = 0;
+        double hp[kHaloEarly];
+        if (HALO) {
+            const int w = tid >> 5, lane = tid & 31;
+            unsigned int word = 0;
+            if (lane < kRowsPerBlock / 32)
+                word = __ldg(&a.nl_rowmask[(size_t)rb * (kRowsPerBlock / 32) + lane]);
+            else if (lane < kRowsPerBlock / 32 + 2)
+                word = (unsigned int)__ldg(&a.tile_nl_ptr[rb + (lane - kRowsPerBlock / 32)]);
+            const label h0 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32);
+            const label h1 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32 + 1);
+            if (h1 > h0) {   // block-uniform
+                const unsigned int mine = __shfl_sync(0xffffffffu, word, w);
+                label before = 0;
+#pragma unroll
+                for (int j = 0; j < kRowsPerBlock / 32; ++j) {
+                    const unsigned int mj = __shfl_sync(0xffffffffu, word, j);
+                    if (j < w) before += __popc(mj);
+                }
+                if ((mine >> lane) & 1u) {
+                    before += __popc(mine & ((1u << lane) - 1u));
+                    hq = __ldg(&a.nl_row_ptrs[h0 + before]);
+                    hqe = __ldg(&a.nl_row_ptrs[h0 + before + 1]);
+#pragma unroll
+                    for (int j = 0; j < kHaloEarly; ++j) {
+                        if (hq + j < hqe) {
+                            double h;
+                            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq + j])) : "memory");
+                            hp[j] = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq + j])), h);
+                        }
+                    }
+                }
+            }
         }
         // ---- gather x for the batch already in registers, park the products
         {
@@ -345,6 +396,17 @@ k_spmv_pipe(const SpmvK a)
             const label row = r0 + tid;
             double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
+            if (HALO && hqe > hq) {
+                // y += A_nl * recv for this row, entry by entry after the local sum
+#pragma unroll
+                for (int j = 0; j < kHaloEarly; ++j)
+                    if (hq + j < hqe) sum = __dadd_rn(sum, hp[j]);
+                for (label q = hq + kHaloEarly; q < hqe; ++q) {
+                    double h;
+                    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
+                    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
+                }
+            }
             a.y[row] = sum;
             if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
             if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
@@ -352,6 +414,23 @@ k_spmv_pipe(const SpmvK a)
         __syncthreads();   // prod is overwritten by the next row block
         s = s2;
         e = e2;
+    }
+    if (HALO) {
+        // the last CTA closes the exchange: acknowledge to the neighbours, advance seq
+        __shared__ bool last_cta;
+        if (tid == 0) {
+            __threadfence();
+            last_cta = (atomicAdd(&cm->nl_ticket, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last_cta) {
+            if (tid < cm->n_targets) st_flag(cm->peer_ack_flag[tid], seq);
+            if (tid == 0) {
+                cm->halo_seq = seq;
+                cm->nl_ticket = 0u;
+            }
+        }
+        __syncthreads();
     }
     if (NRED > 0)
         grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
@@ -872,7 +951,7 @@ static int pick_variant(const Context *ctx)
     const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
     const double mean_len = ctx->n > 0 ? (double)ctx->nnz / ctx->n : 0.0;
     // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
-    if (smem <= (size_t)kStreamSmemMax && mean_len <= 48.0) return 1;
+    if (smem <= (size_t)kStreamSmemMax && mean_len <= 48.0) return 6;   // pipelined stream
     return mean_len >= 16.0 ? 3 : 2;
 }
 
@@ -970,19 +1049,45 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
         static bool attr6 = false;
         if (!attr6) {
-            cudaFuncSetAttribute(k_spmv_pipe<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_pipe<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_pipe<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_pipe<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_pipe<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
-            cudaFuncSetAttribute(k_spmv_pipe<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
+#define SET_ATTR6(A, R)                                                                          \
+    cudaFuncSetAttribute(k_spmv_pipe<A, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                         kStreamSmemMax);                                                        \
+    cudaFuncSetAttribute(k_spmv_pipe<A, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                         kStreamSmemMax);
+            SET_ATTR6(false, 0) SET_ATTR6(false, 1) SET_ATTR6(false, 2)
+            SET_ATTR6(true, 0) SET_ATTR6(true, 1) SET_ATTR6(true, 2)
+#undef SET_ATTR6
             attr6 = true;
         }
         const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
         k.n_row_blocks = nblk;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
         const int grid = nblk < cap ? nblk : (int)cap;
-        DISPATCH(k_spmv_pipe, grid, kStreamThreads, smem);
+#define PIPE_LAUNCH(H)                                                                          \
+    do {                                                                                        \
+        if (sa.advanced) {                                                                      \
+            if (nred == 0) k_spmv_pipe<true, 0, H><<<grid, kStreamThreads, smem, st>>>(k);      \
+            else if (nred == 1) k_spmv_pipe<true, 1, H><<<grid, kStreamThreads, smem, st>>>(k); \
+            else k_spmv_pipe<true, 2, H><<<grid, kStreamThreads, smem, st>>>(k);                \
+        } else {                                                                                \
+            if (nred == 0) k_spmv_pipe<false, 0, H><<<grid, kStreamThreads, smem, st>>>(k);     \
+            else if (nred == 1) k_spmv_pipe<false, 1, H><<<grid, kStreamThreads, smem, st>>>(k);\
+            else k_spmv_pipe<false, 2, H><<<grid, kStreamThreads, smem, st>>>(k);               \
+        }                                                                                       \
+    } while (0)
+        if (sa.fused_halo) {
+            k.tile_nl_ptr = ctx->d_tile_nl_ptr;
+            k.nl_rowmask = ctx->d_nl_rowmask;
+            k.nl_row_ids = ctx->d_nl_row_ids;
+            k.nl_row_ptrs = ctx->d_nl_row_ptrs;
+            k.nl_cols = ctx->d_nl_cols;
+            k.nl_vals = ctx->d_nl_vals;
+            k.ea = make_epi_args(ctx, nred);
+            PIPE_LAUNCH(true);
+        } else {
+            PIPE_LAUNCH(false);
+        }
+#undef PIPE_LAUNCH
     } else if (variant == 5) {
         const int warp_cap = (int)((ctx->max_warp_nnz + 1) & ~(int64_t)1);
         const size_t smem = (size_t)warp_cap * sizeof(double) * (kWarpCtaThreads / 32);
