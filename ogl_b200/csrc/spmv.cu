@@ -36,7 +36,7 @@ constexpr int kBatch = 8;            // entries per thread requested at once (7-
 constexpr int kBatchStream = 7;      // stream kernel: 48-register budget (5 CTAs per SM)
 constexpr int kStreamCtasPerSM = 5;  // <= 51 registers per thread
 constexpr int kMaxTilesPerCta = 1024; // row-block extents cached in shared memory
-constexpr int kHaloEarly = 3;         // halo products of a row prefetched with the tile's loads
+constexpr int kHaloEarly = 1;         // halo products of a row prefetched with the tile's loads
 
 struct SpmvK {
     const label *row_ptrs;
@@ -325,9 +325,13 @@ k_spmv_pipe(const SpmvK a)
         }
         // HALO: first kHaloEarly products of my row's non-local entries, fetched now
         // (mask word / row-group range: one load per lane + shuffles, see k_spmv_stream)
-        label hq = 0, hqe = 0;
-        double hp[kHaloEarly];
+        // (parked in thread-private shared-memory slots: the register budget of
+        // this kernel has no room for values that live across the tile barrier)
+        __shared__ double h_prod[HALO ? kRowsPerBlock : 1];
+        __shared__ label h_beg[HALO ? kRowsPerBlock : 1], h_end[HALO ? kRowsPerBlock : 1];
         if (HALO) {
+            label hq = 0, hqe = 0;
+            double hp0 = 0.0;
             const int w = tid >> 5, lane = tid & 31;
             unsigned int word = 0;
             if (lane < kRowsPerBlock / 32)
@@ -348,16 +352,16 @@ k_spmv_pipe(const SpmvK a)
                     before += __popc(mine & ((1u << lane) - 1u));
                     hq = __ldg(&a.nl_row_ptrs[h0 + before]);
                     hqe = __ldg(&a.nl_row_ptrs[h0 + before + 1]);
-#pragma unroll
-                    for (int j = 0; j < kHaloEarly; ++j) {
-                        if (hq + j < hqe) {
-                            double h;
-                            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq + j])) : "memory");
-                            hp[j] = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq + j])), h);
-                        }
+                    if (hq < hqe) {
+                        double h;
+                        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq])) : "memory");
+                        hp0 = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq])), h);
                     }
                 }
             }
+            h_beg[tid] = hq;
+            h_end[tid] = hqe;
+            h_prod[tid] = hp0;
         }
         // ---- gather x for the batch already in registers, park the products
         {
@@ -396,12 +400,11 @@ k_spmv_pipe(const SpmvK a)
             const label row = r0 + tid;
             double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
-            if (HALO && hqe > hq) {
+            if (HALO && h_end[tid] > h_beg[tid]) {
                 // y += A_nl * recv for this row, entry by entry after the local sum
-#pragma unroll
-                for (int j = 0; j < kHaloEarly; ++j)
-                    if (hq + j < hqe) sum = __dadd_rn(sum, hp[j]);
-                for (label q = hq + kHaloEarly; q < hqe; ++q) {
+                sum = __dadd_rn(sum, h_prod[tid]);
+                const label hqe = h_end[tid];
+                for (label q = h_beg[tid] + 1; q < hqe; ++q) {
                     double h;
                     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
                     sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
