@@ -308,7 +308,8 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "comm_mode in {0,1,2}");
         ctx->comm_mode = value;   // takes effect at the next ogl_partition_create / solve
     } else if (k == "fused_halo") {
-        ctx->fused_halo = value != 0;
+        if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "fused_halo in {0,1,2}");
+        ctx->fused_halo = value;
     } else if (k == "tile_blocked") {
         ctx->tile_blocked = value != 0;
     } else if (k == "tma_stages") {

@@ -122,7 +122,7 @@ struct Context {
 
     // peer-memory window (multi-GPU P2P path, comm.cu)
     int64_t comm_mode = 0;        // 0 auto, 1 NCCL send/recv + allreduce, 2 peer-memory (P2P)
-    int64_t fused_halo = 1;       // P2P: apply the non-local block inside the stream SpMV
+    int64_t fused_halo = 2;       // P2P: non-local block inside the stream SpMV (0 off, 1 on, 2 auto)
     bool p2p_ready = false;
     void *d_window = nullptr;     // my window (exported through CUDA IPC)
     size_t window_bytes = 0;
