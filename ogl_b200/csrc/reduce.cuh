@@ -111,7 +111,7 @@ struct EpiArgs {
 
 EpiArgs make_epi_args(Context *ctx, int ar_count = 0, bool ar_after_epi = false);
 
-static __device__ __forceinline__ void run_epilogue_on(int epi, SolveState *s, const EpiArgs &a)
+__device__ __forceinline__ void run_epilogue(int epi, SolveState *s, const EpiArgs &a)
 {
     switch (epi) {
     case EPI_MEAN_LOCAL:
@@ -176,18 +176,6 @@ static __device__ __forceinline__ void run_epilogue_on(int epi, SolveState *s, c
     default:
         break;
     }
-}
-
-// The epilogue runs in ONE thread while the rest of the GPU idles, so its
-// latency is pure overhead per kernel.  Work on a register/local copy of the
-// state: one burst of independent loads and one burst of stores instead of a
-// chain of ~20 dependent L2 round trips.
-// (not inlined: keeps its ~60 registers out of the streaming kernels' budget)
-static __device__ __noinline__ void run_epilogue(int epi, SolveState *s, const EpiArgs &a)
-{
-    SolveState local = *s;
-    run_epilogue_on(epi, &local, a);
-    *s = local;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
