@@ -20,7 +20,8 @@ CASES = {
     "momentum_bicgstab": (lambda p: cases.momentum_3d(14, p), "GKOBiCGStab", "BJ", 1, 1e-10),
     "channel_gmres": (lambda p: cases.channel((16, 8, 8), p), "GKOGMRES", "BJ", 1, 1e-8),
     # all-Neumann + one reference cell: nearly singular, so solve tighter than the L2 bar
-    "cavity_cg_none": (lambda p: cases.cavity_2d(p), "GKOCG", "none", 1, 1e-11),
+    # 2-D case: fold the z split into x ([2,2,2] -> [4,2,1] like test/integration.yaml:53-55)
+    "cavity_cg_none": (lambda p: cases.cavity_2d((p[0] * p[2], p[1], 1)), "GKOCG", "none", 1, 1e-11),
 }
 
 
@@ -55,4 +56,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        import traceback
+        with open(f"{sys.argv[1]}.err.{os.environ.get('RANK', '0')}", "w") as f:
+            traceback.print_exc(file=f)
+        traceback.print_exc()
+        raise

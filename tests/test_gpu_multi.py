@@ -40,7 +40,10 @@ def test_decomposed_solves_match_oracle(oracle, tmp_path, procs):
            str(world), "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "tests", "_multi_gpu_worker.py"), out, ",".join(map(str, procs))]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    if p.returncode != 0:
+        import glob
+        errs = "".join(open(f).read()[-1500:] for f in sorted(glob.glob(out + ".err.*"))[:2])
+        raise AssertionError(errs + p.stderr[-1500:])
     res = [json.load(open(f"{out}.{r}")) for r in range(world)]
     assert res[0]["pressure_cg@0"]["p2p"] == 1, "peer-memory path not active on an NVLink box"
     assert res[0]["pressure_cg@1"]["p2p"] == 0 and res[0]["pressure_cg@2"]["p2p"] == 1
