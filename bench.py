@@ -66,6 +66,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(cells: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json), or None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return rec.get(str(cells), {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -276,14 +286,23 @@ def run_gpu(args):
     ms_e2e, iters_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup - 2))
     clocks = sampler.stop() if ps.rank == 0 else {}
 
-    # ---- dominant kernel: SpMV fused with <p,q>, CUDA events over back-to-back launches
+    # ---- dominant kernel: SpMV fused with <p,q>.  Measured live in the REAL CG loop:
+    # one more (untimed) solve with the chunk graph off and CUDA events recorded on the
+    # launching stream around every 4th SpMV launch; plus the back-to-back figures
+    ctx.set_option("use_graph", 0)
+    ctx.set_option("profile_stride", 4)
+    flush.zero_()
+    r_prof = step_resident()
+    ctx.set_option("profile_stride", 0)
+    ctx.set_option("use_graph", 1)
     reps = 200
-    spmv_ms = ctx.spmv_bench(reps, fused_dot=True) / reps
+    spmv_b2b_ms = ctx.spmv_bench(reps, fused_dot=True) / reps
     spmv_plain_ms = ctx.spmv_bench(reps, fused_dot=False) / reps
-    t = torch.tensor([spmv_ms, spmv_plain_ms], dtype=torch.float64, device=dev)
+    spmv_ms = r_prof.spmv_us_avg * 1e-3 if r_prof.spmv_samples > 0 else spmv_b2b_ms
+    t = torch.tensor([spmv_ms, spmv_plain_ms, spmv_b2b_ms], dtype=torch.float64, device=dev)
     if n_gpus > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    spmv_ms, spmv_plain_ms = (float(v) for v in t.tolist())
+    spmv_ms, spmv_plain_ms, spmv_b2b_ms = (float(v) for v in t.tolist())
 
     if ps.rank != 0:
         ctx.close()
@@ -335,10 +354,14 @@ def run_gpu(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "kernel": "k_spmv_stream<false,1> (CSR SpMV + fused <p,q>)",
+            "bound": "hbm", "kernel": "k_spmv_pipe<false,1,%s> (FP64 CSR SpMV + fused <p,q>)" % (
+                "true" if n_gpus > 1 else "false"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": ncu_traffic(args.n) if n_gpus == 1 else None, "peak_source": peak_src,
             "alg_bytes_per_launch": b_spmv, "us_per_launch": spmv_ms * 1e3,
+            "us_per_launch_how": ("CUDA events around every 4th SpMV launch inside an extra "
+                                  "solve of the same system (%d samples)" % r_prof.spmv_samples),
+            "us_per_launch_back_to_back": spmv_b2b_ms * 1e3,
             "us_per_launch_unfused": spmv_plain_ms * 1e3,
             "frac_of_nominal_8TBs": achieved / 8000.0,
             "pcg_iteration": {"alg_bytes": b_pcg, "achieved": pcg_gbs, "frac": pcg_gbs / peak,

@@ -120,6 +120,8 @@ static void destroy(Context *c)
         if (w) cudaFree(w);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (cudaEvent_t e : c->profile_events)
+        if (e) cudaEventDestroy(e);
     cudaEvent_t evs[] = {c->ev_pack, c->ev_recv, c->ev_t0, c->ev_t1, c->ev_poll[0], c->ev_poll[1]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);

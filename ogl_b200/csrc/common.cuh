@@ -185,6 +185,12 @@ struct Context {
     int64_t graph_kernels = 0;   // kernels inside one replayed chunk
 
     int64_t launches = 0;
+
+    // sampled SpMV timing inside the solve loop (profile_stride > 0)
+    std::vector<cudaEvent_t> profile_events;
+    int profile_used = 0;
+    int64_t profile_iter = 0;
+    bool capturing = false;
 };
 
 // memory helpers ---------------------------------------------------------------

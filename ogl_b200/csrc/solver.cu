@@ -445,7 +445,14 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
         s.guard_done = true;
         s.epi = EPI_CG_BETA;
         s.halo_stored = pack;
+        // profile_stride > 0 (graphs off): bracket every stride-th SpMV of the real
+        // loop with CUDA events on the launching stream
+        const bool sample = ctx->profile_stride > 0 && !ctx->capturing &&
+                            (ctx->profile_iter++ % ctx->profile_stride) == 0 &&
+                            ctx->profile_used + 2 <= (int)ctx->profile_events.size();
+        if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);
         OGL_TRY(dist_spmv(ctx, s));
+        if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);
     }
     {
         VecK a = base_args(ctx, pk == 2 ? EPI_NONE : EPI_CG_RHO_CHECK, true, pk == 2 ? 0 : 2);
@@ -587,7 +594,9 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
         const int64_t launches_before = ctx->launches;
         OGL_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         int rc = OGL_OK;
+        ctx->capturing = true;
         for (int i = 0; i < chunk && rc == OGL_OK; ++i) rc = enqueue();
+        ctx->capturing = false;
         cudaError_t e = cudaStreamEndCapture(st, &graph);
         const int64_t kernels_per_chunk = ctx->launches - launches_before;
         ctx->launches = launches_before;   // captured, not executed
@@ -646,6 +655,12 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     const int64_t launches0 = ctx->launches;
     cudaStream_t st = ctx->stream;
     OGL_TRY(init_state(ctx, p));
+    ctx->profile_iter = 0;
+    ctx->profile_used = 0;
+    if (ctx->profile_stride > 0 && ctx->profile_events.empty()) {
+        ctx->profile_events.resize(512);
+        for (auto &ev : ctx->profile_events) OGL_CUDA(ctx, cudaEventCreate(&ev));
+    }
     OGL_CUDA(ctx, cudaEventRecord(ctx->ev_t0, st));
     double *r, *z, *pv, *q, *w, *tmp;
     OGL_TRY(get_work(ctx, 0, &r));
@@ -703,6 +718,21 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     // the L1 norm rides inside the fused update kernel: no separate evaluation
     res->resnorm_us = 0.0;
     res->kernel_launches = ctx->launches - launches0;
+    if (ctx->profile_used >= 2) {
+        double total_ms = 0.0;
+        int pairs = 0;
+        for (int i = 0; i + 1 < ctx->profile_used; i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ctx->profile_events[i], ctx->profile_events[i + 1]) == cudaSuccess) {
+                total_ms += t;
+                ++pairs;
+            }
+        }
+        if (pairs > 0) {
+            res->spmv_us_avg = total_ms * 1e3 / pairs;
+            res->spmv_samples = pairs;
+        }
+    }
     if (hs.comm_error)
         return fail(ctx, OGL_ERR_NCCL, "peer synchronisation timed out (a rank left the solve?)");
     if (!hs.done)
