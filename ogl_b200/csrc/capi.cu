@@ -2,6 +2,7 @@
 // host-side helpers shared by the kernels' launchers.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iomanip>
@@ -241,6 +242,7 @@ int ogl_ctx_create(int device_id, int rank, int n_ranks, const void *nccl_id, vo
     c->device = dev;
     c->rank = rank;
     c->n_ranks = n_ranks;
+    if (const char *e = std::getenv("OGL_B200_PDL")) c->use_pdl = std::atoi(e) != 0;   // A/B switch
     auto bail = [&](int code, const std::string &msg) {
         ogl::set_error(nullptr, msg);
         ogl::destroy(c);
@@ -304,6 +306,8 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->chunk_iters = value;
     } else if (k == "use_graph") {
         ctx->use_graph = value != 0;
+    } else if (k == "use_pdl") {
+        ctx->use_pdl = value != 0;
     } else if (k == "profile_stride") {
         ctx->profile_stride = value < 0 ? 0 : value;
     } else if (k == "comm_mode") {
@@ -342,6 +346,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     if (k == "spmv_variant") *value = ctx->spmv_variant;
     else if (k == "chunk_iters") *value = ctx->chunk_iters;
     else if (k == "use_graph") *value = ctx->use_graph;
+    else if (k == "use_pdl") *value = ctx->use_pdl;
     else if (k == "profile_stride") *value = ctx->profile_stride;
     else if (k == "blas1_blocks") *value = ctx->blas1_blocks;
     else if (k == "stream_ctas") *value = ctx->stream_ctas;

@@ -101,6 +101,7 @@ struct Context {
     int64_t blas1_blocks = kNumSM * kBlas1BlocksPerSM;
     int64_t stream_ctas = 0;     // persistent SpMV grid (0 = 8 CTAs per SM)
     int64_t tma_stages = 3;      // shared-memory ring depth of the TMA SpMV
+    int64_t use_pdl = 1;         // programmatic dependent launch between the CG kernels
     int64_t tile_blocked = 0;    // persistent SpMV: 1 = contiguous tile range per CTA (measured slower)
 
     // local pattern (a4/a5) -- resident across solves
@@ -192,6 +193,27 @@ struct Context {
     int64_t profile_iter = 0;
     bool capturing = false;
 };
+
+// Launch with (optional) programmatic stream serialisation: the next kernel's
+// CTAs may become resident while this one drains (its serial reduction tail);
+// kernels call cudaGridDependencySynchronize() before touching anything the
+// previous kernel wrote.  Captured into the chunk graph as programmatic edges.
+template <typename K, typename A>
+inline cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+                              const A &arg)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
 
 // memory helpers ---------------------------------------------------------------
 template <typename T>

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_init_norms(const VecK
 // 128-bit loads/stores (two rows per thread and trip).
 __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
 {
+    cudaGridDependencySynchronize();            // PDL: everything below reads the previous kernel's output
+    cudaTriggerProgrammaticLaunchCompletion();  // the SpMV may start getting resident
     if (a.guard_done && a.state->done) return;
     const bool p_is_z = a.state->flag_p_is_z != 0;
     const double t = a.state->coef_p;
@@ -177,6 +179,8 @@ __device__ __forceinline__ void cg_xr_elem(bool upd, double t, double &x, double
 template <int PK>
 __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
 {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (a.guard_done && a.state->done) return;
     const bool upd = a.state->beta != 0.0;
     const double t = a.state->coef_x;
@@ -434,7 +438,8 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
         a.send_idx = ctx->d_send_idxs;
         a.n_send = ctx->n_send;
         a.pack = pack ? 1 : 0;
-        LAUNCH(k_cg_p, a);
+        OGL_CUDA(ctx, launch_pdl(k_cg_p, vec_grid(ctx), kT, 0, ctx->stream, ctx->use_pdl != 0, a));
+        ctx->launches++;
     }
     {
         SpmvArgs s;
@@ -462,10 +467,15 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
         a.out0 = ctx->d_x;
         a.out1 = r;
         a.out2 = z;
-        if (pk == 0) LAUNCH(k_cg_xr<0>, a);
-        else if (pk == 1) LAUNCH(k_cg_xr<1>, a);
+#define LAUNCH_XR(PKV)                                                                             \
+    do {                                                                                           \
+        OGL_CUDA(ctx, launch_pdl(k_cg_xr<PKV>, vec_grid(ctx), kT, 0, ctx->stream, ctx->use_pdl != 0, a)); \
+        ctx->launches++;                                                                           \
+    } while (0)
+        if (pk == 0) LAUNCH_XR(0);
+        else if (pk == 1) LAUNCH_XR(1);
         else {
-            LAUNCH(k_cg_xr<2>, a);
+            LAUNCH_XR(2);
             OGL_TRY(precond_apply(ctx, r, z, r, 0, true, EPI_CG_RHO_CHECK,
                                   ctx->n_ranks == 1 || use_p2p(ctx), 2));
         }
@@ -583,7 +593,7 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
     cudaStream_t st = ctx->stream;
     const bool graph_ok = ctx->use_graph && (ctx->n_ranks == 1 || use_p2p(ctx)) &&
                           ctx->profile_stride == 0;
-    const int64_t sig = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^
+    const int64_t sig = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^ (ctx->use_pdl << 60) ^
                         ((int64_t)chunk << 32) ^ (int64_t)ctx->n ^ (ctx->spmv_variant << 56);
     if (graph_ok && (!ctx->graph_exec || ctx->graph_sig != sig)) {
         if (ctx->graph_exec) {

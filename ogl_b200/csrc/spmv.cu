@@ -266,18 +266,11 @@ template <bool ADV, int NRED, bool HALO>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSM)
 k_spmv_pipe(const SpmvK a)
 {
-    if (a.guard_done && a.state->done) return;
     extern __shared__ double prod[];
     const int tid = threadIdx.x;
-    // HALO (multi-GPU, peer-memory path): see k_spmv_stream
     CommDev *cm = HALO ? a.ea.comm : nullptr;
     unsigned long long seq = 0;
     const double *recv = nullptr;
-    if (HALO) {
-        seq = cm->halo_seq + 1;
-        if (blockIdx.x == 0 && tid < cm->n_targets) st_flag(cm->peer_data_flag[tid], seq);
-        recv = cm->my_recv + (size_t)(seq & 1ull) * cm->my_recv_stride;
-    }
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
@@ -300,6 +293,17 @@ k_spmv_pipe(const SpmvK a)
     for (int u = 0; u < kBatchStream; ++u) {
         const label q = tid + u * kStreamThreads;
         v[u] = q < e - s ? __ldcs(&a.vals[s + q]) : 0.0;
+    }
+    // PDL: the matrix stream above does not depend on the previous kernel (the
+    // p-update); everything from here on does.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (a.guard_done && a.state->done) return;
+    if (HALO) {
+        // HALO (multi-GPU, peer-memory path): see k_spmv_stream
+        seq = cm->halo_seq + 1;
+        if (blockIdx.x == 0 && tid < cm->n_targets) st_flag(cm->peer_data_flag[tid], seq);
+        recv = cm->my_recv + (size_t)(seq & 1ull) * cm->my_recv_stride;
     }
     if (HALO) {
         // the first tile's loads are in flight; now make sure the neighbours'
@@ -1066,17 +1070,21 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         k.n_row_blocks = nblk;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
         const int grid = nblk < cap ? nblk : (int)cap;
-#define PIPE_LAUNCH(H)                                                                          \
-    do {                                                                                        \
-        if (sa.advanced) {                                                                      \
-            if (nred == 0) k_spmv_pipe<true, 0, H><<<grid, kStreamThreads, smem, st>>>(k);      \
-            else if (nred == 1) k_spmv_pipe<true, 1, H><<<grid, kStreamThreads, smem, st>>>(k); \
-            else k_spmv_pipe<true, 2, H><<<grid, kStreamThreads, smem, st>>>(k);                \
-        } else {                                                                                \
-            if (nred == 0) k_spmv_pipe<false, 0, H><<<grid, kStreamThreads, smem, st>>>(k);     \
-            else if (nred == 1) k_spmv_pipe<false, 1, H><<<grid, kStreamThreads, smem, st>>>(k);\
-            else k_spmv_pipe<false, 2, H><<<grid, kStreamThreads, smem, st>>>(k);               \
-        }                                                                                       \
+#define PIPE_ONE(A, R, H) \
+    launch_pdl(k_spmv_pipe<A, R, H>, grid, kStreamThreads, smem, st, ctx->use_pdl != 0 && sa.guard_done, k)
+#define PIPE_LAUNCH(H)                                                      \
+    do {                                                                    \
+        cudaError_t le;                                                     \
+        if (sa.advanced) {                                                  \
+            if (nred == 0) le = PIPE_ONE(true, 0, H);                       \
+            else if (nred == 1) le = PIPE_ONE(true, 1, H);                  \
+            else le = PIPE_ONE(true, 2, H);                                 \
+        } else {                                                            \
+            if (nred == 0) le = PIPE_ONE(false, 0, H);                      \
+            else if (nred == 1) le = PIPE_ONE(false, 1, H);                 \
+            else le = PIPE_ONE(false, 2, H);                                \
+        }                                                                   \
+        OGL_CUDA(ctx, le);                                                  \
     } while (0)
         if (sa.fused_halo) {
             k.tile_nl_ptr = ctx->d_tile_nl_ptr;
@@ -1091,6 +1099,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
             PIPE_LAUNCH(false);
         }
 #undef PIPE_LAUNCH
+#undef PIPE_ONE
     } else if (variant == 5) {
         const int warp_cap = (int)((ctx->max_warp_nnz + 1) & ~(int64_t)1);
         const size_t smem = (size_t)warp_cap * sizeof(double) * (kWarpCtaThreads / 32);
