@@ -101,7 +101,7 @@ struct Context {
     int64_t blas1_blocks = kNumSM * kBlas1BlocksPerSM;
     int64_t stream_ctas = 0;     // persistent SpMV grid (0 = 8 CTAs per SM)
     int64_t tma_stages = 3;      // shared-memory ring depth of the TMA SpMV
-    int64_t use_pdl = 1;         // programmatic dependent launch between the CG kernels
+    int64_t use_pdl = 0;         // programmatic dependent launch between the CG kernels (measured: no gain inside graphs)
     int64_t tile_blocked = 0;    // persistent SpMV: 1 = contiguous tile range per CTA (measured slower)
 
     // local pattern (a4/a5) -- resident across solves
