@@ -160,28 +160,6 @@ __global__ void k_compact_heads(label n, const label *__restrict__ rows,
     if (i == 0) row_ptrs[n_unique] = n;
 }
 
-// first row group whose row is >= tile * rows_per_tile (row_ids ascending)
-__global__ void k_tile_nl_ptr(label n_tiles, label rows_per_tile, label n_groups,
-                              const label *__restrict__ row_ids, label *tile_ptr)
-{
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    const int64_t want = t * rows_per_tile;
-    label lo = 0, hi = n_groups;
-    while (lo < hi) {
-        const label mid = (lo + hi) >> 1;
-        if (row_ids[mid] < want) lo = mid + 1;
-        else hi = mid;
-    }
-    tile_ptr[t] = lo;
-}
-
-__global__ void k_nl_rowmask(label n_groups, const label *__restrict__ row_ids, unsigned int *mask)
-{
-    const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (u < n_groups) atomicOr(&mask[row_ids[u] >> 5], 1u << (row_ids[u] & 31));
-}
-
 // coefficient gather (HostMatrix.C:685-703 row_gather + CsrMatrixWrapper.H:123-135
 // value copy, fused): vals[k] = scaling * staging[map[k]], the local interface
 // segment negated (HostMatrix.C:204).
@@ -194,6 +172,82 @@ __global__ void k_gather_values(int64_t nnz, const label *__restrict__ map,
         const label m = __ldcs(&map[k]);
         double v = __ldg(&staging[m]);
         if (m >= iface_base) v = v * -1.0;
+        __stcs(&vals[k], scaling == 1.0 ? v : scaling * v);
+    }
+}
+
+// ghosted CSR: structure
+__global__ void k_ghost_counts(label n_groups, const label *__restrict__ row_ids,
+                               const label *__restrict__ nl_row_ptrs, label *__restrict__ cnt)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < n_groups) cnt[row_ids[g]] = nl_row_ptrs[g + 1] - nl_row_ptrs[g];
+}
+
+__global__ void k_ghost_row_ptrs(label n, const label *__restrict__ row_ptrs,
+                                 const label *__restrict__ before, label *__restrict__ g_row_ptrs)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r <= n) g_row_ptrs[r] = row_ptrs[r] + before[r];
+}
+
+__global__ void k_ghost_local(int64_t nnz, const label *__restrict__ rows,
+                              const label *__restrict__ cols, const label *__restrict__ map,
+                              const label *__restrict__ before, label *__restrict__ g_cols,
+                              label *__restrict__ g_map)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += stride) {
+        const int64_t dst = k + before[rows[k]];
+        g_cols[dst] = cols[k];
+        g_map[dst] = map[k];
+    }
+}
+
+__global__ void k_ghost_halo(label n, label n_groups, const label *__restrict__ row_ids,
+                             const label *__restrict__ nl_row_ptrs,
+                             const label *__restrict__ nl_cols, const label *__restrict__ nl_map,
+                             const label *__restrict__ g_row_ptrs, label *__restrict__ g_cols,
+                             label *__restrict__ g_map)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const label row = row_ids[g];
+    const label q0 = nl_row_ptrs[g], q1 = nl_row_ptrs[g + 1];
+    label dst = g_row_ptrs[row + 1] - (q1 - q0);   // behind the row's local entries
+    for (label q = q0; q < q1; ++q, ++dst) {
+        g_cols[dst] = n + nl_cols[q];   // ghost column: index into the receive window
+        g_map[dst] = ~nl_map[q];        // negative: index into the non-local staging
+    }
+}
+
+__global__ void k_block_span_max(label n, const label *__restrict__ row_ptrs, int rows_per_block,
+                                 int *out)
+{
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t r0 = b * rows_per_block;
+    if (r0 < n) {
+        const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+        atomicMax(out, row_ptrs[r1] - row_ptrs[r0]);
+    }
+}
+
+// ghosted CSR: coefficients, same arithmetic as k_gather_values / k_gather_nonlocal
+__global__ void k_gather_ghosted(int64_t nnz, const label *__restrict__ map,
+                                 const double *__restrict__ staging, label iface_base,
+                                 const double *__restrict__ nl_staging, double scaling,
+                                 double *__restrict__ vals)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += stride) {
+        const label m = __ldcs(&map[k]);
+        double v;
+        if (m >= 0) {
+            v = __ldg(&staging[m]);
+            if (m >= iface_base) v = v * -1.0;
+        } else {
+            v = __ldg(&nl_staging[~m]) * -1.0;
+        }
         __stcs(&vals[k], scaling == 1.0 ? v : scaling * v);
     }
 }
@@ -319,6 +373,7 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->have_b = ctx->have_x = false;
     // a new local pattern invalidates the halo description built on the old one
     ctx->have_nonlocal = false;
+    ctx->have_ghosted = false;
     ctx->have_partition = false;
     ctx->n_halo = 0;
     ctx->n_nl_rows = 0;
@@ -348,6 +403,63 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     return spmv_setup(ctx);
 }
 
+// Ghosted CSR for the halo-fused SpMV: row r = its local entries (column order)
+// followed by its non-local entries (interface order), the latter with column
+// n + receive-window index.  One left-to-right row sum over it performs exactly
+// `y = A_local x` followed by `y += A_nonlocal recv` of the reference's
+// distributed apply, without any per-tile halo bookkeeping in the kernel.
+static int build_ghosted(Context *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    const label n = ctx->n;
+    const int64_t nnz_g = ctx->nnz + ctx->n_halo;
+    if (nnz_g >= (int64_t)1 << 31) return fail(ctx, OGL_ERR_UNSUPPORTED, "ghosted nnz exceeds label range");
+    label *d_cnt = nullptr, *d_before = nullptr;
+    int *d_max = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(d_cnt), cudaFree(d_before), cudaFree(d_max), cudaFree(d_tmp); };
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_cnt, (size_t)n + 1)) || (rc = dev_alloc(ctx, &d_before, (size_t)n + 1)) ||
+        (rc = dev_alloc(ctx, &d_max, 1)) || (rc = dev_alloc(ctx, &ctx->d_g_row_ptrs, (size_t)n + 1)) ||
+        (rc = dev_alloc(ctx, &ctx->d_g_cols, (size_t)nnz_g)) ||
+        (rc = dev_alloc(ctx, &ctx->d_g_map, (size_t)nnz_g)) ||
+        (rc = dev_alloc(ctx, &ctx->d_g_vals, (size_t)nnz_g))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemsetAsync(d_cnt, 0, sizeof(label) * ((size_t)n + 1), st);
+    cudaMemsetAsync(d_max, 0, sizeof(int), st);
+    k_ghost_counts<<<grid_for(ctx->n_nl_rows), kThreads, 0, st>>>(ctx->n_nl_rows, ctx->d_nl_row_ids,
+                                                                 ctx->d_nl_row_ptrs, d_cnt);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt, d_before, n + 1, st);
+    if (cudaMalloc(&d_tmp, scan_bytes + 16) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, OGL_ERR_CUDA, "cudaMalloc(scan temp)");
+    }
+    cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, d_cnt, d_before, n + 1, st);
+    k_ghost_row_ptrs<<<grid_for((int64_t)n + 1), kThreads, 0, st>>>(n, ctx->d_row_ptrs, d_before,
+                                                                   ctx->d_g_row_ptrs);
+    int g = grid_for(ctx->nnz);
+    if (g > kNumSM * 16) g = kNumSM * 16;
+    k_ghost_local<<<g, kThreads, 0, st>>>(ctx->nnz, ctx->d_rows, ctx->d_cols, ctx->d_map, d_before,
+                                          ctx->d_g_cols, ctx->d_g_map);
+    k_ghost_halo<<<grid_for(ctx->n_nl_rows), kThreads, 0, st>>>(
+        n, ctx->n_nl_rows, ctx->d_nl_row_ids, ctx->d_nl_row_ptrs, ctx->d_nl_cols, ctx->d_nl_map,
+        ctx->d_g_row_ptrs, ctx->d_g_cols, ctx->d_g_map);
+    const int64_t nblk = ((int64_t)n + 255) / 256;
+    k_block_span_max<<<(int)((nblk + 255) / 256), 256, 0, st>>>(n, ctx->d_g_row_ptrs, 256, d_max);
+    int mx = 0;
+    cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess)
+        return fail(ctx, OGL_ERR_CUDA, std::string("build_ghosted: ") + cudaGetErrorString(e));
+    ctx->max_block_nnz_g = mx;
+    ctx->have_ghosted = true;
+    return OGL_OK;
+}
+
 int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
 {
     if (!ctx->have_pattern)
@@ -357,6 +469,7 @@ int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
     cudaStream_t st = ctx->stream;
     ctx->n_halo = n_halo;
     ctx->n_nl_rows = 0;
+    ctx->have_ghosted = false;
     OGL_TRY(dev_alloc(ctx, &ctx->d_nl_rows, n_halo));
     OGL_TRY(dev_alloc(ctx, &ctx->d_nl_cols, n_halo));
     OGL_TRY(dev_alloc(ctx, &ctx->d_nl_map, n_halo));
@@ -365,15 +478,6 @@ int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
     OGL_TRY(dev_alloc(ctx, &ctx->d_nl_row_ids, n_halo));
     OGL_TRY(dev_alloc(ctx, &ctx->d_nl_row_ptrs, (size_t)n_halo + 1));
     ctx->have_nonlocal = true;
-    {
-        // per-tile ranges of the halo rows for the halo-fused stream SpMV (256-row tiles)
-        const label n_tiles = (ctx->n + 255) / 256;
-        OGL_TRY(dev_alloc(ctx, &ctx->d_tile_nl_ptr, (size_t)n_tiles + 1));
-        OGL_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_nl_ptr, 0, sizeof(label) * ((size_t)n_tiles + 1), st));
-        const size_t words = (size_t)n_tiles * 8 + 8;
-        OGL_TRY(dev_alloc(ctx, &ctx->d_nl_rowmask, words));
-        OGL_CUDA(ctx, cudaMemsetAsync(ctx->d_nl_rowmask, 0, sizeof(unsigned int) * words, st));
-    }
     if (n_halo == 0) return OGL_OK;
 
     label *d_keys = nullptr, *d_iota = nullptr, *d_head = nullptr, *d_scan = nullptr;
@@ -431,18 +535,11 @@ int nonlocal_pattern(Context *ctx, label n_halo, const label *face_cells)
     k_compact_heads<<<grid_for(n_halo), kThreads, 0, st>>>(
         n_halo, ctx->d_nl_rows, d_head, d_scan, ctx->d_nl_row_ids, ctx->d_nl_row_ptrs,
         ctx->n_nl_rows);
-    {
-        const label n_tiles = (ctx->n + 255) / 256;
-        k_tile_nl_ptr<<<grid_for((int64_t)n_tiles + 1), kThreads, 0, st>>>(
-            n_tiles, 256, ctx->n_nl_rows, ctx->d_nl_row_ids, ctx->d_tile_nl_ptr);
-        k_nl_rowmask<<<grid_for(ctx->n_nl_rows), kThreads, 0, st>>>(ctx->n_nl_rows, ctx->d_nl_row_ids,
-                                                                   ctx->d_nl_rowmask);
-    }
     e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess)
         return fail(ctx, OGL_ERR_CUDA, std::string("nonlocal_pattern: ") + cudaGetErrorString(e));
-    return OGL_OK;
+    return build_ghosted(ctx);
 }
 
 int values_update(Context *ctx, const double *diag, const double *upper,
@@ -480,6 +577,12 @@ int values_update(Context *ctx, const double *diag, const double *upper,
         k_gather_nonlocal<<<grid_for(ctx->n_halo), kThreads, 0, st>>>(
             ctx->n_halo, ctx->d_nl_map, ctx->d_nl_staging, scaling, ctx->d_nl_vals);
         ctx->launches++;
+        if (ctx->have_ghosted) {
+            const int64_t nnz_g = ctx->nnz + ctx->n_halo;
+            k_gather_ghosted<<<g, kThreads, 0, st>>>(nnz_g, ctx->d_g_map, ctx->d_staging, iface_base,
+                                                     ctx->d_nl_staging, scaling, ctx->d_g_vals);
+            ctx->launches++;
+        }
     }
     OGL_CUDA(ctx, cudaGetLastError());
     ctx->have_values = true;

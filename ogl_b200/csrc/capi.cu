@@ -114,7 +114,8 @@ static void destroy(Context *c)
                     c->d_b,          c->d_x,          c->d_krylov,     c->d_hess,
                     c->d_inv_diag,   c->d_block_ptrs, c->d_row_block,  c->d_block_offs,
                     c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
-                    c->d_history};
+                    c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
+                    c->d_g_vals};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)
@@ -316,6 +317,9 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     } else if (k == "fused_halo") {
         if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "fused_halo in {0,1,2}");
         ctx->fused_halo = value;
+    } else if (k == "l2_keep_mb") {
+        if (value < -1 || value > 4096) return fail(ctx, OGL_ERR_INVALID, "l2_keep_mb out of range");
+        ctx->l2_keep_mb = value;
     } else if (k == "tile_blocked") {
         ctx->tile_blocked = value != 0;
     } else if (k == "tma_stages") {
@@ -352,6 +356,8 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "stream_ctas") *value = ctx->stream_ctas;
     else if (k == "tma_stages") *value = ctx->tma_stages;
     else if (k == "tile_blocked") *value = ctx->tile_blocked;
+    else if (k == "l2_keep_mb") *value = ctx->l2_keep_mb;
+    else if (k == "l2_keep_level") *value = l2_keep_level(ctx);
     else if (k == "comm_mode") *value = ctx->comm_mode;
     else if (k == "fused_halo") *value = ctx->fused_halo;
     else if (k == "p2p_active") *value = use_p2p(ctx) ? 1 : 0;

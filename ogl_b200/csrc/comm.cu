@@ -311,11 +311,8 @@ bool fused_halo_ok(const Context *ctx)
 {
     const int v = spmv_variant_in_use(ctx);
     if (!use_p2p(ctx) || !(v == 1 || v == 6) || ctx->fused_halo == 0) return false;
-    // auto (2): fusing the halo rows into the SpMV saves two launches and the
-    // pack kernel's fence (worth ~8 us per iteration), but costs a little per
-    // tile; measured on 2 GPUs it wins at 1 M rows per GPU (60 vs 69 us per PCG
-    // iteration) and loses at 8 M (334 vs 305 us) -- profiles/r01_comm_probe_2gpu.jsonl
-    if (ctx->fused_halo == 2) return ctx->n <= 3000000;
+    // With the ghosted CSR (assembly.cu:build_ghosted) the halo costs the kernel
+    // nothing per tile, so auto (2) == on (1).
     return true;
 }
 

@@ -102,6 +102,9 @@ struct Context {
     int64_t stream_ctas = 0;     // persistent SpMV grid (0 = 8 CTAs per SM)
     int64_t tma_stages = 3;      // shared-memory ring depth of the TMA SpMV
     int64_t use_pdl = 0;         // programmatic dependent launch between the CG kernels (measured: no gain inside graphs)
+    int64_t l2_keep_mb = 0;      // MB of the CSR stream kept L2-resident across iterations (-1 auto, 0 off)
+    unsigned long long l2_policies[6] = {0, 0, 0, 0, 0, 0};   // createpolicy results, see spmv.cu:l2_policy
+    bool l2_policies_ready = false;
     int64_t tile_blocked = 0;    // persistent SpMV: 1 = contiguous tile range per CTA (measured slower)
 
     // local pattern (a4/a5) -- resident across solves
@@ -137,8 +140,12 @@ struct Context {
     // CSR-like grouping of the non-local entries by row (rows touching the halo)
     label n_nl_rows = 0;
     label *d_nl_row_ids = nullptr, *d_nl_row_ptrs = nullptr;
-    label *d_tile_nl_ptr = nullptr;   // range of each 256-row tile in the row groups
-    unsigned int *d_nl_rowmask = nullptr;   // bit per row: owns non-local entries
+    // ghosted CSR (multi-GPU, halo-fused SpMV): every row = its local entries followed by
+    // its non-local ones, whose columns are n + index into the receive window
+    label *d_g_row_ptrs = nullptr, *d_g_cols = nullptr, *d_g_map = nullptr;
+    double *d_g_vals = nullptr;
+    int64_t max_block_nnz_g = 0;
+    bool have_ghosted = false;
 
     // values (a8/a9)
     bool have_values = false;
@@ -281,6 +288,7 @@ bool use_p2p(const Context *ctx);
 void comm_teardown(Context *ctx);
 int comm_bench(Context *ctx, int mode, int reps, double *us);
 int spmv_variant_in_use(const Context *ctx);
+int l2_keep_level(const Context *ctx);
 bool fused_halo_ok(const Context *ctx);
 int pack_stores(Context *ctx, const double *x, bool guard_done);
 

@@ -36,7 +36,6 @@ constexpr int kBatch = 8;            // entries per thread requested at once (7-
 constexpr int kBatchStream = 7;      // stream kernel: 48-register budget (5 CTAs per SM)
 constexpr int kStreamCtasPerSM = 5;  // <= 51 registers per thread
 constexpr int kMaxTilesPerCta = 1024; // row-block extents cached in shared memory
-constexpr int kHaloEarly = 1;         // halo products of a row prefetched with the tile's loads
 
 struct SpmvK {
     const label *row_ptrs;
@@ -48,11 +47,7 @@ struct SpmvK {
     label n;
     label n_row_blocks;   // stream kernel: ceil(n / kRowsPerBlock)
     int blocked;          // 1: each CTA walks a CONTIGUOUS range of tiles (x reuse in L1)
-    // halo-fused stream kernel (multi-GPU, peer-memory path): non-local rows grouped by tile
-    const label *tile_nl_ptr;   // [n_row_blocks + 1] range of each tile in the non-local row groups
-    const unsigned int *nl_rowmask;   // bit r set: row r owns non-local entries
-    const label *nl_row_ids, *nl_row_ptrs, *nl_cols;
-    const double *nl_vals;
+    unsigned long long mat_policy;   // L2 cache policy of the (column, value) stream, see l2_policy()
     double alpha, beta;
     const double *dot_with;
     double *partials;
@@ -70,6 +65,39 @@ __device__ __forceinline__ double prod_of(double v, double xv, double alpha, boo
     return adv ? __dmul_rn(__dmul_rn(alpha, v), xv) : __dmul_rn(v, xv);
 }
 
+
+// (column, value) stream of the pipelined kernel: read-only path, no L1
+// allocation, L2 priority from the policy the host picked -- evict-first for a
+// matrix much larger than L2, evict-last (for all or an address-hashed fraction
+// of the lines) when that share of the matrix can stay L2-resident from one
+// Krylov iteration to the next.
+__device__ __forceinline__ label ld_mat(const label *p, unsigned long long pol)
+{
+    label r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double ld_mat(const double *p, unsigned long long pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+// x operand of one entry.  HALO (ghosted CSR, multi-GPU): columns >= n address
+// the receive window the neighbours store into over NVLink -- read with a
+// system-scope load, never through L1.
+template <bool HALO>
+__device__ __forceinline__ double gather_x(const double *__restrict__ x, label n, const double *recv,
+                                           label c)
+{
+    if (HALO && c >= n) {
+        double h;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + (c - n)) : "memory");
+        return h;
+    }
+    return __ldg(&x[c]);
+}
 
 // tile range of a persistent CTA (or warp): strided over the grid, or one
 // contiguous chunk per worker so that consecutive tiles reuse x lines in L1
@@ -135,8 +163,6 @@ k_spmv_stream(const SpmvK a)
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
         }
-        label hq = 0, hqe = 0;
-        double hp[kHaloEarly];
         // ---- stream the slice: coalesced value/column loads, gathered x.
         // All of a thread's entries of the slice are requested in ONE batch
         // (kBatchStream independent loads of columns, of values, then of x), so a row
@@ -156,51 +182,8 @@ k_spmv_stream(const SpmvK a)
                 const label q = base + tid + u * kStreamThreads;
                 v[u] = q < len ? __ldcs(&a.vals[s + q]) : 0.0;
             }
-            if (HALO && base == 0) {
-            // (issued after the tile's own column/value loads so that its dependent
-            // loads overlap their HBM latency)
-            // HALO: does my row own non-local entries?  (bit mask over the rows + the
-            // tile's first row group: O(1), 32 B per tile.)  Its first kHaloEarly
-            // products are fetched NOW, together with the tile's own loads, and added
-            // after the local row sum; otherwise one or two threads per tile would
-            // serialise three dependent L2 round trips behind the tile barrier.
-            {
-                // one load per lane: lanes 0..7 fetch the tile's 8 mask words, lanes 8/9 the
-                // tile's row-group range; everything else is shuffles and popcounts
-                const int w = tid >> 5, lane = tid & 31;
-                unsigned int word = 0;
-                if (lane < kRowsPerBlock / 32)
-                    word = __ldg(&a.nl_rowmask[(size_t)rb * (kRowsPerBlock / 32) + lane]);
-                else if (lane < kRowsPerBlock / 32 + 2)
-                    word = (unsigned int)__ldg(&a.tile_nl_ptr[rb + (lane - kRowsPerBlock / 32)]);
-                const label h0 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32);
-                const label h1 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32 + 1);
-                if (h1 > h0) {   // block-uniform
-                    const unsigned int mine = __shfl_sync(0xffffffffu, word, w);
-                    label before = 0;
-    #pragma unroll
-                    for (int j = 0; j < kRowsPerBlock / 32; ++j) {
-                        const unsigned int mj = __shfl_sync(0xffffffffu, word, j);
-                        if (j < w) before += __popc(mj);
-                    }
-                    if ((mine >> lane) & 1u) {
-                        before += __popc(mine & ((1u << lane) - 1u));
-                        hq = __ldg(&a.nl_row_ptrs[h0 + before]);
-                        hqe = __ldg(&a.nl_row_ptrs[h0 + before + 1]);
-    #pragma unroll
-                        for (int j = 0; j < kHaloEarly; ++j) {
-                            if (hq + j < hqe) {
-                                double h;
-                                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq + j])) : "memory");
-                                hp[j] = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq + j])), h);
-                            }
-                        }
-                    }
-                }
-            }
-            }
 #pragma unroll
-            for (int u = 0; u < kBatchStream; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+            for (int u = 0; u < kBatchStream; ++u) xv[u] = c[u] >= 0 ? gather_x<HALO>(a.x, a.n, recv, c[u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < kBatchStream; ++u) {
                 const label q = base + tid + u * kStreamThreads;
@@ -213,17 +196,6 @@ k_spmv_stream(const SpmvK a)
             const label row = r0 + tid;
             double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
-            if (HALO && hqe > hq) {
-                // y += A_nl * recv for this row, entry by entry after the local sum
-#pragma unroll
-                for (int j = 0; j < kHaloEarly; ++j)
-                    if (hq + j < hqe) sum = __dadd_rn(sum, hp[j]);
-                for (label q = hq + kHaloEarly; q < hqe; ++q) {
-                    double h;
-                    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
-                    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
-                }
-            }
             a.y[row] = sum;
             if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
             if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
@@ -287,12 +259,12 @@ k_spmv_pipe(const SpmvK a)
 #pragma unroll
     for (int u = 0; u < kBatchStream; ++u) {
         const label q = tid + u * kStreamThreads;
-        c[u] = q < e - s ? __ldcs(&a.cols[s + q]) : -1;
+        c[u] = q < e - s ? ld_mat(&a.cols[s + q], a.mat_policy) : -1;
     }
 #pragma unroll
     for (int u = 0; u < kBatchStream; ++u) {
         const label q = tid + u * kStreamThreads;
-        v[u] = q < e - s ? __ldcs(&a.vals[s + q]) : 0.0;
+        v[u] = q < e - s ? ld_mat(&a.vals[s + q], a.mat_policy) : 0.0;
     }
     // PDL: the matrix stream above does not depend on the previous kernel (the
     // p-update); everything from here on does.
@@ -327,51 +299,11 @@ k_spmv_pipe(const SpmvK a)
             rs = __ldg(&a.row_ptrs[r0 + tid]);
             re = __ldg(&a.row_ptrs[r0 + tid + 1]);
         }
-        // HALO: first kHaloEarly products of my row's non-local entries, fetched now
-        // (mask word / row-group range: one load per lane + shuffles, see k_spmv_stream)
-        // (parked in thread-private shared-memory slots: the register budget of
-        // this kernel has no room for values that live across the tile barrier)
-        __shared__ double h_prod[HALO ? kRowsPerBlock : 1];
-        __shared__ label h_beg[HALO ? kRowsPerBlock : 1], h_end[HALO ? kRowsPerBlock : 1];
-        if (HALO) {
-            label hq = 0, hqe = 0;
-            double hp0 = 0.0;
-            const int w = tid >> 5, lane = tid & 31;
-            unsigned int word = 0;
-            if (lane < kRowsPerBlock / 32)
-                word = __ldg(&a.nl_rowmask[(size_t)rb * (kRowsPerBlock / 32) + lane]);
-            else if (lane < kRowsPerBlock / 32 + 2)
-                word = (unsigned int)__ldg(&a.tile_nl_ptr[rb + (lane - kRowsPerBlock / 32)]);
-            const label h0 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32);
-            const label h1 = (label)__shfl_sync(0xffffffffu, word, kRowsPerBlock / 32 + 1);
-            if (h1 > h0) {   // block-uniform
-                const unsigned int mine = __shfl_sync(0xffffffffu, word, w);
-                label before = 0;
-#pragma unroll
-                for (int j = 0; j < kRowsPerBlock / 32; ++j) {
-                    const unsigned int mj = __shfl_sync(0xffffffffu, word, j);
-                    if (j < w) before += __popc(mj);
-                }
-                if ((mine >> lane) & 1u) {
-                    before += __popc(mine & ((1u << lane) - 1u));
-                    hq = __ldg(&a.nl_row_ptrs[h0 + before]);
-                    hqe = __ldg(&a.nl_row_ptrs[h0 + before + 1]);
-                    if (hq < hqe) {
-                        double h;
-                        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + __ldg(&a.nl_cols[hq])) : "memory");
-                        hp0 = __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, __ldg(&a.nl_vals[hq])), h);
-                    }
-                }
-            }
-            h_beg[tid] = hq;
-            h_end[tid] = hqe;
-            h_prod[tid] = hp0;
-        }
         // ---- gather x for the batch already in registers, park the products
         {
             double xv[kBatchStream];
 #pragma unroll
-            for (int u = 0; u < kBatchStream; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+            for (int u = 0; u < kBatchStream; ++u) xv[u] = c[u] >= 0 ? gather_x<HALO>(a.x, a.n, recv, c[u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < kBatchStream; ++u) {
                 const label q = tid + u * kStreamThreads;
@@ -384,19 +316,20 @@ k_spmv_pipe(const SpmvK a)
             for (int u = 0; u < kBatchStream; ++u) {
                 const label q = base + tid + u * kStreamThreads;
                 if (q < len)
-                    prod[q] = prod_of(__ldcs(&a.vals[s + q]), __ldg(&a.x[__ldcs(&a.cols[s + q])]), a.alpha, ADV);
+                    prod[q] = prod_of(ld_mat(&a.vals[s + q], a.mat_policy),
+                                      gather_x<HALO>(a.x, a.n, recv, ld_mat(&a.cols[s + q], a.mat_policy)), a.alpha, ADV);
             }
         }
         // ---- prefetch the next tile's first batch into the freed registers
 #pragma unroll
         for (int u = 0; u < kBatchStream; ++u) {
             const label q = tid + u * kStreamThreads;
-            c[u] = q < e2 - s2 ? __ldcs(&a.cols[s2 + q]) : -1;
+            c[u] = q < e2 - s2 ? ld_mat(&a.cols[s2 + q], a.mat_policy) : -1;
         }
 #pragma unroll
         for (int u = 0; u < kBatchStream; ++u) {
             const label q = tid + u * kStreamThreads;
-            v[u] = q < e2 - s2 ? __ldcs(&a.vals[s2 + q]) : 0.0;
+            v[u] = q < e2 - s2 ? ld_mat(&a.vals[s2 + q], a.mat_policy) : 0.0;
         }
         __syncthreads();
         // ---- one thread per row: left-to-right sum of its products
@@ -404,16 +337,6 @@ k_spmv_pipe(const SpmvK a)
             const label row = r0 + tid;
             double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (label q = rs - s; q < re - s; ++q) sum = __dadd_rn(sum, prod[q]);
-            if (HALO && h_end[tid] > h_beg[tid]) {
-                // y += A_nl * recv for this row, entry by entry after the local sum
-                sum = __dadd_rn(sum, h_prod[tid]);
-                const label hqe = h_end[tid];
-                for (label q = h_beg[tid] + 1; q < hqe; ++q) {
-                    double h;
-                    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(h) : "l"(recv + a.nl_cols[q]) : "memory");
-                    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ADV ? a.alpha : 1.0, a.nl_vals[q]), h));
-                }
-            }
             a.y[row] = sum;
             if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(a.dot_with[row], sum));
             if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
@@ -919,6 +842,7 @@ EpiArgs make_epi_args(Context *ctx, int ar_count, bool ar_after_epi)
     return ea;
 }
 
+static unsigned long long l2_policy(Context *ctx);
 int spmv_setup(Context *ctx)
 {
     // largest slice any kRowsPerBlock-row CTA would have to park in shared memory
@@ -948,7 +872,60 @@ int spmv_setup(Context *ctx)
     if (vec_grid > max_grid) max_grid = vec_grid;
     if (ctx->blas1_blocks > max_grid) max_grid = ctx->blas1_blocks;
     OGL_TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)(max_grid + 1) * kMaxReduce));
+    (void)l2_policy(ctx);   // create the policy words outside any graph capture
     return OGL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// L2 residency of the matrix stream.  The 126 MB L2 of a B200 holds the whole
+// CSR stream of a 1 M-cell system (87 MB): marking those lines evict-last keeps
+// them on chip from one Krylov iteration to the next, so that only the vectors
+// travel over HBM.  Larger matrices keep an address-hashed fraction
+// (1/2 .. 1/16) resident and stream the rest evict-first.  The 64-bit policy
+// words are produced once per context by createpolicy on the device.
+// ---------------------------------------------------------------------------
+__global__ void k_make_policies(unsigned long long *out)
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    out[0] = p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    out[1] = p;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(p));
+    out[2] = p;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.25;" : "=l"(p));
+    out[3] = p;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.125;" : "=l"(p));
+    out[4] = p;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.0625;" : "=l"(p));
+    out[5] = p;
+}
+
+// 0: stream everything; 1..5: keep 1, 1/2, 1/4, 1/8, 1/16 of the lines
+int l2_keep_level(const Context *ctx)
+{
+    // auto: leave ~1/3 of the L2 to the vectors of the iteration
+    const double budget = (ctx->l2_keep_mb < 0 ? 88.0 : (double)ctx->l2_keep_mb) * 1.0e6;
+    if (budget <= 0.0 || ctx->nnz <= 0) return 0;
+    const double bytes = 12.0 * (double)ctx->nnz;
+    double frac = 1.0;
+    for (int level = 1; level <= 5; ++level, frac *= 0.5)
+        if (bytes * frac <= budget) return level;
+    return 0;
+}
+
+static unsigned long long l2_policy(Context *ctx)
+{
+    if (!ctx->l2_policies_ready) {
+        unsigned long long *d = nullptr;
+        if (cudaMalloc(&d, sizeof(ctx->l2_policies)) != cudaSuccess) return 0;   // caught by the launch check
+        k_make_policies<<<1, 1, 0, ctx->stream>>>(d);
+        cudaMemcpyAsync(ctx->l2_policies, d, sizeof(ctx->l2_policies), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d);
+        ctx->l2_policies_ready = true;
+    }
+    return ctx->l2_policies[l2_keep_level(ctx)];
 }
 
 int spmv_variant_in_use(const Context *ctx);
@@ -979,10 +956,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.n = ctx->n;
     k.n_row_blocks = 0;
     k.blocked = ctx->tile_blocked ? 1 : 0;
-    k.tile_nl_ptr = nullptr;
-    k.nl_rowmask = nullptr;
-    k.nl_row_ids = k.nl_row_ptrs = k.nl_cols = nullptr;
-    k.nl_vals = nullptr;
+    k.mat_policy = l2_policy(ctx);
     k.alpha = sa.alpha;
     k.beta = sa.beta;
     k.dot_with = sa.dot_with;
@@ -996,6 +970,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     const int nred = sa.nred;
     if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
     const int variant = pick_variant(ctx);
+    // a rank without halo rows (n_halo == 0) runs the halo kernel on its local matrix
+    const bool ghosted = sa.fused_halo && ctx->have_ghosted;
     cudaStream_t st = ctx->stream;
 #define DISPATCH(KERNEL, GRID, BLOCK, SMEM)                                              \
     do {                                                                                 \
@@ -1010,7 +986,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         }                                                                                \
     } while (0)
     if (variant == 1) {
-        const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
+        const size_t smem = (size_t)(ghosted ? ctx->max_block_nnz_g : ctx->max_block_nnz) * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {
 #define SET_ATTR(A, R)                                                                             \
@@ -1040,12 +1016,12 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         }                                                                                         \
     } while (0)
         if (sa.fused_halo) {
-            k.tile_nl_ptr = ctx->d_tile_nl_ptr;
-            k.nl_rowmask = ctx->d_nl_rowmask;
-            k.nl_row_ids = ctx->d_nl_row_ids;
-            k.nl_row_ptrs = ctx->d_nl_row_ptrs;
-            k.nl_cols = ctx->d_nl_cols;
-            k.nl_vals = ctx->d_nl_vals;
+            if (ghosted) {
+                // the ghosted CSR: local entries + non-local ones behind them in every row
+                k.row_ptrs = ctx->d_g_row_ptrs;
+                k.cols = ctx->d_g_cols;
+                k.vals = ctx->d_g_vals;
+            }
             k.ea = make_epi_args(ctx, nred);
             STREAM_LAUNCH(true);
         } else {
@@ -1053,7 +1029,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         }
 #undef STREAM_LAUNCH
     } else if (variant == 6) {
-        const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
+        const size_t smem = (size_t)(ghosted ? ctx->max_block_nnz_g : ctx->max_block_nnz) * sizeof(double);
         static bool attr6 = false;
         if (!attr6) {
 #define SET_ATTR6(A, R)                                                                          \
@@ -1087,12 +1063,12 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         OGL_CUDA(ctx, le);                                                  \
     } while (0)
         if (sa.fused_halo) {
-            k.tile_nl_ptr = ctx->d_tile_nl_ptr;
-            k.nl_rowmask = ctx->d_nl_rowmask;
-            k.nl_row_ids = ctx->d_nl_row_ids;
-            k.nl_row_ptrs = ctx->d_nl_row_ptrs;
-            k.nl_cols = ctx->d_nl_cols;
-            k.nl_vals = ctx->d_nl_vals;
+            if (ghosted) {
+                // the ghosted CSR: local entries + non-local ones behind them in every row
+                k.row_ptrs = ctx->d_g_row_ptrs;
+                k.cols = ctx->d_g_cols;
+                k.vals = ctx->d_g_vals;
+            }
             k.ea = make_epi_args(ctx, nred);
             PIPE_LAUNCH(true);
         } else {
