@@ -191,6 +191,12 @@ int ogl_spmv_bench(ogl_ctx *ctx, int32_t reps, int fused_dot, float *ms);
  * (roofline measurement of the whole iteration), timed with CUDA events. */
 int ogl_pcg_bench(ogl_ctx *ctx, int32_t iters, float *ms);
 int ogl_synchronize(ogl_ctx *ctx);
+/* Diagnostics: with option `trace` 1 the iteration kernels log (tag << 48 | %globaltimer ns)
+ * events -- launch start, last CTA arrived, local sums done, all-reduced, epilogue done; tags
+ * 10.. p-update, 20.. SpMV, 30.. x/r-update -- into a device buffer.  Copies up to `cap` events
+ * to the host and restarts the timeline.  No reference counterpart (nsys-style tooling). */
+int ogl_trace_download(ogl_ctx *ctx, uint64_t *events, int64_t cap, int64_t *n_events);
+
 /* HBM calibration kernels (roofline context for the numbers above), timed with
  * CUDA events; *gbs = bytes moved / time.  mode 0: copy (read + write, 128-bit),
  * 1: read-only sum, 2: read-only 8 B + 4 B streams (values + columns like CSR). */

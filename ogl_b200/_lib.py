@@ -71,6 +71,7 @@ SYMBOLS = {
     "ogl_spmv_bench": (C.c_int, [ctx_p, C.c_int32, C.c_int, C.POINTER(C.c_float)]),
     "ogl_pcg_bench": (C.c_int, [ctx_p, C.c_int32, C.POINTER(C.c_float)]),
     "ogl_synchronize": (C.c_int, [ctx_p]),
+    "ogl_trace_download": (C.c_int, [ctx_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "ogl_membench": (C.c_int, [ctx_p, C.c_int, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
     "ogl_commbench": (C.c_int, [ctx_p, C.c_int, C.c_int32, C.POINTER(C.c_double)]),
     "ogl_export_mtx": (C.c_int, [ctx_p, C.c_int, C.c_char_p]),

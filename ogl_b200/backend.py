@@ -197,6 +197,14 @@ class Context:
         self._check(self.lib.ogl_pcg_bench(self.h, iters, C.byref(ms)))
         return ms.value
 
+    def trace_download(self, cap: int = 1 << 16):
+        """Timeline events logged since the last call (option `trace` 1): (tags, times_ns)."""
+        ev = np.zeros(cap, dtype=np.uint64)
+        n = C.c_int64(0)
+        self._check(self.lib.ogl_trace_download(self.h, ev.ctypes.data, cap, C.byref(n)))
+        ev = ev[: n.value]
+        return (ev >> np.uint64(48)).astype(np.int64), (ev & np.uint64((1 << 48) - 1)).astype(np.int64)
+
     def membench(self, mode: int, n_doubles: int = 1 << 27, reps: int = 10) -> float:
         g = C.c_double(0)
         self._check(self.lib.ogl_membench(self.h, mode, n_doubles, reps, C.byref(g)))

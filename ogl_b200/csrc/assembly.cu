@@ -400,6 +400,7 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
         if (w) cudaFree(w);
         w = nullptr;
     }
+    ctx->work_len = 0;
     return spmv_setup(ctx);
 }
 

@@ -49,7 +49,20 @@ int download(Context *ctx, void *dst, const void *src, size_t bytes)
 int get_work(Context *ctx, int idx, double **out)
 {
     if ((int)ctx->work.size() <= idx) ctx->work.resize(idx + 1, nullptr);
-    if (!ctx->work[idx]) OGL_TRY(dev_alloc(ctx, &ctx->work[idx], ctx->n));
+    // n rows + room for the ghost entries (CG ghost-p mode keeps p with its halo)
+    const size_t need = (size_t)ctx->n + (size_t)(ctx->n_halo > ctx->n_send ? ctx->n_halo : ctx->n_send);
+    if (ctx->work_len < need) {
+        for (auto &w : ctx->work) {
+            if (w) cudaFree(w);
+            w = nullptr;
+        }
+        if (ctx->graph_exec) {   // a captured chunk holds the old addresses
+            cudaGraphExecDestroy(ctx->graph_exec);
+            ctx->graph_exec = nullptr;
+        }
+        ctx->work_len = need;
+    }
+    if (!ctx->work[idx]) OGL_TRY(dev_alloc(ctx, &ctx->work[idx], ctx->work_len));
     *out = ctx->work[idx];
     return OGL_OK;
 }
@@ -115,7 +128,7 @@ static void destroy(Context *c)
                     c->d_inv_diag,   c->d_block_ptrs, c->d_row_block,  c->d_block_offs,
                     c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
                     c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
-                    c->d_g_vals};
+                    c->d_g_vals,     c->d_push_ptr,   c->d_push_ent,   c->d_trace};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)
@@ -317,6 +330,14 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     } else if (k == "fused_halo") {
         if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "fused_halo in {0,1,2}");
         ctx->fused_halo = value;
+    } else if (k == "ghost_p") {
+        ctx->ghost_p = value != 0;
+    } else if (k == "trace") {
+        ctx->trace = value != 0;
+        if (ctx->trace) {
+            if (!ctx->d_trace) OGL_TRY(dev_alloc(ctx, &ctx->d_trace, (size_t)ogl::kTraceCap + 1));
+            OGL_CUDA(ctx, cudaMemsetAsync(ctx->d_trace, 0, sizeof(unsigned long long), ctx->stream));
+        }
     } else if (k == "l2_keep_mb") {
         if (value < -1 || value > 4096) return fail(ctx, OGL_ERR_INVALID, "l2_keep_mb out of range");
         ctx->l2_keep_mb = value;
@@ -357,6 +378,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "tma_stages") *value = ctx->tma_stages;
     else if (k == "tile_blocked") *value = ctx->tile_blocked;
     else if (k == "l2_keep_mb") *value = ctx->l2_keep_mb;
+    else if (k == "ghost_p") *value = ctx->ghost_p;
     else if (k == "l2_keep_level") *value = l2_keep_level(ctx);
     else if (k == "comm_mode") *value = ctx->comm_mode;
     else if (k == "fused_halo") *value = ctx->fused_halo;
@@ -589,6 +611,24 @@ int ogl_pcg_bench(ogl_ctx *ctx, int32_t iters, float *ms)
     ogl_solve_result r;
     OGL_TRY(solve(ctx, &p, &r));
     *ms = (float)(r.solve_us * 1e-3);
+    return OGL_OK;
+}
+
+int ogl_trace_download(ogl_ctx *ctx, uint64_t *events, int64_t cap, int64_t *n_events)
+{
+    CHECK_CTX(ctx);
+    if (!n_events || cap < 0 || (cap > 0 && !events))
+        return fail(ctx, OGL_ERR_INVALID, "ogl_trace_download: bad arguments");
+    *n_events = 0;
+    if (!ctx->d_trace) return OGL_OK;
+    unsigned long long cursor = 0;
+    OGL_TRY(download(ctx, &cursor, ctx->d_trace, sizeof(cursor)));
+    int64_t n = (int64_t)(cursor < (unsigned long long)ogl::kTraceCap ? cursor : ogl::kTraceCap);
+    if (n > cap) n = cap;
+    if (n > 0) OGL_TRY(download(ctx, events, ctx->d_trace + 1, sizeof(uint64_t) * (size_t)n));
+    *n_events = n;
+    // restart the timeline
+    OGL_CUDA(ctx, cudaMemsetAsync(ctx->d_trace, 0, sizeof(unsigned long long), ctx->stream));
     return OGL_OK;
 }
 

@@ -21,6 +21,7 @@ using scalar = double;
 constexpr int kMaxReduce = 4;          // scalars reduced by one kernel launch
 constexpr int kNumSM = 148;            // B200
 constexpr int kBlas1Threads = 256;
+constexpr int kTraceCap = 1 << 16;   // timeline events kept per context
 constexpr int kBlas1BlocksPerSM = 4;   // 1024 resident threads per SM, <= 64 registers each
 constexpr int kMaxPartialBlocks = 4096;
 
@@ -140,6 +141,15 @@ struct Context {
     // CSR-like grouping of the non-local entries by row (rows touching the halo)
     label n_nl_rows = 0;
     label *d_nl_row_ids = nullptr, *d_nl_row_ptrs = nullptr;
+    // CG on several GPUs, "ghost p" mode (solver.cu): boundary z pushed by the x/r-update
+    // kernel, p kept with n + n_halo entries; per-CTA lists of the send entries a CTA owns
+    int64_t trace = 0;           // 1: kernels log (tag, globaltimer) events into d_trace
+    unsigned long long *d_trace = nullptr;
+    int64_t ghost_p = 1;
+    std::vector<label> h_send_idxs;
+    label *d_push_ptr = nullptr, *d_push_ent = nullptr;
+    int push_grid = 0;
+    size_t work_len = 0;
     // ghosted CSR (multi-GPU, halo-fused SpMV): every row = its local entries followed by
     // its non-local ones, whose columns are n + index into the receive window
     label *d_g_row_ptrs = nullptr, *d_g_cols = nullptr, *d_g_map = nullptr;
@@ -265,6 +275,8 @@ struct SpmvArgs {
     bool inline_epi = true;             // run it inside the kernel (single rank)
     bool fused_halo = false;            // stream kernel applies the non-local block itself (P2P)
     bool halo_stored = false;           // boundary values already stored by the previous kernel
+    bool ghost_x = false;               // x has n + n_halo entries, the ghost part already filled:
+                                        // ghosted CSR, no flag handshake (CG ghost-p mode)
 };
 int spmv_local(Context *ctx, const SpmvArgs &a);
 int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
@@ -291,6 +303,8 @@ int spmv_variant_in_use(const Context *ctx);
 int l2_keep_level(const Context *ctx);
 bool fused_halo_ok(const Context *ctx);
 int pack_stores(Context *ctx, const double *x, bool guard_done);
+int push_boundary(Context *ctx, const double *v);
+int ensure_push_lists(Context *ctx, int grid, int threads);
 
 // solver.cu ----------------------------------------------------------------------
 int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res);

@@ -107,7 +107,21 @@ struct EpiArgs {
     CommDev *comm;        // peer-memory window (nullptr: single rank or NCCL path)
     int ar_count;         // leading state->red[] slots to all-reduce in this launch (0: none)
     int ar_after_epi;     // 1: run the epilogue on the local sums first (mean)
+    // device-side timeline (option `trace`): [0] = cursor, then (tag << 48 | globaltimer ns)
+    unsigned long long *trace;
+    int trace_tag, trace_cap;
 };
+
+// one timeline event; called by single threads at a handful of points per launch
+__device__ __forceinline__ void trace_event(const EpiArgs &ea, int sub)
+{
+    if (!ea.trace) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(ea.trace, 1ull);
+    if (i < (unsigned long long)ea.trace_cap)
+        ea.trace[1 + i] = ((unsigned long long)(ea.trace_tag + sub) << 48) | (t & 0xffffffffffffull);
+}
 
 EpiArgs make_epi_args(Context *ctx, int ar_count = 0, bool ar_after_epi = false);
 
@@ -287,6 +301,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
     }
     __syncthreads();
     if (!is_last) return;
+    if (threadIdx.x == 0) trace_event(ea, 1);   // last CTA of the grid has arrived
     __threadfence();
     double acc[NRED];
 #pragma unroll
@@ -307,13 +322,16 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
             state->red[red_base + j] = accumulate ? state->red[red_base + j] + acc[j] : acc[j];
         }
         *ticket = 0u;
+        trace_event(ea, 2);   // local sums done
     }
     const bool ar = ea.comm != nullptr && ea.ar_count > 0;   // block-uniform
     if (ar && !ea.ar_after_epi) {
         __syncthreads();
         p2p_allreduce(state, ea.ar_count, ea.comm);
+        if (threadIdx.x == 0) trace_event(ea, 3);   // all-reduced
     }
     if (threadIdx.x == 0 && inline_epi && epi != EPI_NONE) run_epilogue(epi, state, ea);
+    if (threadIdx.x == 0) trace_event(ea, 4);   // epilogue done
     if (ar && ea.ar_after_epi) {
         __syncthreads();
         p2p_allreduce(state, ea.ar_count, ea.comm);

@@ -40,7 +40,8 @@ struct VecK {
     double *out0, *out1, *out2, *out3;
     const label *send_idx;   // fused halo pack (multi-GPU peer-memory path)
     label n_send;
-    int pack;
+    int pack;                // k_cg_p: 1 store boundary p', 2 update ghost p; k_cg_xr: 1 push boundary z
+    const label *push_ptr, *push_ent;   // k_cg_xr: send entries owned by each CTA
 };
 
 #define GRID_STRIDE(i, n)                                                             \
@@ -115,9 +116,22 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
     cudaGridDependencySynchronize();            // PDL: everything below reads the previous kernel's output
     cudaTriggerProgrammaticLaunchCompletion();  // the SpMV may start getting resident
     if (a.guard_done && a.state->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(a.ea, 0);
     const bool p_is_z = a.state->flag_p_is_z != 0;
     const double t = a.state->coef_p;
-    if (a.pack) {
+    if (a.pack == 2) {
+        // ghost-p mode: the neighbours pushed their boundary z into slot 2 of my
+        // window (k_cg_xr / push_boundary), published by the all-reduce that gave
+        // rho; the ghost entries of p get the same update as the neighbours' own
+        // cells -- same operands, same operations, same bits.
+        const CommDev *c = a.ea.comm;
+        const double *zg = c->my_recv + 2 * (size_t)c->my_recv_stride;
+        GRID_STRIDE(k, a.n_send) {
+            double z;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(z) : "l"(zg + k) : "memory");
+            a.out0[a.n + k] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.in1[a.n + k]));
+        }
+    } else if (a.pack) {
         CommDev *c = a.ea.comm;
         const unsigned long long seq = c->halo_seq + 1;
         const int parity = (int)(seq & 1ull);
@@ -182,9 +196,29 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.guard_done && a.state->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(a.ea, 0);
     const bool upd = a.state->beta != 0.0;
     const double t = a.state->coef_x;
     double red[2] = {0.0, 0.0};
+    if (a.pack && PK != 2) {
+        // ghost-p mode: the new z (r when unpreconditioned) of the boundary cells THIS CTA
+        // owns goes into slot 2 of the neighbours' windows first, so the NVLink stores
+        // drain while the main loop runs; the all-reduce of rho below publishes them.
+        const CommDev *c = a.ea.comm;
+        const label j1 = a.push_ptr[blockIdx.x + 1];
+        for (label j = a.push_ptr[blockIdx.x] + threadIdx.x; j < j1; j += blockDim.x) {
+            const label k = a.push_ent[j];
+            const label cell = a.send_idx[k];
+            double r = a.out1[cell];
+            if (upd) r = __dsub_rn(r, __dmul_rn(t, a.in1[cell]));
+            const double v = PK == 1 ? __dmul_rn(r, a.in2[cell]) : r;
+            int tg = 0;
+            while (k >= c->send_offs[tg + 1]) ++tg;
+            double *dst = c->peer_recv[tg] + 2 * (size_t)c->peer_recv_stride[tg] + (k - c->send_offs[tg]);
+            *dst = v;
+        }
+        __syncthreads();   // nobody overwrites r before every push of this CTA has read it
+    }
     const double2 *__restrict__ p2 = reinterpret_cast<const double2 *>(a.in0);
     const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(a.in1);
     const double2 *__restrict__ d2 = reinterpret_cast<const double2 *>(a.in2);
@@ -219,6 +253,11 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
             a.out1[i] = r;
         }
         if (PK == 1) a.out2[i] = z;
+    }
+    if (a.pack && PK != 2) {
+        // system-scope fence (cumulative over this CTA's pushes) ahead of the ticket
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();
     }
     grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
 }
@@ -424,12 +463,25 @@ int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, dou
     return finish_reduction(ctx, 3, epi, false);
 }
 
+// CG on several GPUs over peer memory, scalar (or no) preconditioner: "ghost p".
+// The only vector the SpMV needs from the neighbours is p = z + beta p_old.  Its
+// boundary z is pushed by the kernel that computes z (k_cg_xr) and published by
+// the all-reduce of rho that the same kernel ends with; every rank then updates
+// the ghost entries of p itself.  The iteration has no halo handshake left --
+// its two all-reduces are its only rendezvous -- and the SpMV is the plain
+// single-GPU kernel over the ghosted CSR.
+static bool ghost_p_mode(const Context *ctx)
+{
+    return ctx->ghost_p != 0 && ctx->n_ranks > 1 && fused_halo_ok(ctx) && pk_of(ctx) != 2;
+}
+
 static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old, double *p,
                         double *q)
 {
     const int pk = pk_of(ctx);
     const double *zz = pk == 0 ? r : z;
-    const bool pack = fused_halo_ok(ctx) && ctx->n_send > 0;
+    const bool ghost = ghost_p_mode(ctx);
+    const bool pack = !ghost && fused_halo_ok(ctx) && ctx->n_send > 0;
     {
         VecK a = base_args(ctx, EPI_NONE, true);
         a.in0 = zz;
@@ -437,7 +489,8 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
         a.out0 = p;
         a.send_idx = ctx->d_send_idxs;
         a.n_send = ctx->n_send;
-        a.pack = pack ? 1 : 0;
+        a.pack = ghost ? 2 : (pack ? 1 : 0);
+        a.ea.trace_tag = 10;
         OGL_CUDA(ctx, launch_pdl(k_cg_p, vec_grid(ctx), kT, 0, ctx->stream, ctx->use_pdl != 0, a));
         ctx->launches++;
     }
@@ -450,6 +503,7 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
         s.guard_done = true;
         s.epi = EPI_CG_BETA;
         s.halo_stored = pack;
+        s.ghost_x = ghost;
         // profile_stride > 0 (graphs off): bracket every stride-th SpMV of the real
         // loop with CUDA events on the launching stream
         const bool sample = ctx->profile_stride > 0 && !ctx->capturing &&
@@ -467,6 +521,14 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
         a.out0 = ctx->d_x;
         a.out1 = r;
         a.out2 = z;
+        a.ea.trace_tag = 30;
+        if (ghost) {
+            a.pack = 1;
+            a.send_idx = ctx->d_send_idxs;
+            a.n_send = ctx->n_send;
+            a.push_ptr = ctx->d_push_ptr;
+            a.push_ent = ctx->d_push_ent;
+        }
 #define LAUNCH_XR(PKV)                                                                             \
     do {                                                                                           \
         OGL_CUDA(ctx, launch_pdl(k_cg_xr<PKV>, vec_grid(ctx), kT, 0, ctx->stream, ctx->use_pdl != 0, a)); \
@@ -683,8 +745,12 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
         double *pv2;
         OGL_TRY(get_work(ctx, 9, &pv2));
         OGL_TRY(solve_prologue(ctx, 0, r, z, nullptr, w, tmp, EPI_INIT_CHECK));
-        OGL_CUDA(ctx, cudaMemsetAsync(pv, 0, sizeof(double) * ctx->n, st));
-        OGL_CUDA(ctx, cudaMemsetAsync(pv2, 0, sizeof(double) * ctx->n, st));
+        OGL_CUDA(ctx, cudaMemsetAsync(pv, 0, sizeof(double) * ctx->work_len, st));
+        OGL_CUDA(ctx, cudaMemsetAsync(pv2, 0, sizeof(double) * ctx->work_len, st));
+        if (ghost_p_mode(ctx)) {
+            OGL_TRY(ensure_push_lists(ctx, vec_grid(ctx), kT));
+            OGL_TRY(push_boundary(ctx, pk_of(ctx) == 0 ? r : z));   // boundary z0
+        }
         int flip = 0;   // the two p buffers alternate; a chunk holds an even number of iterations
         OGL_TRY(run_chunks(ctx, OGL_SOLVER_CG, p->max_iter, [&]() {
             double *p_old = flip ? pv2 : pv, *p_new = flip ? pv : pv2;

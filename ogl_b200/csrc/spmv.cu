@@ -271,6 +271,7 @@ k_spmv_pipe(const SpmvK a)
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.guard_done && a.state->done) return;
+    if (blockIdx.x == 0 && tid == 0) trace_event(a.ea, 0);
     if (HALO) {
         // HALO (multi-GPU, peer-memory path): see k_spmv_stream
         seq = cm->halo_seq + 1;
@@ -839,6 +840,9 @@ EpiArgs make_epi_args(Context *ctx, int ar_count, bool ar_after_epi)
     ea.comm = p2p ? ctx->d_commdev : nullptr;
     ea.ar_count = p2p ? ar_count : 0;
     ea.ar_after_epi = ar_after_epi ? 1 : 0;
+    ea.trace = ctx->trace ? ctx->d_trace : nullptr;
+    ea.trace_tag = 0;
+    ea.trace_cap = kTraceCap;
     return ea;
 }
 
@@ -967,11 +971,12 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.inline_epi = sa.inline_epi ? 1 : 0;
     k.guard_done = sa.guard_done ? 1 : 0;
     k.ea = make_epi_args(ctx, 0);
+    k.ea.trace_tag = 20;
     const int nred = sa.nred;
     if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
     const int variant = pick_variant(ctx);
     // a rank without halo rows (n_halo == 0) runs the halo kernel on its local matrix
-    const bool ghosted = sa.fused_halo && ctx->have_ghosted;
+    const bool ghosted = (sa.fused_halo || sa.ghost_x) && ctx->have_ghosted;
     cudaStream_t st = ctx->stream;
 #define DISPATCH(KERNEL, GRID, BLOCK, SMEM)                                              \
     do {                                                                                 \
@@ -1022,9 +1027,17 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
                 k.cols = ctx->d_g_cols;
                 k.vals = ctx->d_g_vals;
             }
-            k.ea = make_epi_args(ctx, nred);
+            k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;
             STREAM_LAUNCH(true);
         } else {
+            if (sa.ghost_x) {
+                if (ghosted) {
+                    k.row_ptrs = ctx->d_g_row_ptrs;
+                    k.cols = ctx->d_g_cols;
+                    k.vals = ctx->d_g_vals;
+                }
+                k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;
+            }
             STREAM_LAUNCH(false);
         }
 #undef STREAM_LAUNCH
@@ -1069,9 +1082,17 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
                 k.cols = ctx->d_g_cols;
                 k.vals = ctx->d_g_vals;
             }
-            k.ea = make_epi_args(ctx, nred);
+            k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;
             PIPE_LAUNCH(true);
         } else {
+            if (sa.ghost_x) {
+                if (ghosted) {
+                    k.row_ptrs = ctx->d_g_row_ptrs;
+                    k.cols = ctx->d_g_cols;
+                    k.vals = ctx->d_g_vals;
+                }
+                k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;   // the fused sums are all-reduced in this launch
+            }
             PIPE_LAUNCH(false);
         }
 #undef PIPE_LAUNCH
@@ -1173,7 +1194,7 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
     k.epi = epi;
     k.inline_epi = inline_epi ? 1 : 0;
     k.guard_done = guard_done ? 1 : 0;
-    k.ea = make_epi_args(ctx, nred);
+    k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;
     int grid = (ctx->n_nl_rows + 255) / 256;
     if (grid < 1) grid = 1;
     if (nred == 0) k_spmv_nonlocal<0><<<grid, 256, 0, ctx->stream>>>(k);

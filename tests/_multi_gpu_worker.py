@@ -24,20 +24,23 @@ CASES = {
     "cavity_cg_none": (lambda p: cases.cavity_2d((p[0] * p[2], p[1], 1)), "GKOCG", "none", 1, 1e-11),
 }
 
+MODES = (0, 1, 2, 3)
+
 
 def main():
     out, procs = sys.argv[1], tuple(int(v) for v in sys.argv[2].split(","))
     ps = init_from_env("nccl")
     db = ObjectRegistry()
     results = {}
-    # every case on the three data paths: 0 peer-memory windows with the halo fused into
-    # the SpMV (default), 1 NCCL, 2 peer-memory windows with separate pack / non-local kernels
+    # every case on the four data paths: 0 peer-memory windows, halo fused into the SpMV, CG
+    # in ghost-p mode (default); 1 NCCL; 2 peer-memory windows with separate pack / non-local
+    # kernels; 3 like 0 but CG with the flag handshake instead of ghost p
     for name, (builder, solver, precond, mbs, tol), mode in (
-            (n, c, m) for n, c in CASES.items() for m in (0, 1, 2)):
+            (n, c, m) for n, c in CASES.items() for m in MODES):
         s = builder(procs)[ps.rank]
         controls = {"solver": solver, "executor": "cuda", "tolerance": tol, "relTol": 0.0,
                     "adaptMinIter": False, "krylovDim": 30, "comm_mode": 1 if mode == 1 else 0,
-                    "fused_halo": 0 if mode == 2 else 1,
+                    "fused_halo": 0 if mode == 2 else 1, "ghost_p": 0 if mode == 3 else 1,
                     "preconditioner": {"preconditioner": precond, "maxBlockSize": mbs}}
         name = f"{name}@{mode}"
         sol = lduMatrix_solver_New(name, s, controls, db, ps)

@@ -34,7 +34,7 @@ def test_decomposed_solves_match_oracle(oracle, tmp_path, procs):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from _multi_gpu_worker import CASES
+    from _multi_gpu_worker import CASES, MODES
     out = str(tmp_path / "res")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
            str(world), "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
@@ -47,8 +47,9 @@ def test_decomposed_solves_match_oracle(oracle, tmp_path, procs):
     res = [json.load(open(f"{out}.{r}")) for r in range(world)]
     assert res[0]["pressure_cg@0"]["p2p"] == 1, "peer-memory path not active on an NVLink box"
     assert res[0]["pressure_cg@1"]["p2p"] == 0 and res[0]["pressure_cg@2"]["p2p"] == 1
+    assert res[0]["pressure_cg@3"]["p2p"] == 1
     for name, (builder, solver, precond, mbs, tol) in (
-            (f"{n}@{m}", c) for n, c in CASES.items() for m in (0, 1, 2)):
+            (f"{n}@{m}", c) for n, c in CASES.items() for m in MODES):
         systems = builder(procs)
         asms = [oracle.assemble(s) for s in systems]
         o = oracle.solve(asms, solver, precond, max_block_size=mbs, tolerance=tol, krylov_dim=30)

@@ -17,10 +17,11 @@ def main():
     ps = init_from_env("nccl")
     s = bench.build_rank_system(cells, ps.n_ranks, ps.rank)
     out = {}
-    for mode in (0, 2, 1):
+    for mode in (0, 3, 2, 1):
         ctx = Context(device_id=ps.local_rank, rank=ps.rank, n_ranks=ps.n_ranks, nccl_id=ps.nccl_id)
         ctx.set_option("comm_mode", 1 if mode == 1 else 0)
         ctx.set_option("fused_halo", 0 if mode == 2 else 1)
+        ctx.set_option("ghost_p", 0 if mode == 3 else 1)
         ctx.pattern_from_ldu(s.n, s.lower_addr, s.upper_addr, True)
         ctx.partition_create(s.n, *host.create_communication_pattern(s))
         ctx.nonlocal_pattern(host.collect_cells_on_non_local_interface(s))
@@ -28,7 +29,7 @@ def main():
         ctx.vector_upload(L.OGL_VEC_B, s.source)
         ctx.vector_fill(L.OGL_VEC_X, 0.0)
         ctx.precond_setup(L.OGL_PRECOND_BJ, 1)
-        tag = ("p2p_fused" if mode == 0 else "p2p") if ctx.get_option("p2p_active") else "nccl"
+        tag = ({0: "p2p_ghost_p", 3: "p2p_fused"}.get(mode, "p2p")) if ctx.get_option("p2p_active") else "nccl"
         r = {}
         if tag == "p2p":
             r["ar_per_launch_us"] = ctx.commbench(0, 300)
