@@ -128,7 +128,7 @@ static void destroy(Context *c)
                     c->d_inv_diag,   c->d_block_ptrs, c->d_row_block,  c->d_block_offs,
                     c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
                     c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
-                    c->d_g_vals,     c->d_push_ptr,   c->d_push_ent,   c->d_trace};
+                    c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)
@@ -332,6 +332,9 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->fused_halo = value;
     } else if (k == "ghost_p") {
         ctx->ghost_p = value != 0;
+    } else if (k == "fused_pcg") {
+        if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "fused_pcg in {0,1,2}");
+        ctx->fused_pcg = value;
     } else if (k == "trace") {
         ctx->trace = value != 0;
         if (ctx->trace) {
@@ -379,6 +382,8 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "tile_blocked") *value = ctx->tile_blocked;
     else if (k == "l2_keep_mb") *value = ctx->l2_keep_mb;
     else if (k == "ghost_p") *value = ctx->ghost_p;
+    else if (k == "fused_pcg") *value = ctx->fused_pcg;
+    else if (k == "fused_pcg_active") *value = pcg_fused_ok(ctx) ? 1 : 0;
     else if (k == "l2_keep_level") *value = l2_keep_level(ctx);
     else if (k == "comm_mode") *value = ctx->comm_mode;
     else if (k == "fused_halo") *value = ctx->fused_halo;

@@ -102,20 +102,16 @@ k_pack_stores(label n_send, const label *__restrict__ idx, const double *__restr
 // CG ghost-p mode, before the first iteration: boundary values of v into slot 2
 // of the neighbours' windows (afterwards the x/r-update kernel does this itself)
 __global__ void __launch_bounds__(256)
-k_push_boundary(label n_send, const label *__restrict__ idx, const double *__restrict__ v, CommDev *c)
+k_push_boundary(label n_send, const label *__restrict__ idx, const double *__restrict__ v,
+                double *const *__restrict__ dst, const CommDev *c)
 {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < n_send) {
-        int t = 0;
-        while (k >= c->send_offs[t + 1]) ++t;
-        double *dst = c->peer_recv[t] + 2 * (size_t)c->peer_recv_stride[t] + (k - c->send_offs[t]);
-        *dst = v[idx[k]];
-        __threadfence_system();
-    }
+    if (k < n_send)
+        push_stamped(reinterpret_cast<unsigned long long *>(dst[k]), v[idx[k]], stamp_of(ld_ar_seq(c) + 1));
 }
 
-// rendezvous of all ranks (an all-reduce of nothing): what every rank stored
-// into a peer window before it is visible to the peer afterwards
+// rendezvous of all ranks (an all-reduce of nothing): keeps the rule "a push is
+// stamped with the number of the all-reduce that follows it" for the first push
 __global__ void k_rank_barrier(SolveState *state, CommDev *c) { p2p_allreduce(state, 0, c); }
 
 struct Directory {
@@ -162,13 +158,13 @@ static int p2p_setup(Context *ctx)
     for (int t = 0; t <= ctx->n_targets; ++t) mine.send_offs[t] = ctx->send_offs[t];
     size_t off = 0;
     mine.off_mbox = (long long)off;
-    off = align_up(off + sizeof(double) * 2 * R * kSlot, 256);
+    off = align_up(off + sizeof(unsigned long long) * 2 * R * kSlot, 256);
     mine.off_data_flag = (long long)off;
     off = align_up(off + sizeof(unsigned long long) * kMaxTargets, 256);
     mine.off_ack_flag = (long long)off;
     off = align_up(off + sizeof(unsigned long long) * kMaxTargets, 256);
     mine.off_recv = (long long)off;
-    off = align_up(off + sizeof(double) * 3 * (size_t)(ctx->n_send > 0 ? ctx->n_send : 1), 256);   // parity 0/1 + slot 2 (boundary z of the CG ghost-p mode)
+    off = align_up(off + sizeof(double) * 4 * (size_t)(ctx->n_send > 0 ? ctx->n_send : 1), 256);   // parity 0/1 + slot 2: boundary z of the CG ghost-p mode, 16 B per (stamped) value
     ctx->window_bytes = off;
     int ok_local = 1;
     if (cudaMalloc(&ctx->d_window, off) != cudaSuccess) ok_local = 0;
@@ -262,6 +258,16 @@ static int p2p_setup(Context *ctx)
     h.my_recv_stride = ctx->n_send > 0 ? ctx->n_send : 1;
     OGL_TRY(dev_alloc(ctx, &ctx->d_commdev, 1));
     OGL_CUDA(ctx, cudaMemcpy(ctx->d_commdev, &h, sizeof(h), cudaMemcpyHostToDevice));
+    {
+        // CG ghost-p mode: destination of every send entry in slot 2 of its neighbour's window
+        std::vector<double *> dst((size_t)ctx->n_send, nullptr);
+        for (label t = 0; t < ctx->n_targets; ++t)
+            for (label k = ctx->send_offs[t]; k < ctx->send_offs[t + 1]; ++k)
+                dst[(size_t)k] = h.peer_recv[t] + 2 * h.peer_recv_stride[t] + 2 * (size_t)(k - ctx->send_offs[t]);
+        OGL_TRY(dev_alloc(ctx, &ctx->d_push_dst, (size_t)ctx->n_send));
+        OGL_CUDA(ctx, cudaMemcpy(ctx->d_push_dst, dst.data(), sizeof(double *) * dst.size(),
+                                 cudaMemcpyHostToDevice));
+    }
     // nobody may touch a window before every rank has finished zeroing/mapping
     int *d_bar = nullptr;
     OGL_TRY(dev_alloc(ctx, &d_bar, 1));
@@ -339,41 +345,13 @@ int push_boundary(Context *ctx, const double *v)
 {
     if (!use_p2p(ctx)) return fail(ctx, OGL_ERR_INVALID, "push_boundary needs the peer-memory path");
     if (ctx->n_send > 0) {
-        k_push_boundary<<<(ctx->n_send + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_send, ctx->d_send_idxs, v,
-                                                                           ctx->d_commdev);
+        k_push_boundary<<<(ctx->n_send + 255) / 256, 256, 0, ctx->stream>>>(
+            ctx->n_send, ctx->d_send_idxs, v, ctx->d_push_dst, ctx->d_commdev);
         ctx->launches++;
     }
     k_rank_barrier<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_commdev);
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
-    return OGL_OK;
-}
-
-// Per-CTA lists of the send entries whose cell a CTA of the BLAS-1 grid owns
-// (k_cg_xr's grid-stride loop over row pairs): entry k belongs to the CTA that
-// updates r[send_idxs[k]], so that CTA can push the new boundary z without a race.
-int ensure_push_lists(Context *ctx, int grid, int threads)
-{
-    if (ctx->push_grid == grid && ctx->d_push_ptr) return OGL_OK;
-    const int64_t n2 = ctx->n >> 1;
-    const int64_t total = (int64_t)grid * threads;
-    auto owner = [&](label cell) -> int {
-        if ((int64_t)cell >= 2 * n2) return 0;   // odd tail: block 0
-        return (int)((((int64_t)cell >> 1) % total) / threads);
-    };
-    std::vector<label> ptr((size_t)grid + 1, 0), ent((size_t)ctx->n_send);
-    for (label k = 0; k < ctx->n_send; ++k) ptr[(size_t)owner(ctx->h_send_idxs[k]) + 1]++;
-    for (int g = 0; g < grid; ++g) ptr[(size_t)g + 1] += ptr[(size_t)g];
-    std::vector<label> fill(ptr.begin(), ptr.end() - 1);
-    for (label k = 0; k < ctx->n_send; ++k) ent[(size_t)fill[(size_t)owner(ctx->h_send_idxs[k])]++] = k;
-    if (ctx->d_push_ptr) cudaFree(ctx->d_push_ptr);
-    if (ctx->d_push_ent) cudaFree(ctx->d_push_ent);
-    ctx->d_push_ptr = ctx->d_push_ent = nullptr;
-    OGL_TRY(dev_alloc(ctx, &ctx->d_push_ptr, (size_t)grid + 1));
-    OGL_TRY(dev_alloc(ctx, &ctx->d_push_ent, (size_t)ctx->n_send));
-    OGL_TRY(upload(ctx, ctx->d_push_ptr, ptr.data(), sizeof(label) * ptr.size()));
-    OGL_TRY(upload(ctx, ctx->d_push_ent, ent.data(), sizeof(label) * ent.size()));
-    ctx->push_grid = grid;
     return OGL_OK;
 }
 
@@ -422,8 +400,6 @@ int partition_create(Context *ctx, label n_local, label n_targets, const label *
     OGL_TRY(dev_alloc(ctx, &ctx->d_send_buf, ctx->n_send));
     OGL_TRY(dev_alloc(ctx, &ctx->d_recv_buf, ctx->n_send));
     OGL_TRY(upload(ctx, ctx->d_send_idxs, send_idxs, sizeof(label) * ctx->n_send));
-    ctx->h_send_idxs.assign(send_idxs, send_idxs + ctx->n_send);
-    ctx->push_grid = 0;
     // global size (Partition.H:118-121): sum of the local sizes over all ranks
     ctx->global_n = ctx->n;
     if (ctx->n_ranks > 1) {

@@ -146,9 +146,10 @@ struct Context {
     int64_t trace = 0;           // 1: kernels log (tag, globaltimer) events into d_trace
     unsigned long long *d_trace = nullptr;
     int64_t ghost_p = 1;
-    std::vector<label> h_send_idxs;
-    label *d_push_ptr = nullptr, *d_push_ent = nullptr;
-    int push_grid = 0;
+    double **d_push_dst = nullptr;   // [n_send] slot 2 of the neighbour's window, per send entry
+    int64_t fused_pcg = 2;       // CG loop as one persistent cooperative kernel (pcg_fused.cu): 0 off, 1 on,
+                                 // 2 auto = on for small systems, where launch latencies dominate
+    unsigned int *d_bar = nullptr;   // its grid barrier: arrivals, generation
     size_t work_len = 0;
     // ghosted CSR (multi-GPU, halo-fused SpMV): every row = its local entries followed by
     // its non-local ones, whose columns are n + index into the receive window
@@ -304,7 +305,10 @@ int l2_keep_level(const Context *ctx);
 bool fused_halo_ok(const Context *ctx);
 int pack_stores(Context *ctx, const double *x, bool guard_done);
 int push_boundary(Context *ctx, const double *v);
-int ensure_push_lists(Context *ctx, int grid, int threads);
+bool pcg_fused_ok(const Context *ctx);
+int pcg_fused_run(Context *ctx, double *r0, double *r1, double *z, double *p0, double *p1,
+                  double *q, int64_t max_iter);
+unsigned long long spmv_l2_policy(Context *ctx);
 
 // solver.cu ----------------------------------------------------------------------
 int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res);

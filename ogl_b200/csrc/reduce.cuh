@@ -10,6 +10,8 @@
 // (comm.cu) and a one-thread kernel runs the same epilogue.
 #pragma once
 
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace ogl {
@@ -77,12 +79,12 @@ __device__ __forceinline__ bool criterion_check(SolveState *s, double norm1,
 // is needed per iteration, so a chunk of iterations replays as one CUDA graph.
 constexpr int kMaxPeers = 8;       // ranks per NVSwitch domain
 constexpr int kMaxTargets = 32;    // neighbour ranks of one rank
-constexpr int kSlot = kMaxReduce + 1;   // payload + stamp
+constexpr int kSlot = 2 * kMaxReduce;   // 8-byte words per source rank: (low half | seq), (high half | seq) per value
 constexpr long long kSpinCycles = 6000000000LL;   // ~3 s: fail loudly instead of hanging
 
 struct CommDev {
     int rank, n_ranks, n_targets, pad;
-    // all-reduce mailboxes: mbox[r] = rank r's mailbox base, [2][n_ranks][kSlot] doubles
+    // all-reduce mailboxes: mbox[r] = rank r's mailbox base, [2][n_ranks][kSlot] 8-byte words
     double *mbox[kMaxPeers];
     unsigned long long ar_seq;          // device-side sequence counters
     unsigned long long halo_seq;
@@ -234,45 +236,100 @@ __device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long lon
 // spin until *p >= want; false on timeout
 __device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long want)
 {
+    // relaxed polls (an acquire load per poll would invalidate the SM's L1 each time),
+    // one acquire fence once the flag is up
     const long long t0 = clock64();
-    while (ld_flag(p) < want) {
+    unsigned long long v;
+    while (true) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= want) break;
         if (clock64() - t0 > kSpinCycles) return false;
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
     return true;
+}
+
+// A double that validates itself: two 8-byte words, each 32 payload bits under a
+// 32-bit sequence stamp, written with one 16-byte store.  The reader polls until
+// both words carry the stamp it expects -- no flag, no fence, one NVLink traversal.
+__device__ __forceinline__ void push_stamped(unsigned long long *dst, double v, unsigned long long stamp)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long lo = (bits & 0xffffffffull) | stamp, hi = (bits >> 32) | stamp;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+// false on timeout (t0: clock64() when the caller started waiting)
+__device__ __forceinline__ bool pull_stamped(const unsigned long long *src, unsigned long long stamp,
+                                             long long t0, double &v)
+{
+    unsigned long long lo, hi;
+    while (true) {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+        if ((lo & 0xffffffff00000000ull) == stamp && (hi & 0xffffffff00000000ull) == stamp) break;
+        if (clock64() - t0 > kSpinCycles) return false;
+    }
+    v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    return true;
+}
+// stamp of the all-reduce number `seq`
+__device__ __forceinline__ unsigned long long stamp_of(unsigned long long seq) { return (seq & 0xffffffffull) << 32; }
+__device__ __forceinline__ unsigned long long ld_ar_seq(const CommDev *c)
+{
+    unsigned long long q;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(q) : "l"(&c->ar_seq) : "memory");
+    return q;
 }
 
 // All-reduce (sum) of state->red[0..count) over the ranks through the peers'
 // mailboxes.  Called by ALL threads of ONE block per rank (the last block of a
-// reducing kernel); state->red must already hold the local sums.
+// reducing kernel); s->red must already hold the local sums (s may be a
+// shared-memory copy of the state).
+//
+// Low-latency protocol: every value travels as two self-validating 8-byte words
+// (32 payload bits | 32-bit sequence stamp), so a contribution is ONE NVLink
+// traversal -- no flag behind the data and hence no release fence that would
+// wait for the data to be acknowledged first.  The receiver polls the words
+// until both carry the current stamp.  Mailboxes are double-buffered by the
+// parity of the sequence number; a slot is overwritten every second all-reduce,
+// so a stale stamp can never match.  Sums are formed in rank order on every
+// rank: bit-identical results everywhere.  Boundary values pushed into peer
+// windows (CG ghost-p mode) use the same self-validating words, stamped with the
+// number of the all-reduce that follows them, so nothing here has to publish.
 __device__ __forceinline__ void p2p_allreduce(SolveState *s, int count, CommDev *c)
 {
     __shared__ unsigned long long seq_sh;
-    if (threadIdx.x == 0) seq_sh = ++c->ar_seq;
+    __shared__ double vals_sh[kMaxPeers][kMaxReduce];
+    if (threadIdx.x == 0) {
+        const unsigned long long q = ld_ar_seq(c) + 1;
+        c->ar_seq = q;
+        seq_sh = q;
+    }
     __syncthreads();
     const unsigned long long seq = seq_sh;
+    const unsigned long long stamp = stamp_of(seq);
     const int parity = (int)(seq & 1ull);
     const int t = threadIdx.x;
+    const int nw = count > 0 ? count : 1;   // count 0: pure rendezvous
     if (t < c->n_ranks) {
         // my partial sums -> slot[my rank] of rank t's mailbox
-        double *box = c->mbox[t] + ((size_t)(parity * c->n_ranks + c->rank)) * kSlot;
-        for (int j = 0; j < count; ++j)
-            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(box + j), "d"(s->red[j]) : "memory");
-        st_flag(reinterpret_cast<unsigned long long *>(box + kMaxReduce), seq);
-        // wait for rank t's contribution in my own mailbox
-        const double *mine = c->mbox[c->rank] + ((size_t)(parity * c->n_ranks + t)) * kSlot;
-        if (!wait_flag(reinterpret_cast<const unsigned long long *>(mine + kMaxReduce), seq))
-            s->comm_error = 1;
+        unsigned long long *box = reinterpret_cast<unsigned long long *>(c->mbox[t]) +
+                                  ((size_t)(parity * c->n_ranks + c->rank)) * kSlot;
+        for (int j = 0; j < nw; ++j) push_stamped(box + 2 * j, s->red[j], stamp);
+        // rank t's contribution in my own mailbox
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(c->mbox[c->rank]) +
+                                         ((size_t)(parity * c->n_ranks + t)) * kSlot;
+        const long long t0 = clock64();
+        for (int j = 0; j < nw; ++j) {
+            double v = 0.0;
+            if (!pull_stamped(mine + 2 * j, stamp, t0, v)) s->comm_error = 1;
+            vals_sh[t][j] = v;
+        }
     }
     __syncthreads();
     if (t == 0) {
-        const double *base = c->mbox[c->rank] + (size_t)parity * c->n_ranks * kSlot;
         for (int j = 0; j < count; ++j) {
             double acc = 0.0;
-            for (int r = 0; r < c->n_ranks; ++r) {
-                double v;
-                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(base + (size_t)r * kSlot + j) : "memory");
-                acc += v;   // rank order: the same on every rank
-            }
+            for (int r = 0; r < c->n_ranks; ++r) acc += vals_sh[r][j];   // rank order: the same on every rank
             s->red[j] = acc;
         }
         if (s->comm_error) s->done = 1;
@@ -283,6 +340,18 @@ __device__ __forceinline__ void p2p_allreduce(SolveState *s, int count, CommDev 
 // Grid-wide deterministic reduction + optional inline epilogue.
 // All threads of all blocks call this exactly once per kernel.
 // red_base: first slot of state->red the sums go to.
+//
+// The last block to arrive (one acq_rel ticket per block: release of the
+// block's partials and acquire of everybody else's in one operation) adds the
+// partials in block order and then does ALL the scalar work -- all-reduce over
+// the ranks, Krylov coefficients, stopping criterion -- on a shared-memory copy
+// of the SolveState, written back in one coalesced pass.  One thread chasing
+// the state's fields through L2 one dependent load at a time cost ~2 us per
+// reduction on the device timeline (tools/trace_iter.py).
+constexpr int kStateWords = (int)(sizeof(SolveState) / sizeof(double));
+static_assert(sizeof(SolveState) % sizeof(double) == 0, "SolveState is copied in 8-byte words");
+constexpr int kCommErrWord = (int)(offsetof(SolveState, comm_error) / sizeof(double));
+
 template <int NRED>
 __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
                                             unsigned int *ticket, SolveState *state,
@@ -290,19 +359,24 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
                                             const EpiArgs &ea, bool accumulate = false)
 {
     __shared__ double sm[NRED * 32];
+    __shared__ double st_sh[kStateWords];
     __shared__ bool is_last;
     block_sum<NRED>(v, sm);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int j = 0; j < NRED; ++j) partials[(size_t)blockIdx.x * NRED + j] = v[j];
-        __threadfence();
-        const unsigned int t = atomicAdd(ticket, 1u);
+        unsigned int t;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(t) : "l"(ticket), "r"(1u) : "memory");
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return;
     if (threadIdx.x == 0) trace_event(ea, 1);   // last CTA of the grid has arrived
-    __threadfence();
+    for (int w = threadIdx.x; w < kStateWords; w += blockDim.x) {
+        double d;
+        asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(d) : "l"(reinterpret_cast<const double *>(state) + w) : "memory");
+        st_sh[w] = d;
+    }
     double acc[NRED];
 #pragma unroll
     for (int j = 0; j < NRED; ++j) acc[j] = 0.0;
@@ -312,14 +386,15 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
         for (int j = 0; j < NRED; ++j)
             acc[j] += __ldcg(&partials[(size_t)b * NRED + j]);
     }
-    __syncthreads();   // sm reuse
+    __syncthreads();   // sm reuse; st_sh complete
     block_sum<NRED>(acc, sm);
+    SolveState *s = reinterpret_cast<SolveState *>(st_sh);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int j = 0; j < NRED; ++j) {
             // accumulate: corrections of the non-local block on top of the
             // local kernel's sums (multi-rank SpMV with fused reductions)
-            state->red[red_base + j] = accumulate ? state->red[red_base + j] + acc[j] : acc[j];
+            s->red[red_base + j] = accumulate ? s->red[red_base + j] + acc[j] : acc[j];
         }
         *ticket = 0u;
         trace_event(ea, 2);   // local sums done
@@ -327,15 +402,21 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
     const bool ar = ea.comm != nullptr && ea.ar_count > 0;   // block-uniform
     if (ar && !ea.ar_after_epi) {
         __syncthreads();
-        p2p_allreduce(state, ea.ar_count, ea.comm);
+        p2p_allreduce(s, ea.ar_count, ea.comm);
         if (threadIdx.x == 0) trace_event(ea, 3);   // all-reduced
     }
-    if (threadIdx.x == 0 && inline_epi && epi != EPI_NONE) run_epilogue(epi, state, ea);
+    if (threadIdx.x == 0 && inline_epi && epi != EPI_NONE) run_epilogue(epi, s, ea);
     if (threadIdx.x == 0) trace_event(ea, 4);   // epilogue done
     if (ar && ea.ar_after_epi) {
         __syncthreads();
-        p2p_allreduce(state, ea.ar_count, ea.comm);
+        p2p_allreduce(s, ea.ar_count, ea.comm);
     }
+    __syncthreads();
+    // write the state back; the comm_error word only when it was raised here
+    // (waiting CTAs of a halo kernel may be raising it in global memory)
+    for (int w = threadIdx.x; w < kStateWords; w += blockDim.x)
+        if (w != kCommErrWord) reinterpret_cast<double *>(state)[w] = st_sh[w];
+    if (threadIdx.x == 0 && s->comm_error) state->comm_error = 1;
 }
 
 }  // namespace ogl

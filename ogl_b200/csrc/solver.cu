@@ -41,7 +41,7 @@ struct VecK {
     const label *send_idx;   // fused halo pack (multi-GPU peer-memory path)
     label n_send;
     int pack;                // k_cg_p: 1 store boundary p', 2 update ghost p; k_cg_xr: 1 push boundary z
-    const label *push_ptr, *push_ent;   // k_cg_xr: send entries owned by each CTA
+    double *const *push_dst;   // k_cg_xr: destination of every send entry (slot 2 of the peer windows)
 };
 
 #define GRID_STRIDE(i, n)                                                             \
@@ -120,15 +120,18 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
     const bool p_is_z = a.state->flag_p_is_z != 0;
     const double t = a.state->coef_p;
     if (a.pack == 2) {
-        // ghost-p mode: the neighbours pushed their boundary z into slot 2 of my
-        // window (k_cg_xr / push_boundary), published by the all-reduce that gave
-        // rho; the ghost entries of p get the same update as the neighbours' own
-        // cells -- same operands, same operations, same bits.
+        // ghost-p mode: the neighbours pushed their boundary z into slot 2 of my window
+        // (k_cg_xr / push_boundary) as self-validating words stamped with the number of the
+        // all-reduce that gave rho; the ghost entries of p get the same update as the
+        // neighbours' own cells -- same operands, same operations, same bits.
         const CommDev *c = a.ea.comm;
-        const double *zg = c->my_recv + 2 * (size_t)c->my_recv_stride;
+        const unsigned long long *zg =
+            reinterpret_cast<const unsigned long long *>(c->my_recv + 2 * (size_t)c->my_recv_stride);
+        const unsigned long long stamp = stamp_of(ld_ar_seq(c));
+        const long long t0 = clock64();
         GRID_STRIDE(k, a.n_send) {
-            double z;
-            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(z) : "l"(zg + k) : "memory");
+            double z = 0.0;
+            if (!pull_stamped(zg + 2 * k, stamp, t0, z)) a.state->comm_error = 1;
             a.out0[a.n + k] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.in1[a.n + k]));
         }
     } else if (a.pack) {
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
 }
 
 // cg::step_2 + preconditioner + <r,z> + |r|_1 (+ criterion on one rank)
-//   in0 = p, in1 = q, in2 = inv_diag ; out0 = x, out1 = r, out2 = z
+//   in0 = p, in1 = q, in2 = inv_diag, in3 = r ; out0 = x, out1 = r' (the other r buffer), out2 = z
 template <int PK>
 __device__ __forceinline__ void cg_xr_elem(bool upd, double t, double &x, double &r, double p,
                                            double q, double d, double &z, double (&red)[2])
@@ -201,34 +204,30 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
     const double t = a.state->coef_x;
     double red[2] = {0.0, 0.0};
     if (a.pack && PK != 2) {
-        // ghost-p mode: the new z (r when unpreconditioned) of the boundary cells THIS CTA
-        // owns goes into slot 2 of the neighbours' windows first, so the NVLink stores
-        // drain while the main loop runs; the all-reduce of rho below publishes them.
-        const CommDev *c = a.ea.comm;
-        const label j1 = a.push_ptr[blockIdx.x + 1];
-        for (label j = a.push_ptr[blockIdx.x] + threadIdx.x; j < j1; j += blockDim.x) {
-            const label k = a.push_ent[j];
+        // ghost-p mode: the new z (r when unpreconditioned) of the boundary cells goes into
+        // slot 2 of the neighbours' windows first -- r is read from the OLD buffer, so any
+        // CTA may do this without a race -- and the NVLink stores drain while the main loop
+        // runs.  Every value carries the number of the all-reduce this kernel ends with.
+        const unsigned long long stamp = stamp_of(ld_ar_seq(a.ea.comm) + 1);
+        GRID_STRIDE(k, a.n_send) {
             const label cell = a.send_idx[k];
-            double r = a.out1[cell];
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.push_dst[k]);
+            double r = a.in3[cell];
             if (upd) r = __dsub_rn(r, __dmul_rn(t, a.in1[cell]));
-            const double v = PK == 1 ? __dmul_rn(r, a.in2[cell]) : r;
-            int tg = 0;
-            while (k >= c->send_offs[tg + 1]) ++tg;
-            double *dst = c->peer_recv[tg] + 2 * (size_t)c->peer_recv_stride[tg] + (k - c->send_offs[tg]);
-            *dst = v;
+            push_stamped(dst, PK == 1 ? __dmul_rn(r, a.in2[cell]) : r, stamp);
         }
-        __syncthreads();   // nobody overwrites r before every push of this CTA has read it
     }
     const double2 *__restrict__ p2 = reinterpret_cast<const double2 *>(a.in0);
     const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(a.in1);
     const double2 *__restrict__ d2 = reinterpret_cast<const double2 *>(a.in2);
     double2 *__restrict__ x2 = reinterpret_cast<double2 *>(a.out0);
+    const double2 *__restrict__ ro2 = reinterpret_cast<const double2 *>(a.in3);
     double2 *__restrict__ r2 = reinterpret_cast<double2 *>(a.out1);
     double2 *__restrict__ z2 = reinterpret_cast<double2 *>(a.out2);
     const int64_t n2 = a.n >> 1;
 #pragma unroll 2
     GRID_STRIDE(i, n2) {
-        double2 r = r2[i];
+        double2 r = ro2[i];
         double2 x = make_double2(0.0, 0.0), p = x, q = x, d = x, z = x;
         if (upd) {
             x = x2[i];
@@ -238,26 +237,17 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
         if (PK == 1) d = d2[i];
         cg_xr_elem<PK>(upd, t, x.x, r.x, p.x, q.x, d.x, z.x, red);
         cg_xr_elem<PK>(upd, t, x.y, r.y, p.y, q.y, d.y, z.y, red);
-        if (upd) {
-            x2[i] = x;
-            r2[i] = r;
-        }
+        if (upd) x2[i] = x;
+        r2[i] = r;
         if (PK == 1) z2[i] = z;
     }
     if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = a.n - 1;
-        double x = a.out0[i], r = a.out1[i], z = 0.0;
+        double x = a.out0[i], r = a.in3[i], z = 0.0;
         cg_xr_elem<PK>(upd, t, x, r, a.in0[i], a.in1[i], PK == 1 ? a.in2[i] : 0.0, z, red);
-        if (upd) {
-            a.out0[i] = x;
-            a.out1[i] = r;
-        }
+        if (upd) a.out0[i] = x;
+        a.out1[i] = r;
         if (PK == 1) a.out2[i] = z;
-    }
-    if (a.pack && PK != 2) {
-        // system-scope fence (cumulative over this CTA's pushes) ahead of the ticket
-        __syncthreads();
-        if (threadIdx.x == 0) __threadfence_system();
     }
     grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
 }
@@ -475,11 +465,11 @@ static bool ghost_p_mode(const Context *ctx)
     return ctx->ghost_p != 0 && ctx->n_ranks > 1 && fused_halo_ok(ctx) && pk_of(ctx) != 2;
 }
 
-static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old, double *p,
-                        double *q)
+static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z, const double *p_old,
+                        double *p, double *q)
 {
     const int pk = pk_of(ctx);
-    const double *zz = pk == 0 ? r : z;
+    const double *zz = pk == 0 ? r_old : z;   // the residual this iteration starts from
     const bool ghost = ghost_p_mode(ctx);
     const bool pack = !ghost && fused_halo_ok(ctx) && ctx->n_send > 0;
     {
@@ -518,6 +508,7 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
         a.in0 = p;
         a.in1 = q;
         a.in2 = ctx->d_inv_diag;
+        a.in3 = r_old;
         a.out0 = ctx->d_x;
         a.out1 = r;
         a.out2 = z;
@@ -526,8 +517,7 @@ static int cg_iteration(Context *ctx, double *r, double *z, const double *p_old,
             a.pack = 1;
             a.send_idx = ctx->d_send_idxs;
             a.n_send = ctx->n_send;
-            a.push_ptr = ctx->d_push_ptr;
-            a.push_ent = ctx->d_push_ent;
+            a.push_dst = ctx->d_push_dst;
         }
 #define LAUNCH_XR(PKV)                                                                             \
     do {                                                                                           \
@@ -747,16 +737,22 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
         OGL_TRY(solve_prologue(ctx, 0, r, z, nullptr, w, tmp, EPI_INIT_CHECK));
         OGL_CUDA(ctx, cudaMemsetAsync(pv, 0, sizeof(double) * ctx->work_len, st));
         OGL_CUDA(ctx, cudaMemsetAsync(pv2, 0, sizeof(double) * ctx->work_len, st));
-        if (ghost_p_mode(ctx)) {
-            OGL_TRY(ensure_push_lists(ctx, vec_grid(ctx), kT));
-            OGL_TRY(push_boundary(ctx, pk_of(ctx) == 0 ? r : z));   // boundary z0
+        const bool fused = pcg_fused_ok(ctx);
+        if (ghost_p_mode(ctx)) OGL_TRY(push_boundary(ctx, pk_of(ctx) == 0 ? r : z));   // boundary z0
+        double *r_alt;   // r is ping-ponged like p: the x/r-update writes the other buffer
+        OGL_TRY(get_work(ctx, 10, &r_alt));
+        if (fused) {
+            // the whole loop in one persistent kernel (pcg_fused.cu)
+            OGL_TRY(pcg_fused_run(ctx, r, r_alt, z, pv, pv2, q, p->max_iter));
+        } else {
+            int flip = 0;   // the p and r buffers alternate; a chunk holds an even number of iterations
+            OGL_TRY(run_chunks(ctx, OGL_SOLVER_CG, p->max_iter, [&]() {
+                double *p_old = flip ? pv2 : pv, *p_new = flip ? pv : pv2;
+                double *r_old = flip ? r_alt : r, *r_new = flip ? r : r_alt;
+                flip ^= 1;
+                return cg_iteration(ctx, r_old, r_new, z, p_old, p_new, q);
+            }));
         }
-        int flip = 0;   // the two p buffers alternate; a chunk holds an even number of iterations
-        OGL_TRY(run_chunks(ctx, OGL_SOLVER_CG, p->max_iter, [&]() {
-            double *p_old = flip ? pv2 : pv, *p_new = flip ? pv : pv2;
-            flip ^= 1;
-            return cg_iteration(ctx, r, z, p_old, p_new, q);
-        }));
     } else {
         double *rr, *v, *s, *t, *y;
         OGL_TRY(get_work(ctx, 4, &rr));

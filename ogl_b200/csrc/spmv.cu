@@ -846,7 +846,6 @@ EpiArgs make_epi_args(Context *ctx, int ar_count, bool ar_after_epi)
     return ea;
 }
 
-static unsigned long long l2_policy(Context *ctx);
 int spmv_setup(Context *ctx)
 {
     // largest slice any kRowsPerBlock-row CTA would have to park in shared memory
@@ -876,7 +875,7 @@ int spmv_setup(Context *ctx)
     if (vec_grid > max_grid) max_grid = vec_grid;
     if (ctx->blas1_blocks > max_grid) max_grid = ctx->blas1_blocks;
     OGL_TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)(max_grid + 1) * kMaxReduce));
-    (void)l2_policy(ctx);   // create the policy words outside any graph capture
+    (void)spmv_l2_policy(ctx);   // create the policy words outside any graph capture
     return OGL_OK;
 }
 
@@ -918,7 +917,7 @@ int l2_keep_level(const Context *ctx)
     return 0;
 }
 
-static unsigned long long l2_policy(Context *ctx)
+unsigned long long spmv_l2_policy(Context *ctx)
 {
     if (!ctx->l2_policies_ready) {
         unsigned long long *d = nullptr;
@@ -960,7 +959,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.n = ctx->n;
     k.n_row_blocks = 0;
     k.blocked = ctx->tile_blocked ? 1 : 0;
-    k.mat_policy = l2_policy(ctx);
+    k.mat_policy = spmv_l2_policy(ctx);
     k.alpha = sa.alpha;
     k.beta = sa.beta;
     k.dot_with = sa.dot_with;
