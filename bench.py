@@ -341,7 +341,8 @@ def run_gpu(args):
             "rows_per_gpu": n, "nnz_per_gpu": nnz, "halo_per_gpu": n_halo,
             "decomposition": list(procs_for(n_gpus)),
             "comm": ("none" if n_gpus == 1 else
-                     ("peer-memory windows over NVLink (P2P stores + in-kernel all-reduce)"
+                     ("peer-memory windows over NVLink (stamped P2P stores of the boundary z + in-kernel "
+                      "all-reduce, no halo handshake in the CG loop)"
                       if p2p_active else "NCCL send/recv + allreduce")),
             "iterations_per_solve": iters_res / args.steps,
             "l2": "working set ~%.0f MB vs 126 MB L2; 512 MB written between steps to flush L2; "
@@ -354,8 +355,8 @@ def run_gpu(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "kernel": "k_spmv_pipe<false,1,%s> (FP64 CSR SpMV + fused <p,q>)" % (
-                "true" if n_gpus > 1 else "false"),
+            "bound": "hbm", "kernel": "k_spmv_pipe<false,1,false> (FP64 CSR SpMV + fused <p,q>%s)" % (
+                "; ghosted CSR, all-reduce of <p,q> inside the launch" if n_gpus > 1 else ""),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic(args.n) if n_gpus == 1 else None, "peak_source": peak_src,
             "alg_bytes_per_launch": b_spmv, "us_per_launch": spmv_ms * 1e3,

@@ -233,6 +233,7 @@ static int p2p_setup(Context *ctx)
     };
     for (int q = 0; q < R; ++q) h.mbox[q] = reinterpret_cast<double *>(base_of(q) + all[q].off_mbox);
     for (int t = 0; t <= ctx->n_targets; ++t) h.send_offs[t] = ctx->send_offs[t];
+    std::vector<long long> peer_block_off((size_t)ctx->n_targets, 0);   // my block inside q's recv buffer
     for (int t = 0; t < ctx->n_targets; ++t) {
         const int q = ctx->target_ids[t];
         const Directory &dq = all[q];
@@ -247,6 +248,7 @@ static int p2p_setup(Context *ctx)
         // my values land in the neighbour's recv block reserved for me: same offset
         // as the neighbour's own send block towards me (blocked by ascending rank)
         h.peer_recv[t] = reinterpret_cast<double *>(base_of(q) + dq.off_recv) + dq.send_offs[u];
+        peer_block_off[(size_t)t] = dq.send_offs[u];
         h.peer_recv_stride[t] = dq.n_halo > 0 ? dq.n_halo : 1;
         h.peer_data_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_data_flag) + u;
         h.peer_ack_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_ack_flag) + u;
@@ -263,7 +265,10 @@ static int p2p_setup(Context *ctx)
         std::vector<double *> dst((size_t)ctx->n_send, nullptr);
         for (label t = 0; t < ctx->n_targets; ++t)
             for (label k = ctx->send_offs[t]; k < ctx->send_offs[t + 1]; ++k)
-                dst[(size_t)k] = h.peer_recv[t] + 2 * h.peer_recv_stride[t] + 2 * (size_t)(k - ctx->send_offs[t]);
+                // slot 2 holds 16 B per entry: my block starts at 2 * (its offset in q's buffer);
+                // peer_recv[t] already contains that offset once
+                dst[(size_t)k] = h.peer_recv[t] + 2 * h.peer_recv_stride[t] + peer_block_off[(size_t)t] +
+                                 2 * (size_t)(k - ctx->send_offs[t]);
         OGL_TRY(dev_alloc(ctx, &ctx->d_push_dst, (size_t)ctx->n_send));
         OGL_CUDA(ctx, cudaMemcpy(ctx->d_push_dst, dst.data(), sizeof(double *) * dst.size(),
                                  cudaMemcpyHostToDevice));
