@@ -117,7 +117,7 @@ struct EpiArgs {
 // one timeline event; called by single threads at a handful of points per launch
 __device__ __forceinline__ void trace_event(const EpiArgs &ea, int sub)
 {
-    if (!ea.trace) return;
+    if (!ea.trace || ea.trace_tag == 0) return;   // untagged launches (prologue, other solvers) stay silent
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     const unsigned long long i = atomicAdd(ea.trace, 1ull);

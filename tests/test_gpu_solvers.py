@@ -145,6 +145,7 @@ def test_graph_and_stream_paths_agree(ctx):
     s = cases.pressure_3d(24)[0]
     upload_system(ctx, s, partition=False)
     res = []
+    ctx.set_option("fused_pcg", 0)   # the three-kernel iteration: captured chunks vs plain launches
     for use_graph, chunk in ((1, 16), (0, 16), (1, 3), (0, 1)):
         ctx.set_option("use_graph", use_graph)
         ctx.set_option("chunk_iters", chunk)
@@ -153,8 +154,72 @@ def test_graph_and_stream_paths_agree(ctx):
         res.append((r.n_iterations, x.copy()))
     ctx.set_option("use_graph", 1)
     ctx.set_option("chunk_iters", 16)
+    ctx.set_option("fused_pcg", 2)
     for n_it, x in res[1:]:
         assert n_it == res[0][0] and np.array_equal(x, res[0][1])
+
+
+@pytest.mark.parametrize("precond", ["none", "BJ"])
+def test_fused_loop_and_three_kernel_iteration(ctx, oracle, precond):
+    """CG as one persistent cooperative kernel (pcg_fused.cu) and as three kernels per
+    iteration (solver.cu): both against the oracle, both run-to-run deterministic; they
+    differ only in how the partial sums are grouped."""
+    s = cases.pressure_3d(28)[0]
+    iters = {}
+    try:
+        for fused in (0, 1):
+            ctx.set_option("fused_pcg", fused)
+            r, o, x = check_against_oracle(ctx, oracle, s, "GKOCG", precond, tolerance=1e-9)
+            assert ctx.get_option("fused_pcg_active") == fused
+            ctx.vector_upload(L.OGL_VEC_X, s.psi)
+            r2, x2 = gpu_solve(ctx, "GKOCG", precond, tolerance=1e-9)
+            assert r2.n_iterations == r.n_iterations and np.array_equal(x, x2)
+            iters[fused] = r.n_iterations
+            # one launch for the whole loop vs three per iteration
+            if fused:
+                assert r.kernel_launches < 40
+            else:
+                assert r.kernel_launches >= 3 * r.n_iterations
+    finally:
+        ctx.set_option("fused_pcg", 2)
+    assert abs(iters[0] - iters[1]) <= ITER_TOL
+
+
+def test_fused_loop_respects_criterion_options(ctx, oracle):
+    s = cases.pressure_3d(20)[0]
+    ctx.set_option("fused_pcg", 1)
+    try:
+        # maxIter stop, minIter and evalFrequency go through the same device-side criterion
+        r, o, x = check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", tolerance=1e-30, max_iter=17)
+        assert r.criterion_calls == o.criterion_calls
+        check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", tolerance=1e-4, min_iter=30, frequency=4)
+    finally:
+        ctx.set_option("fused_pcg", 2)
+
+
+def test_device_timeline(ctx):
+    """option `trace`: the iteration kernels log (tag, globaltimer) events."""
+    s = cases.pressure_3d(24)[0]
+    upload_system(ctx, s, partition=False)
+    for fused in (0, 1):
+        ctx.set_option("fused_pcg", fused)
+        ctx.set_option("trace", 1)
+        ctx.vector_upload(L.OGL_VEC_X, s.psi)
+        r, x = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-9)
+        tags, times = ctx.trace_download()
+        ctx.set_option("trace", 0)
+        assert len(tags) >= 3 * r.n_iterations
+        assert set(np.unique(tags)) <= {10, 20, 21, 22, 23, 24, 30, 31, 32, 33, 34}
+        # per iteration: p-update start, SpMV start, x/r-update start
+        for tag in (10, 20, 30):
+            assert abs(int((tags == tag).sum()) - r.n_iterations) <= 20
+        order = np.argsort(times, kind="stable")
+        assert (np.diff(times[order]) >= 0).all() and times.max() > times.min()
+        # tracing must not change the arithmetic
+        ctx.vector_upload(L.OGL_VEC_X, s.psi)
+        r2, x2 = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-9)
+        assert r2.n_iterations == r.n_iterations and np.array_equal(x, x2)
+    ctx.set_option("fused_pcg", 2)
 
 
 def test_cg_with_every_spmv_kernel(ctx, oracle):

@@ -81,6 +81,21 @@ def test_spmv_properties_at_baseline_size(ctx):
     assert np.abs(ys[2] - ys[0]).max() <= 1e-14 * scale
 
 
+def test_l2_policy_of_the_matrix_stream_is_bit_exact(ctx, oracle):
+    """l2_keep_mb only changes the cache hints of the (column, value) loads."""
+    s = cases.pressure_3d(24)[0]
+    upload_system(ctx, s, partition=False)
+    x = np.random.default_rng(4).normal(size=s.n)
+    ys = []
+    for keep in (0, -1, 1):
+        ctx.set_option("l2_keep_mb", keep)
+        ys.append(ctx.spmv(x))
+    ctx.set_option("l2_keep_mb", 0)
+    assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2])
+    a = oracle.assemble(s)
+    assert np.array_equal(ys[0], oracle.dist_spmv([a], [x])[0])
+
+
 def test_spmv_bench_entry_point(ctx):
     s = cases.pressure_3d(32)[0]
     upload_system(ctx, s, partition=False)
