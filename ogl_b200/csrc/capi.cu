@@ -332,6 +332,11 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->fused_halo = value;
     } else if (k == "ghost_p") {
         ctx->ghost_p = value != 0;
+    } else if (k == "device_loop") {
+        ctx->device_loop = value != 0;
+    } else if (k == "loop_iters") {
+        if (value < 1 || value > 1024) return fail(ctx, OGL_ERR_INVALID, "loop_iters in [1,1024]");
+        ctx->loop_iters = value;
     } else if (k == "fused_pcg") {
         if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "fused_pcg in {0,1,2}");
         ctx->fused_pcg = value;
@@ -383,6 +388,9 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "l2_keep_mb") *value = ctx->l2_keep_mb;
     else if (k == "ghost_p") *value = ctx->ghost_p;
     else if (k == "fused_pcg") *value = ctx->fused_pcg;
+    else if (k == "device_loop") *value = ctx->device_loop;
+    else if (k == "loop_iters") *value = ctx->loop_iters;
+    else if (k == "device_loop_active") *value = ctx->graph_exec && ctx->graph_is_loop ? 1 : 0;
     else if (k == "fused_pcg_active") *value = pcg_fused_ok(ctx) ? 1 : 0;
     else if (k == "l2_keep_level") *value = l2_keep_level(ctx);
     else if (k == "comm_mode") *value = ctx->comm_mode;

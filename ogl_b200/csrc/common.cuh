@@ -202,6 +202,13 @@ struct Context {
     int graph_solver = -1;
     int64_t graph_sig = 0;
     int64_t graph_kernels = 0;   // kernels inside one replayed chunk
+    int64_t device_loop = 1;     // CG: chunk graph = body of a CUDA-graph WHILE node whose condition the
+                                 // criterion epilogue clears on the device (one launch per solve)
+    int64_t loop_iters = 16;     // iterations per loop body (even): ~3.2 us per body of loop overhead vs
+                                 // up to loop_iters-1 early-exit iterations after the criterion fired
+    int64_t loop_body_iters = 0; // > 0: a loop graph was launched by this solve
+    bool graph_is_loop = false;
+    unsigned long long cond_handle = 0;   // cudaGraphConditionalHandle while the loop body is captured
 
     int64_t launches = 0;
 

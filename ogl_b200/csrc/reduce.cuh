@@ -352,8 +352,10 @@ constexpr int kStateWords = (int)(sizeof(SolveState) / sizeof(double));
 static_assert(sizeof(SolveState) % sizeof(double) == 0, "SolveState is copied in 8-byte words");
 constexpr int kCommErrWord = (int)(offsetof(SolveState, comm_error) / sizeof(double));
 
+// Returns 0 in every block but the last one to arrive; there 1, or 2 when the
+// state says the solve is over (criterion fired / peer timeout) after the epilogue.
 template <int NRED>
-__device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
+__device__ __forceinline__ int grid_reduce(double (&v)[NRED], double *partials,
                                             unsigned int *ticket, SolveState *state,
                                             int red_base, int epi, bool inline_epi,
                                             const EpiArgs &ea, bool accumulate = false)
@@ -370,7 +372,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return 0;
     if (threadIdx.x == 0) trace_event(ea, 1);   // last CTA of the grid has arrived
     for (int w = threadIdx.x; w < kStateWords; w += blockDim.x) {
         double d;
@@ -417,6 +419,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NRED], double *partials,
     for (int w = threadIdx.x; w < kStateWords; w += blockDim.x)
         if (w != kCommErrWord) reinterpret_cast<double *>(state)[w] = st_sh[w];
     if (threadIdx.x == 0 && s->comm_error) state->comm_error = 1;
+    return s->done ? 2 : 1;
 }
 
 }  // namespace ogl

@@ -42,6 +42,7 @@ struct VecK {
     label n_send;
     int pack;                // k_cg_p: 1 store boundary p', 2 update ghost p; k_cg_xr: 1 push boundary z
     double *const *push_dst;   // k_cg_xr: destination of every send entry (slot 2 of the peer windows)
+    cudaGraphConditionalHandle cond;   // k_cg_xr inside a WHILE-node body: cleared when the solve is done
 };
 
 #define GRID_STRIDE(i, n)                                                             \
@@ -198,7 +199,11 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
 {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
-    if (a.guard_done && a.state->done) return;
+    if (a.guard_done && a.state->done) {
+        // (also reached when the criterion fired before the loop, or in the first half of a body)
+        if (a.cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
+        return;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(a.ea, 0);
     const bool upd = a.state->beta != 0.0;
     const double t = a.state->coef_x;
@@ -249,7 +254,9 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
         a.out1[i] = r;
         if (PK == 1) a.out2[i] = z;
     }
-    grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+    const int last = grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+    // device-side loop (CUDA-graph WHILE node): the criterion ends it
+    if (a.cond && last == 2 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
 }
 
 // bicgstab::step_1 + y = M^-1 p     in0 = r, in1 = v, in2 = inv_diag ; out0 = p, out1 = y
@@ -512,6 +519,7 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
         a.out0 = ctx->d_x;
         a.out1 = r;
         a.out2 = z;
+        a.cond = ctx->cond_handle;
         a.ea.trace_tag = 30;
         if (ghost) {
             a.pack = 1;
@@ -640,26 +648,55 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
 {
     // an even number of iterations per chunk: CG alternates two p buffers and a
     // replayed chunk must end where it started
-    int chunk = (int)(ctx->chunk_iters < 1 ? 1 : ctx->chunk_iters);
-    chunk += chunk & 1;
     cudaStream_t st = ctx->stream;
     const bool graph_ok = ctx->use_graph && (ctx->n_ranks == 1 || use_p2p(ctx)) &&
                           ctx->profile_stride == 0;
-    const int64_t sig = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^ (ctx->use_pdl << 60) ^
-                        ((int64_t)chunk << 32) ^ (int64_t)ctx->n ^ (ctx->spmv_variant << 56);
+    // CG with an in-kernel criterion (no block-Jacobi apply kernel): the chunk becomes the body
+    // of a WHILE node; k_cg_xr clears the condition when the criterion fires, so a solve is one
+    // graph launch with no early-exit launches behind the last iteration and no host polling
+    const bool loop = graph_ok && ctx->device_loop && solver == OGL_SOLVER_CG && pk_of(ctx) != 2;
+    int chunk = (int)(loop ? ctx->loop_iters : ctx->chunk_iters);
+    if (chunk < 1) chunk = 1;
+    chunk += chunk & 1;
+    const int64_t sig0 = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^ (ctx->use_pdl << 60) ^
+                         ((int64_t)chunk << 32) ^ (int64_t)ctx->n ^ (ctx->spmv_variant << 56);
+    const int64_t sig = sig0 ^ ((int64_t)(loop ? 1 : 0) << 62);
     if (graph_ok && (!ctx->graph_exec || ctx->graph_sig != sig)) {
         if (ctx->graph_exec) {
             cudaGraphExecDestroy(ctx->graph_exec);
             ctx->graph_exec = nullptr;
         }
-        cudaGraph_t graph = nullptr;
+        cudaGraph_t graph = nullptr, body = nullptr;
         const int64_t launches_before = ctx->launches;
-        OGL_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        if (loop) {
+            OGL_CUDA(ctx, cudaGraphCreate(&graph, 0));
+            cudaGraphConditionalHandle handle;
+            cudaError_t ce = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault);
+            cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = handle;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            if (ce == cudaSuccess) ce = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
+            if (ce != cudaSuccess) {
+                cudaGraphDestroy(graph);
+                return fail(ctx, OGL_ERR_CUDA, std::string("conditional graph node: ") + cudaGetErrorString(ce));
+            }
+            body = np.conditional.phGraph_out[0];
+            ctx->cond_handle = handle;
+            OGL_CUDA(ctx, cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        } else {
+            OGL_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        }
         int rc = OGL_OK;
         ctx->capturing = true;
         for (int i = 0; i < chunk && rc == OGL_OK; ++i) rc = enqueue();
         ctx->capturing = false;
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        ctx->cond_handle = 0;
+        cudaGraph_t captured = nullptr;
+        cudaError_t e = cudaStreamEndCapture(st, &captured);
+        if (!loop) graph = captured;
         const int64_t kernels_per_chunk = ctx->launches - launches_before;
         ctx->launches = launches_before;   // captured, not executed
         if (rc != OGL_OK) {
@@ -672,6 +709,13 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
         OGL_CUDA(ctx, e);
         ctx->graph_sig = sig;
         ctx->graph_kernels = kernels_per_chunk;
+        ctx->graph_is_loop = loop;
+    }
+    if (graph_ok && ctx->graph_is_loop) {
+        // one launch: the loop ends on the device; solve() reads the state back afterwards
+        OGL_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+        ctx->loop_body_iters = chunk;   // solve() counts the launches once it has the final state
+        return OGL_OK;
     }
     cudaEvent_t ev[2] = {ctx->ev_poll[0], ctx->ev_poll[1]};
     int64_t enqueued = 0;
@@ -789,6 +833,14 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     res->solve_us = ms * 1e3;
     // the L1 norm rides inside the fused update kernel: no separate evaluation
     res->resnorm_us = 0.0;
+    if (ctx->loop_body_iters > 0) {
+        // device-side loop: whole bodies ran, up to and including the one the criterion fired in
+        const int64_t calls = hs.iter > 0 ? hs.iter - 1 : 0;   // minus the prologue's criterion call
+        int64_t bodies = (calls + ctx->loop_body_iters - 1) / ctx->loop_body_iters;
+        if (bodies < 1) bodies = 1;
+        ctx->launches += bodies * ctx->graph_kernels;
+        ctx->loop_body_iters = 0;
+    }
     res->kernel_launches = ctx->launches - launches0;
     if (ctx->profile_used >= 2) {
         double total_ms = 0.0;

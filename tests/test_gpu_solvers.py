@@ -159,6 +159,36 @@ def test_graph_and_stream_paths_agree(ctx):
         assert n_it == res[0][0] and np.array_equal(x, res[0][1])
 
 
+def test_device_side_loop_graph(ctx, oracle):
+    """Three kernels per iteration as the body of a CUDA-graph WHILE node (the criterion
+    epilogue clears the condition) vs chunks replayed under host polling: identical results;
+    also when the criterion fires before the first iteration and at maxIter."""
+    s = cases.pressure_3d(24)[0]
+    ctx.set_option("fused_pcg", 0)
+    try:
+        res = {}
+        for loop, body in ((0, 4), (1, 2), (1, 4), (1, 16)):
+            ctx.set_option("device_loop", loop)
+            ctx.set_option("loop_iters", body)
+            r, o, x = check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", tolerance=1e-9)
+            assert ctx.get_option("device_loop_active") == loop
+            res[(loop, body)] = (r.n_iterations, x.copy(), r.kernel_launches)
+            r9, o9, _ = check_against_oracle(ctx, oracle, s, "GKOCG", "BJ", tolerance=1e-30, max_iter=9)
+            assert r9.criterion_calls == o9.criterion_calls
+            # already converged: the loop body must run once and stop
+            ctx.vector_upload(L.OGL_VEC_X, x)
+            r0, _ = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-6)
+            assert r0.n_iterations <= 1
+        ref = res[(0, 4)]
+        for key, (n_it, x, launches) in res.items():
+            assert n_it == ref[0] and np.array_equal(x, ref[1]), key
+            assert launches >= 3 * n_it
+    finally:
+        ctx.set_option("device_loop", 1)
+        ctx.set_option("loop_iters", 16)
+        ctx.set_option("fused_pcg", 2)
+
+
 @pytest.mark.parametrize("precond", ["none", "BJ"])
 def test_fused_loop_and_three_kernel_iteration(ctx, oracle, precond):
     """CG as one persistent cooperative kernel (pcg_fused.cu) and as three kernels per
