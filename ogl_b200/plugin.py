@@ -129,7 +129,7 @@ class GKOlduBaseSolver:
                               nccl_id=self.pstream.nccl_id)
         self.ctx: Context = db[key]
         for opt in ("spmv_variant", "chunk_iters", "use_graph", "comm_mode", "fused_halo", "ghost_p",
-                    "fused_pcg", "l2_keep_mb"):
+                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb"):
             if opt in controls:
                 self.ctx.set_option(opt, int(controls[opt]))
         # preconditioner keyword: word or sub-dict (Preconditioner.H:363-382)
