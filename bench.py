@@ -154,6 +154,11 @@ def cpu_pcg_sample(system, threads: int, iters: int):
     return done / r.seconds, r.seconds, done
 
 
+def workload_text(n: int) -> str:
+    return (f"{n}^3 cells per GPU, 3-D lid-driven-cavity pressure system, GKOCG+BJ(maxBlockSize 1) FP64, "
+            "tolerance 1e-6, relTol 0, x0=0 (BASELINE configs[1])")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -174,8 +179,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.n}^3 pressure GKOCG+BJ FP64 (BASELINE configs[1])",
-                   "rows": s.n, "nnz": s.n + 2 * s.n_faces},
+        "config": {"workload": workload_text(args.n),
+                   "rows_per_gpu": s.n, "nnz_per_gpu": s.n + 2 * s.n_faces,
+                   "value_definition": "iterations x n_gpus / s (1M-cell block iterations, whole job): the "
+                                       "host cores work through the blocks one after the other, so the "
+                                       "figure does not depend on n_gpus"},
         "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "port",
                          "sample": f"{sample_iters} PCG iterations per step of the oracle port "
                                    f"(OpenMP, {cores} threads) on the full {args.n}^3 system; the "
@@ -335,9 +343,7 @@ def run_gpu(args):
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"{args.n}^3 cells per GPU, 3-D lid-driven-cavity pressure system, "
-                        "GKOCG+BJ(maxBlockSize 1) FP64, tolerance 1e-6, relTol 0, x0=0 "
-                        "(BASELINE configs[1])",
+            "workload": workload_text(args.n),
             "rows_per_gpu": n, "nnz_per_gpu": nnz, "halo_per_gpu": n_halo,
             "decomposition": list(procs_for(n_gpus)),
             "comm": ("none" if n_gpus == 1 else
