@@ -9,11 +9,13 @@
 //
 // Two data paths:
 //   comm_mode 2 (default when every peer is reachable over NVLink P2P):
-//     peer-memory windows (reduce.cuh).  The pack kernel stores boundary values
-//     straight into the neighbours' receive buffers; reducing kernels all-reduce
-//     their partial sums through the peers' mailboxes in their own last block.
-//     No NCCL call, no extra launch per iteration; the stores travel while the
-//     local-block SpMV runs.
+//     peer-memory windows (reduce.cuh).  Reducing kernels all-reduce their
+//     partial sums through the peers' mailboxes in their own last block
+//     (self-validating stamped words).  Boundary values: the CG loop pushes the
+//     boundary z from its x/r-update kernel and keeps ghost entries of p itself
+//     (solver.cu "ghost p"); every other distributed SpMV stores x[send_idxs]
+//     into the neighbours' receive buffers and shakes hands with flags.
+//     No NCCL call, no extra launch per iteration.
 //   comm_mode 1: NCCL -- grouped ncclSend/ncclRecv on a side stream overlapped
 //     with the local SpMV, ncclAllReduce of the packed scalars in place in the
 //     device-resident SolveState, then a one-thread epilogue kernel.

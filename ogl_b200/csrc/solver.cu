@@ -5,14 +5,17 @@
 // Operation order follows Ginkgo's core/solver/{cg,bicgstab}.cpp; each vector
 // update is fused with the preconditioner apply (scalar Jacobi / none) and with
 // the reductions the next step needs, every coefficient stays on the device
-// (SolveState), and the host only polls a `done` flag once per chunk of
-// iterations -- no per-iteration D2H + sync as in StoppingCriterion.C:95-97.
+// (SolveState).  CG runs as the body of a CUDA-graph WHILE node that the
+// criterion epilogue ends on the device (run_chunks); the other solvers replay
+// chunk graphs while the host polls a `done` flag -- never a per-iteration
+// D2H + sync as in StoppingCriterion.C:95-97.
 //
-// PCG iteration, scalar Jacobi, one rank (3 launches, ~192 n bytes for 7-pt):
-//   k_cg_p    p = z + (rho/prev_rho) p                                  24 n
-//   spmv      q = A p, beta = <p,q>, alpha = rho/beta       12 nnz + 4 n + 16 n (+8 n p)
-//   k_cg_xr   x += alpha p; r -= alpha q; z = r/diag;
-//             rho = <r,z>; |r|_1; criterion                             64 n
+// PCG iteration, scalar Jacobi (3 launches on 1..8 GPUs, ~192 n bytes for 7-pt):
+//   k_cg_p    p' = z + (rho/prev_rho) p (other buffer; + ghost entries)  24 n
+//   spmv      q = A p', beta = <p',q>, alpha = rho/beta     12 nnz + 4 n + 16 n (+8 n p)
+//   k_cg_xr   x += alpha p'; r' = r - alpha q (other buffer); z = r'/diag;
+//             rho = <r',z>; |r'|_1; criterion (+ push of the boundary z)  64 n
+// Small systems: the same loop as one persistent kernel (pcg_fused.cu).
 #include <cmath>
 #include <cstring>
 

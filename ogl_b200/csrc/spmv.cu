@@ -20,6 +20,16 @@
 //               sums + shuffle reduction (not bit-identical, deterministic).
 //   4 "tma"     persistent CTAs, slices staged by cp.async.bulk (TMA) into a
 //               multi-stage shared-memory ring guarded by mbarriers.
+//   5 "warp"    warp x 32-row tiles, no CTA barrier.
+//   6 "pipe"    (default for short rows) variant 1 software-pipelined: the next
+//               tile's (column, value) loads are in flight while this tile's
+//               products are gathered, parked and added.
+//
+// Several GPUs: the same kernels run over the ghosted CSR (assembly.cu:
+// build_ghosted; every row = local entries, then its non-local entries with
+// column n + halo slot), either on x = [p | ghost p] kept current by the CG
+// loop itself (ghost_x, no handshake) or, HALO, reading the ghost operands from
+// the receive window after a flag handshake with the neighbours.
 //
 // Fused reductions (NRED): red[0] = <dot_with, y>, red[1] = <y, y>; reduced
 // deterministically (reduce.cuh) and, on one rank, followed in the same launch
