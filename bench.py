@@ -316,6 +316,7 @@ def run_gpu(args):
         ctx.close()
         return 0
 
+    variant = ctx.get_option("spmv_variant_in_use")
     peak, peak_src = measured_peak()
     b_spmv = alg_bytes_spmv(n, nnz, n_halo)
     b_pcg = alg_bytes_pcg(n, nnz, n_halo)
@@ -361,10 +362,12 @@ def run_gpu(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "kernel": "k_spmv_pipe<false,1,false> (FP64 CSR SpMV + fused <p,q>%s)" % (
-                "; ghosted CSR, all-reduce of <p,q> inside the launch" if n_gpus > 1 else ""),
+            "bound": "hbm", "kernel": ("k_spmv_ell<false,1> (FP64 ELL SpMV + fused <p,q>)" if variant == 7 else
+                                       "k_spmv_pipe<false,1,false> (FP64 CSR SpMV + fused <p,q>%s)" % (
+                "; ghosted CSR, all-reduce of <p,q> inside the launch" if n_gpus > 1 else "")),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic(args.n) if n_gpus == 1 else None, "peak_source": peak_src,
+            # the committed ncu capture is of the CSR kernel
+            "traffic": ncu_traffic(args.n) if n_gpus == 1 and variant != 7 else None, "peak_source": peak_src,
             "alg_bytes_per_launch": b_spmv, "us_per_launch": spmv_ms * 1e3,
             "us_per_launch_how": ("CUDA events around every 4th SpMV launch inside an extra "
                                   "solve of the same system (%d samples)" % r_prof.spmv_samples),

@@ -368,6 +368,8 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->nnz = nnz;
     ctx->max_row_len = max_len;
     ctx->have_pattern = true;
+    ctx->ell_ready = false;
+    ctx->ell_width = 0;
     ctx->have_values = false;
     ctx->have_precond = false;
     ctx->have_b = ctx->have_x = false;
@@ -587,6 +589,7 @@ int values_update(Context *ctx, const double *diag, const double *upper,
     }
     OGL_CUDA(ctx, cudaGetLastError());
     ctx->have_values = true;
+    ctx->ell_ready = false;      // the ELL copy (if in use) is rebuilt from the new values on demand
     ctx->have_precond = false;   // regenerated every solve (caching 0, Preconditioner.H:416-422)
     return OGL_OK;
 }

@@ -128,7 +128,8 @@ static void destroy(Context *c)
                     c->d_inv_diag,   c->d_block_ptrs, c->d_row_block,  c->d_block_offs,
                     c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
                     c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
-                    c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar};
+                    c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar,        c->d_ell_cols,
+                    c->d_ell_vals};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)
@@ -313,7 +314,7 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     if (!key) return fail(ctx, OGL_ERR_INVALID, "null option key");
     const std::string k(key);
     if (k == "spmv_variant") {
-        if (value < 0 || value > 6) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,6]");
+        if (value < 0 || value > 7) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,7]");
         ctx->spmv_variant = value;
     } else if (k == "chunk_iters") {
         if (value < 1) return fail(ctx, OGL_ERR_INVALID, "chunk_iters >= 1");
@@ -332,6 +333,8 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->fused_halo = value;
     } else if (k == "ghost_p") {
         ctx->ghost_p = value != 0;
+    } else if (k == "ell_auto") {
+        ctx->ell_auto = value != 0;
     } else if (k == "device_loop") {
         ctx->device_loop = value != 0;
     } else if (k == "loop_iters") {
@@ -389,6 +392,8 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "ghost_p") *value = ctx->ghost_p;
     else if (k == "fused_pcg") *value = ctx->fused_pcg;
     else if (k == "device_loop") *value = ctx->device_loop;
+    else if (k == "ell_auto") *value = ctx->ell_auto;
+    else if (k == "spmv_variant_in_use") *value = spmv_variant_in_use(ctx);
     else if (k == "loop_iters") *value = ctx->loop_iters;
     else if (k == "device_loop_active") *value = ctx->graph_exec && ctx->graph_is_loop ? 1 : 0;
     else if (k == "fused_pcg_active") *value = pcg_fused_ok(ctx) ? 1 : 0;

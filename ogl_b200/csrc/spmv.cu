@@ -818,6 +818,68 @@ __global__ void __launch_bounds__(256) k_spmv_nonlocal(const NonLocalK a)
                                            a.inline_epi != 0, a.ea, /*accumulate=*/true);
 }
 
+// ---------------------------------------------------------------------------
+// Variant 7: ELL (`matrixFormat Ell`).  Slot j of row r lives at [j * pitch + r],
+// so a warp reads 32 consecutive columns / values per slot and gathers x from
+// (for a stencil) 32 consecutive addresses; no row pointers, no shared memory,
+// no barrier.  Slots are added left to right in the row's CSR order and padding
+// slots (column -1) are skipped: bit-identical to the CSR kernels.
+// ---------------------------------------------------------------------------
+constexpr int kEllBatch = 8;
+
+__global__ void k_ell_build(label n, const label *__restrict__ row_ptrs, const label *__restrict__ cols,
+                            const double *__restrict__ vals, int width, int64_t pitch,
+                            label *__restrict__ ell_cols, double *__restrict__ ell_vals)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const label rs = row_ptrs[row], len = row_ptrs[row + 1] - rs;
+    for (int j = 0; j < width; ++j) {
+        ell_cols[j * pitch + row] = j < len ? cols[rs + j] : -1;
+        ell_vals[j * pitch + row] = j < len ? vals[rs + j] : 0.0;
+    }
+}
+
+template <bool ADV, int NRED>
+__global__ void __launch_bounds__(256, 4)
+k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__restrict__ ell_vals,
+           int width, int64_t pitch)
+{
+    if (a.guard_done && a.state->done) return;
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
+        // everything the row needs is requested up front: a warp issues in order, so a load
+        // placed behind the row sum would add its whole latency to every trip
+        double dw = 0.0;
+        if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
+        double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
+        for (int j0 = 0; j0 < width; j0 += kEllBatch) {
+            label c[kEllBatch];
+            double v[kEllBatch], xv[kEllBatch];
+#pragma unroll
+            for (int u = 0; u < kEllBatch; ++u)
+                c[u] = j0 + u < width ? ld_mat(&ell_cols[(j0 + u) * pitch + row], a.mat_policy) : -1;
+#pragma unroll
+            for (int u = 0; u < kEllBatch; ++u)
+                v[u] = j0 + u < width ? ld_mat(&ell_vals[(j0 + u) * pitch + row], a.mat_policy) : 0.0;
+#pragma unroll
+            for (int u = 0; u < kEllBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < kEllBatch; ++u)
+                if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
+        }
+        a.y[row] = sum;
+        if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
+        if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
 __global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int rows_per_block,
                                 int *out)
 {
@@ -944,15 +1006,50 @@ unsigned long long spmv_l2_policy(Context *ctx)
 int spmv_variant_in_use(const Context *ctx);
 static int pick_variant(const Context *ctx)
 {
-    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 6) return (int)ctx->spmv_variant;
+    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 7) return (int)ctx->spmv_variant;
     const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
     const double mean_len = ctx->n > 0 ? (double)ctx->nnz / ctx->n : 0.0;
+    // ell_auto (default off): short regular rows on one rank -> ELL.  The plain ELL SpMV is the
+    // fastest kernel here (profiles/r01_ell_probe.jsonl: 124.6 us = 6.65 TB/s at 8 M rows against
+    // 142.9 us CSR; 16.4 vs 20.5 us at 1 M), but its instantiation with the fused <p,q> is not
+    // (167 vs 155 us; 24.6-26.6 vs 24.6 us), so the PCG iteration loses (39.9 vs 38.6 us).
+    // Several ranks keep the CSR kernels: the ghosted matrix has no ELL copy yet.
+    if (ctx->ell_auto && ctx->n_ranks == 1 && ctx->n > 262144 && ctx->max_row_len <= 16 &&
+        (double)ctx->max_row_len * ctx->n <= 1.25 * (double)ctx->nnz)
+        return 7;
     // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
     if (smem <= (size_t)kStreamSmemMax && mean_len <= 48.0) return 6;   // pipelined stream
     return mean_len >= 16.0 ? 3 : 2;
 }
 
 int spmv_variant_in_use(const Context *ctx) { return pick_variant(ctx); }
+
+// (re)build the ELL copy from the current CSR values; never inside a graph capture
+static int ell_prepare(Context *ctx)
+{
+    if (ctx->ell_ready) return OGL_OK;
+    if (ctx->capturing) return fail(ctx, OGL_ERR_INVALID, "ELL matrix not built before the graph capture");
+    const int width = (int)ctx->max_row_len;
+    if (width < 1 || width > 64 || (int64_t)width * ctx->n > 3 * ctx->nnz)
+        return fail(ctx, OGL_ERR_UNSUPPORTED, "rows too long or too irregular for the ELL format");
+    const int64_t pitch = ((int64_t)ctx->n + 31) / 32 * 32;
+    if (ctx->ell_width != width || ctx->ell_pitch != pitch || !ctx->d_ell_cols) {
+        OGL_TRY(dev_alloc(ctx, &ctx->d_ell_cols, (size_t)(width * pitch)));
+        OGL_TRY(dev_alloc(ctx, &ctx->d_ell_vals, (size_t)(width * pitch)));
+        ctx->ell_width = width;
+        ctx->ell_pitch = pitch;
+        if (ctx->graph_exec) {   // a captured chunk holds the old addresses
+            cudaGraphExecDestroy(ctx->graph_exec);
+            ctx->graph_exec = nullptr;
+        }
+    }
+    k_ell_build<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->n, ctx->d_row_ptrs, ctx->d_cols, ctx->d_vals,
+                                                              width, pitch, ctx->d_ell_cols, ctx->d_ell_vals);
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    ctx->ell_ready = true;
+    return OGL_OK;
+}
 
 int spmv_local(Context *ctx, const SpmvArgs &sa)
 {
@@ -1166,6 +1263,23 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
             else TMA_LAUNCH(false, 2);
         }
 #undef TMA_LAUNCH
+    } else if (variant == 7) {
+        OGL_TRY(ell_prepare(ctx));
+        const int64_t need = ((int64_t)ctx->n + 255) / 256;
+        const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;   // resident: persistent
+        const int grid = (int)(need < cap ? need : cap);
+#define ELL_LAUNCH(A, R) \
+    k_spmv_ell<A, R><<<grid, 256, 0, st>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_width, ctx->ell_pitch)
+        if (sa.advanced) {
+            if (nred == 0) ELL_LAUNCH(true, 0);
+            else if (nred == 1) ELL_LAUNCH(true, 1);
+            else ELL_LAUNCH(true, 2);
+        } else {
+            if (nred == 0) ELL_LAUNCH(false, 0);
+            else if (nred == 1) ELL_LAUNCH(false, 1);
+            else ELL_LAUNCH(false, 2);
+        }
+#undef ELL_LAUNCH
     } else if (variant == 2) {
         const int grid = (ctx->n + 255) / 256;
         DISPATCH(k_spmv_scalar, grid, 256, 0);

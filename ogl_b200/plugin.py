@@ -128,8 +128,14 @@ class GKOlduBaseSolver:
                               rank=self.pstream.rank, n_ranks=self.pstream.n_ranks,
                               nccl_id=self.pstream.nccl_id)
         self.ctx: Context = db[key]
+        # matrixFormat (lduLduBase.H:55-56, CsrMatrixWrapper.H:249-250): Coo (the reference's
+        # default) and Csr both map to the CSR kernels -- same row-major order --, Ell to the ELL copy
+        fmt = str(controls.get("matrixFormat", "Coo"))
+        if fmt not in ("Coo", "Csr", "Ell"):
+            raise FatalError(f"unknown matrixFormat {fmt}\nValid choices are: Coo, Csr, Ell")
+        self.ctx.set_option("spmv_variant", 7 if fmt == "Ell" else 0)
         for opt in ("spmv_variant", "chunk_iters", "use_graph", "comm_mode", "fused_halo", "ghost_p",
-                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb"):
+                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb", "ell_auto"):
             if opt in controls:
                 self.ctx.set_option(opt, int(controls[opt]))
         # preconditioner keyword: word or sub-dict (Preconditioner.H:363-382)
