@@ -223,12 +223,6 @@ __device__ __forceinline__ void block_sum(double (&v)[NRED], double *sm)
     }
 }
 
-__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

@@ -1098,7 +1098,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     } while (0)
     if (variant == 1) {
         const size_t smem = (size_t)(ghosted ? ctx->max_block_nnz_g : ctx->max_block_nnz) * sizeof(double);
-        static bool attr_set = false;
+        static bool attr_done[64] = {};   // cudaFuncSetAttribute is per device
+        bool &attr_set = attr_done[ctx->device & 63];
         if (!attr_set) {
 #define SET_ATTR(A, R)                                                                             \
     cudaFuncSetAttribute(k_spmv_stream<A, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -1149,7 +1150,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
 #undef STREAM_LAUNCH
     } else if (variant == 6) {
         const size_t smem = (size_t)(ghosted ? ctx->max_block_nnz_g : ctx->max_block_nnz) * sizeof(double);
-        static bool attr6 = false;
+        static bool attr6_done[64] = {};
+        bool &attr6 = attr6_done[ctx->device & 63];
         if (!attr6) {
 #define SET_ATTR6(A, R)                                                                          \
     cudaFuncSetAttribute(k_spmv_pipe<A, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -1208,7 +1210,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const size_t smem = (size_t)warp_cap * sizeof(double) * (kWarpCtaThreads / 32);
         if (smem > (size_t)kStreamSmemMax)
             return fail(ctx, OGL_ERR_UNSUPPORTED, "rows too long for the warp-tile SpMV");
-        static bool attr5 = false;
+        static bool attr5_done[64] = {};
+        bool &attr5 = attr5_done[ctx->device & 63];
         if (!attr5) {
             cudaFuncSetAttribute(k_spmv_warp<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
             cudaFuncSetAttribute(k_spmv_warp<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemMax);
