@@ -154,6 +154,15 @@ def cpu_pcg_sample(system, threads: int, iters: int):
     return done / r.seconds, r.seconds, done
 
 
+def cpu_foam_sample(system, iters: int):
+    """`iters` iterations of the OpenFOAM-native-equivalent PCG (face-based Amul + diagonal
+    preconditioner, oracle/foam_pcg.cpp), single thread; returns (it/s, seconds, iterations)."""
+    import oracle
+    r = oracle.foam_pcg(system, tolerance=0.0, rel_tol=0.0, max_iter=iters)
+    done = max(r.n_iterations, 1)
+    return done / r.seconds, r.seconds, done
+
+
 def workload_text(n: int) -> str:
     return (f"{n}^3 cells per GPU, 3-D lid-driven-cavity pressure system, GKOCG+BJ(maxBlockSize 1) FP64, "
             "tolerance 1e-6, relTol 0, x0=0 (BASELINE configs[1])")
@@ -333,10 +342,16 @@ def run_gpu(args):
     if n_gpus == 1:
         cpu_iters = 40 if args.n >= 100 else 200
         cpu_rate, cpu_sec, cpu_done = cpu_pcg_sample(s, 1, cpu_iters)
+        foam_rate, foam_sec, foam_done = cpu_foam_sample(s, cpu_iters)
         cpu_baseline = {"value": cpu_rate, "unit": "iter/s", "cores": 1, "kind": "port",
                         "sample": f"{cpu_done} PCG iterations of the oracle (single thread, Ginkgo "
                                   f"reference-executor order) on the full {args.n}^3 system, "
-                                  f"{cpu_sec:.1f} s"}
+                                  f"{cpu_sec:.1f} s",
+                        # what OpenFOAM itself would run without OGL (baseline iii)
+                        "openfoam_native_equivalent": {
+                            "value": foam_rate, "unit": "iter/s", "cores": 1, "kind": "port",
+                            "sample": f"{foam_done} iterations of face-based lduMatrix::Amul + diagonal PCG "
+                                      f"(oracle/foam_pcg.cpp) on the same system, {foam_sec:.1f} s"}}
 
     line = {
         "metric": "PCG iterations/sec", "value": it_per_s * n_gpus, "unit": "iter/s",

@@ -188,6 +188,18 @@ double orc_time_spmv(orc_label n, const orc_label *row_ptrs,
                      const orc_label *cols, const orc_scalar *vals,
                      const orc_scalar *x, orc_scalar *y, int reps, int threads);
 
+/* OpenFOAM-native-equivalent CPU baseline (foam_pcg.cpp): face-based lduMatrix::Amul +
+ * PCG with the diagonal preconditioner and OpenFOAM's own normFactor / convergence test,
+ * on one rank's lduMatrix (cyclic interfaces as rows/cols/bouCoeffs; lower == NULL when
+ * symmetric).  psi: in initial guess, out solution.  history[k] = residual after k iterations. */
+int orc_foam_pcg(orc_label n, orc_label n_faces, const orc_label *lower_addr,
+                 const orc_label *upper_addr, const orc_scalar *diag, const orc_scalar *upper,
+                 const orc_scalar *lower, orc_label n_if, const orc_label *if_rows,
+                 const orc_label *if_cols, const orc_scalar *if_bou, const orc_scalar *source,
+                 orc_scalar *psi, orc_scalar tolerance, orc_scalar rel_tol, orc_label min_iter,
+                 orc_label max_iter, orc_solve_result *result, orc_scalar *history,
+                 orc_label history_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -295,6 +295,40 @@ def solve(asms: Sequence[Assembled], solver="GKOCG", preconditioner="BJ", max_bl
                        history=hist[:res.n_history].copy(), seconds=res.seconds)
 
 
+def foam_pcg(s, tolerance=1e-6, rel_tol=0.0, min_iter=0, max_iter=1000) -> OracleSolve:
+    """OpenFOAM-native-equivalent baseline (foam_pcg.cpp): face-based Amul + diagonal PCG with
+    OpenFOAM's own normFactor / convergence test on one rank's LduSystem (cyclic interfaces only)."""
+    if any(i.kind == "processor" for i in s.interfaces):
+        raise ValueError("foam_pcg is a single-rank baseline")
+    cyc = [k for k, i in enumerate(s.interfaces) if i.kind != "processor"]
+    if cyc:
+        ir = _i32(np.concatenate([s.interfaces[k].face_cells for k in cyc]))
+        ic = _i32(np.concatenate([s.interfaces[s.interfaces[k].nbr_patch].face_cells for k in cyc]))
+        ib = _f64(np.concatenate([s.interfaces[k].bou_coeffs for k in cyc]))
+    else:
+        ir = ic = np.zeros(0, np.int32)
+        ib = np.zeros(0)
+    la, ua = _i32(s.lower_addr), _i32(s.upper_addr)
+    diag, upper = _f64(s.diag), _f64(s.upper)
+    lower = None if s.lower is None else _f64(s.lower)
+    b, x = _f64(s.source), _f64(s.psi).copy()
+    res = SolveResult()
+    cap = max_iter + 8
+    hist = np.zeros(cap)
+    fn = lib().orc_foam_pcg
+    fn.restype = C.c_int
+    rc = fn(C.c_int32(s.n), C.c_int32(la.size), _ip(la), _ip(ua), _fp(diag), _fp(upper),
+            _fp(lower) if lower is not None else None, C.c_int32(ir.size), _ip(ir), _ip(ic), _fp(ib),
+            _fp(b), _fp(x), C.c_double(tolerance), C.c_double(rel_tol), C.c_int32(min_iter),
+            C.c_int32(max_iter), C.byref(res), _fp(hist), C.c_int32(cap))
+    if rc != 0:
+        raise RuntimeError(f"orc_foam_pcg failed with code {rc}")
+    return OracleSolve(x=[x], init_residual=res.init_residual, final_residual=res.final_residual,
+                       criterion_calls=res.criterion_calls, n_iterations=res.n_iterations,
+                       norm_factor=res.norm_factor, history=hist[:res.n_history].copy(),
+                       seconds=res.seconds)
+
+
 def dist_spmv(asms: Sequence[Assembled], xs: Sequence[np.ndarray]) -> List[np.ndarray]:
     keep: list = []
     arr = _rank_structs(asms, keep)

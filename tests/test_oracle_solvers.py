@@ -124,3 +124,42 @@ def test_block_jacobi_blocks(oracle):
     assert bp.tolist() == [0, 2, 4]
     bp, inv = oracle.bj_blocks(4, rp, cols, vals, 3)
     assert bp.tolist() == [0, 3, 4]
+
+
+@pytest.mark.parametrize("builder", [lambda: cases.pressure_3d(14)[0],
+                                     lambda: cases.pressure_3d(10, sign=-1.0)[0],
+                                     lambda: cases.channel((16, 8, 8), (1, 1, 1))[0],
+                                     lambda: cases.cavity_2d((1, 1, 1))[0]])
+def test_two_restatements_agree(oracle, builder):
+    """The OGL path (assembled CSR, Ginkgo-order CG + scalar Jacobi, OGL's criterion --
+    krylov.cpp) against what OpenFOAM itself would run on the same lduMatrix (face-based
+    Amul, PCG + diagonal preconditioner, OpenFOAM's normFactor -- foam_pcg.cpp).  Two
+    restatements written from different sources must describe the same iteration: OGL's
+    criterion counts its call at iteration 0, OpenFOAM counts completed iterations."""
+    s = builder()
+    # (not tighter: OpenFOAM's checkSingularity, |wApA| / normFactor < 1e-20, ends the tiny-valued
+    # cavity case early at 1e-10 -- a test OGL/Ginkgo do not have)
+    tol = 1e-8
+    o = oracle.solve([oracle.assemble(s)], "GKOCG", "BJ", tolerance=tol)
+    f = oracle.foam_pcg(s, tolerance=tol)
+    assert o.n_iterations == f.n_iterations + 1
+    assert o.norm_factor == pytest.approx(f.norm_factor, rel=1e-12)   # SMALL 1e-15 vs small_ 1e-20
+    assert o.init_residual == pytest.approx(f.init_residual, rel=1e-12)
+    k = min(len(o.history), len(f.history))
+    assert k == f.n_iterations + 1
+    assert np.allclose(o.history[:k], f.history[:k], rtol=1e-8, atol=0)
+    assert np.linalg.norm(o.x[0] - f.x[0]) <= 1e-10 * np.linalg.norm(f.x[0])
+
+
+def test_foam_pcg_options(oracle):
+    s = cases.pressure_3d(10)[0]
+    f = oracle.foam_pcg(s, tolerance=1e-30, max_iter=7)
+    assert f.n_iterations == 7
+    f = oracle.foam_pcg(s, tolerance=1.0, min_iter=5)      # converged at once, minIter forces 5
+    assert f.n_iterations == 5
+    f = oracle.foam_pcg(s, tolerance=1e-30, rel_tol=1e-3)
+    assert f.final_residual < 1e-3 * f.init_residual
+    import scipy.sparse.linalg as spla
+    A, b = cases.assemble_global_csr([s])
+    f = oracle.foam_pcg(s, tolerance=1e-12)
+    assert np.linalg.norm(f.x[0] - spla.spsolve(A.tocsc(), b)) <= 1e-8 * np.linalg.norm(f.x[0])
