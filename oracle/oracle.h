@@ -200,6 +200,16 @@ int orc_foam_pcg(orc_label n, orc_label n_faces, const orc_label *lower_addr,
                  orc_label max_iter, orc_solve_result *result, orc_scalar *history,
                  orc_label history_cap);
 
+/* Same for PBiCGStab::scalarSolve (asymmetric matrices).  history: the residual at every
+ * convergence test (initial, then on s and on r in each iteration). */
+int orc_foam_pbicgstab(orc_label n, orc_label n_faces, const orc_label *lower_addr,
+                       const orc_label *upper_addr, const orc_scalar *diag, const orc_scalar *upper,
+                       const orc_scalar *lower, orc_label n_if, const orc_label *if_rows,
+                       const orc_label *if_cols, const orc_scalar *if_bou, const orc_scalar *source,
+                       orc_scalar *psi, orc_scalar tolerance, orc_scalar rel_tol, orc_label min_iter,
+                       orc_label max_iter, orc_solve_result *result, orc_scalar *history,
+                       orc_label history_cap);
+
 #ifdef __cplusplus
 }
 #endif

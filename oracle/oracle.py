@@ -295,7 +295,7 @@ def solve(asms: Sequence[Assembled], solver="GKOCG", preconditioner="BJ", max_bl
                        history=hist[:res.n_history].copy(), seconds=res.seconds)
 
 
-def foam_pcg(s, tolerance=1e-6, rel_tol=0.0, min_iter=0, max_iter=1000) -> OracleSolve:
+def foam_pcg(s, tolerance=1e-6, rel_tol=0.0, min_iter=0, max_iter=1000, solver="PCG") -> OracleSolve:
     """OpenFOAM-native-equivalent baseline (foam_pcg.cpp): face-based Amul + diagonal PCG with
     OpenFOAM's own normFactor / convergence test on one rank's LduSystem (cyclic interfaces only)."""
     if any(i.kind == "processor" for i in s.interfaces):
@@ -313,9 +313,9 @@ def foam_pcg(s, tolerance=1e-6, rel_tol=0.0, min_iter=0, max_iter=1000) -> Oracl
     lower = None if s.lower is None else _f64(s.lower)
     b, x = _f64(s.source), _f64(s.psi).copy()
     res = SolveResult()
-    cap = max_iter + 8
+    cap = 2 * max_iter + 8
     hist = np.zeros(cap)
-    fn = lib().orc_foam_pcg
+    fn = lib().orc_foam_pcg if solver == "PCG" else lib().orc_foam_pbicgstab
     fn.restype = C.c_int
     rc = fn(C.c_int32(s.n), C.c_int32(la.size), _ip(la), _ip(ua), _fp(diag), _fp(upper),
             _fp(lower) if lower is not None else None, C.c_int32(ir.size), _ip(ir), _ip(ic), _fp(ib),
@@ -327,6 +327,11 @@ def foam_pcg(s, tolerance=1e-6, rel_tol=0.0, min_iter=0, max_iter=1000) -> Oracl
                        criterion_calls=res.criterion_calls, n_iterations=res.n_iterations,
                        norm_factor=res.norm_factor, history=hist[:res.n_history].copy(),
                        seconds=res.seconds)
+
+
+def foam_pbicgstab(s, **kw) -> OracleSolve:
+    """OpenFOAM-native-equivalent PBiCGStab + diagonal preconditioner (foam_pcg.cpp)."""
+    return foam_pcg(s, solver="PBiCGStab", **kw)
 
 
 def dist_spmv(asms: Sequence[Assembled], xs: Sequence[np.ndarray]) -> List[np.ndarray]:

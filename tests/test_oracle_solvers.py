@@ -163,3 +163,19 @@ def test_foam_pcg_options(oracle):
     A, b = cases.assemble_global_csr([s])
     f = oracle.foam_pcg(s, tolerance=1e-12)
     assert np.linalg.norm(f.x[0] - spla.spsolve(A.tocsc(), b)) <= 1e-8 * np.linalg.norm(f.x[0])
+
+
+@pytest.mark.parametrize("n", [10, 16])
+def test_two_restatements_agree_bicgstab(oracle, n):
+    """Same for the asymmetric half: Ginkgo-order BiCGStab + scalar Jacobi under OGL's criterion
+    (two criterion calls per iteration) vs OpenFOAM's PBiCGStab + diagonal preconditioner (two
+    convergence tests per iteration) on the momentum systems."""
+    s = cases.momentum_3d(n)[0]
+    o = oracle.solve([oracle.assemble(s)], "GKOBiCGStab", "BJ", tolerance=1e-9)
+    f = oracle.foam_pbicgstab(s, tolerance=1e-9)
+    assert o.criterion_calls == f.criterion_calls
+    assert o.n_iterations == f.n_iterations or o.n_iterations + 1 == f.n_iterations   # calls / 2 vs ++nIterations
+    k = len(f.history)
+    assert len(o.history) == k
+    assert np.allclose(o.history, f.history, rtol=1e-5, atol=0)
+    assert np.linalg.norm(o.x[0] - f.x[0]) <= 1e-10 * np.linalg.norm(f.x[0])
