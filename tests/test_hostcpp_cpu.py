@@ -26,6 +26,8 @@ def test_selection_table_and_keyword_errors():
             asym.solve("U", BASE, asym.s.psi, asym.s.source)
         with pytest.raises(FoamFatalError, match="Unknown symmetric matrix solver PCG"):
             sym.solve("p", dict(BASE, solver="PCG"), s.psi, s.source)
+        with pytest.raises(FoamFatalError, match="unknown matrixFormat Hybrid"):
+            sym.solve("p", dict(BASE, matrixFormat="Hybrid"), s.psi, s.source)
         with pytest.raises(FoamFatalError, match="does not support the executor: reference"):
             sym.solve("p", {k: v for k, v in BASE.items() if k != "executor"}, s.psi, s.source)
     finally:
