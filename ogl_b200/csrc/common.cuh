@@ -120,7 +120,7 @@ struct Context {
     int64_t ell_pitch = 0;
     int ell_width = 0;
     bool ell_ready = false;
-    int64_t ell_auto = 0;        // 1: spmv_variant 0 may pick the ELL kernel (spmv.cu:pick_variant); off: the
+    int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernel (spmv.cu:pick_variant); off: the
                                  // fused-dot ELL instantiation is slower than the CSR one (r01_ell_probe.jsonl)
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
     int64_t max_warp_nnz = 0;    // warp-tile kernel: max nnz of 32 consecutive rows

@@ -840,7 +840,11 @@ __global__ void k_ell_build(label n, const label *__restrict__ row_ptrs, const l
     }
 }
 
-template <bool ADV, int NRED>
+// W > 0: compile-time row width.  With the run-time slot loop (W == 0) ptxas peels the first
+// two slots of the instantiation with the fused dot and puts their DMUL/DADD between the loads,
+// so an in-order warp waits two extra memory round trips per row; with the width known all
+// 3 W loads of a row are issued before the first dependent instruction (cuobjdump -sass).
+template <bool ADV, int NRED, int W>
 __global__ void __launch_bounds__(256, 4)
 k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__restrict__ ell_vals,
            int width, int64_t pitch)
@@ -856,20 +860,34 @@ k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__re
         double dw = 0.0;
         if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
         double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
-        for (int j0 = 0; j0 < width; j0 += kEllBatch) {
-            label c[kEllBatch];
-            double v[kEllBatch], xv[kEllBatch];
+        if (W > 0) {
+            label c[W > 0 ? W : 1];
+            double v[W > 0 ? W : 1], xv[W > 0 ? W : 1];
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u)
-                c[u] = j0 + u < width ? ld_mat(&ell_cols[(j0 + u) * pitch + row], a.mat_policy) : -1;
+            for (int u = 0; u < W; ++u) c[u] = ld_mat(&ell_cols[u * pitch + row], a.mat_policy);
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u)
-                v[u] = j0 + u < width ? ld_mat(&ell_vals[(j0 + u) * pitch + row], a.mat_policy) : 0.0;
+            for (int u = 0; u < W; ++u) v[u] = ld_mat(&ell_vals[u * pitch + row], a.mat_policy);
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+            for (int u = 0; u < W; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u)
+            for (int u = 0; u < W; ++u)
                 if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
+        } else {
+            for (int j0 = 0; j0 < width; j0 += kEllBatch) {
+                label c[kEllBatch];
+                double v[kEllBatch], xv[kEllBatch];
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u)
+                    c[u] = j0 + u < width ? ld_mat(&ell_cols[(j0 + u) * pitch + row], a.mat_policy) : -1;
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u)
+                    v[u] = j0 + u < width ? ld_mat(&ell_vals[(j0 + u) * pitch + row], a.mat_policy) : 0.0;
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u)
+                    if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
+            }
         }
         a.y[row] = sum;
         if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
@@ -1271,8 +1289,15 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const int64_t need = ((int64_t)ctx->n + 255) / 256;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;   // resident: persistent
         const int grid = (int)(need < cap ? need : cap);
-#define ELL_LAUNCH(A, R) \
-    k_spmv_ell<A, R><<<grid, 256, 0, st>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_width, ctx->ell_pitch)
+#define ELL_LAUNCH_W(A, R, W) \
+    k_spmv_ell<A, R, W><<<grid, 256, 0, st>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_width, ctx->ell_pitch)
+#define ELL_LAUNCH(A, R)                                        \
+    do {                                                        \
+        if (ctx->ell_width == 7) ELL_LAUNCH_W(A, R, 7);         \
+        else if (ctx->ell_width == 5) ELL_LAUNCH_W(A, R, 5);    \
+        else if (ctx->ell_width == 8) ELL_LAUNCH_W(A, R, 8);    \
+        else ELL_LAUNCH_W(A, R, 0);                             \
+    } while (0)
         if (sa.advanced) {
             if (nred == 0) ELL_LAUNCH(true, 0);
             else if (nred == 1) ELL_LAUNCH(true, 1);
@@ -1282,6 +1307,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
             else if (nred == 1) ELL_LAUNCH(false, 1);
             else ELL_LAUNCH(false, 2);
         }
+#undef ELL_LAUNCH_W
 #undef ELL_LAUNCH
     } else if (variant == 2) {
         const int grid = (ctx->n + 255) / 256;
