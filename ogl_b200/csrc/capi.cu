@@ -129,7 +129,7 @@ static void destroy(Context *c)
                     c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
                     c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
                     c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar,        c->d_ell_cols,
-                    c->d_ell_vals};
+                    c->d_ell_vals,   c->d_gell_cols,  c->d_gell_vals};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)

@@ -120,6 +120,13 @@ struct Context {
     int64_t ell_pitch = 0;
     int ell_width = 0;
     bool ell_ready = false;
+    // ... and of the ghosted matrix (several ranks, CG ghost-p mode)
+    label *d_gell_cols = nullptr;
+    double *d_gell_vals = nullptr;
+    int64_t gell_pitch = 0;
+    int gell_width = 0;
+    bool gell_ready = false;
+    label max_row_len_g = 0;     // longest row of the ghosted CSR
     int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernel (spmv.cu:pick_variant); off: the
                                  // fused-dot ELL instantiation is slower than the CSR one (r01_ell_probe.jsonl)
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block

@@ -1031,8 +1031,9 @@ static int pick_variant(const Context *ctx)
     // fastest kernel here (profiles/r01_ell_probe.jsonl: 124.6 us = 6.65 TB/s at 8 M rows against
     // 142.9 us CSR; 16.4 vs 20.5 us at 1 M), but its instantiation with the fused <p,q> is not
     // (167 vs 155 us; 24.6-26.6 vs 24.6 us), so the PCG iteration loses (39.9 vs 38.6 us).
-    // Several ranks keep the CSR kernels: the ghosted matrix has no ELL copy yet.
-    if (ctx->ell_auto && ctx->n_ranks == 1 && ctx->n > 262144 && ctx->max_row_len <= 16 &&
+    // Several ranks: the CG loop's SpMV (ghost_x) runs over an ELL copy of the ghosted matrix; the
+    // flag-handshake SpMV of the other solvers stays on the pipelined CSR kernel.
+    if (ctx->ell_auto && ctx->n > 262144 && ctx->max_row_len <= 16 &&
         (double)ctx->max_row_len * ctx->n <= 1.25 * (double)ctx->nnz)
         return 7;
     // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
@@ -1043,29 +1044,36 @@ static int pick_variant(const Context *ctx)
 int spmv_variant_in_use(const Context *ctx) { return pick_variant(ctx); }
 
 // (re)build the ELL copy from the current CSR values; never inside a graph capture
-static int ell_prepare(Context *ctx)
+static int ell_prepare(Context *ctx, bool ghosted)
 {
-    if (ctx->ell_ready) return OGL_OK;
+    bool &ready = ghosted ? ctx->gell_ready : ctx->ell_ready;
+    if (ready) return OGL_OK;
     if (ctx->capturing) return fail(ctx, OGL_ERR_INVALID, "ELL matrix not built before the graph capture");
-    const int width = (int)ctx->max_row_len;
-    if (width < 1 || width > 64 || (int64_t)width * ctx->n > 3 * ctx->nnz)
+    const int width = (int)(ghosted ? ctx->max_row_len_g : ctx->max_row_len);
+    const int64_t nnz = ghosted ? ctx->nnz + ctx->n_halo : ctx->nnz;
+    if (width < 1 || width > 64 || (int64_t)width * ctx->n > 3 * nnz)
         return fail(ctx, OGL_ERR_UNSUPPORTED, "rows too long or too irregular for the ELL format");
     const int64_t pitch = ((int64_t)ctx->n + 31) / 32 * 32;
-    if (ctx->ell_width != width || ctx->ell_pitch != pitch || !ctx->d_ell_cols) {
-        OGL_TRY(dev_alloc(ctx, &ctx->d_ell_cols, (size_t)(width * pitch)));
-        OGL_TRY(dev_alloc(ctx, &ctx->d_ell_vals, (size_t)(width * pitch)));
-        ctx->ell_width = width;
-        ctx->ell_pitch = pitch;
+    label *&cols = ghosted ? ctx->d_gell_cols : ctx->d_ell_cols;
+    double *&vals = ghosted ? ctx->d_gell_vals : ctx->d_ell_vals;
+    int &w = ghosted ? ctx->gell_width : ctx->ell_width;
+    int64_t &pt = ghosted ? ctx->gell_pitch : ctx->ell_pitch;
+    if (w != width || pt != pitch || !cols) {
+        OGL_TRY(dev_alloc(ctx, &cols, (size_t)(width * pitch)));
+        OGL_TRY(dev_alloc(ctx, &vals, (size_t)(width * pitch)));
+        w = width;
+        pt = pitch;
         if (ctx->graph_exec) {   // a captured chunk holds the old addresses
             cudaGraphExecDestroy(ctx->graph_exec);
             ctx->graph_exec = nullptr;
         }
     }
-    k_ell_build<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->n, ctx->d_row_ptrs, ctx->d_cols, ctx->d_vals,
-                                                              width, pitch, ctx->d_ell_cols, ctx->d_ell_vals);
+    k_ell_build<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->n, ghosted ? ctx->d_g_row_ptrs : ctx->d_row_ptrs, ghosted ? ctx->d_g_cols : ctx->d_cols,
+        ghosted ? ctx->d_g_vals : ctx->d_vals, width, pitch, cols, vals);
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
-    ctx->ell_ready = true;
+    ready = true;
     return OGL_OK;
 }
 
@@ -1098,7 +1106,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.ea.trace_tag = 20;
     const int nred = sa.nred;
     if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
-    const int variant = pick_variant(ctx);
+    int variant = pick_variant(ctx);
+    if (variant == 7 && sa.fused_halo) variant = 6;   // the flag-handshake kernel exists for CSR only
     // a rank without halo rows (n_halo == 0) runs the halo kernel on its local matrix
     const bool ghosted = (sa.fused_halo || sa.ghost_x) && ctx->have_ghosted;
     cudaStream_t st = ctx->stream;
@@ -1285,17 +1294,22 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         }
 #undef TMA_LAUNCH
     } else if (variant == 7) {
-        OGL_TRY(ell_prepare(ctx));
+        OGL_TRY(ell_prepare(ctx, ghosted));
+        if (sa.ghost_x) k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;   // all-reduce inside the launch
+        const label *e_cols = ghosted ? ctx->d_gell_cols : ctx->d_ell_cols;
+        const double *e_vals = ghosted ? ctx->d_gell_vals : ctx->d_ell_vals;
+        const int e_width = ghosted ? ctx->gell_width : ctx->ell_width;
+        const int64_t e_pitch = ghosted ? ctx->gell_pitch : ctx->ell_pitch;
         const int64_t need = ((int64_t)ctx->n + 255) / 256;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;   // resident: persistent
         const int grid = (int)(need < cap ? need : cap);
 #define ELL_LAUNCH_W(A, R, W) \
-    k_spmv_ell<A, R, W><<<grid, 256, 0, st>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_width, ctx->ell_pitch)
+    k_spmv_ell<A, R, W><<<grid, 256, 0, st>>>(k, e_cols, e_vals, e_width, e_pitch)
 #define ELL_LAUNCH(A, R)                                        \
     do {                                                        \
-        if (ctx->ell_width == 7) ELL_LAUNCH_W(A, R, 7);         \
-        else if (ctx->ell_width == 5) ELL_LAUNCH_W(A, R, 5);    \
-        else if (ctx->ell_width == 8) ELL_LAUNCH_W(A, R, 8);    \
+        if (e_width == 7) ELL_LAUNCH_W(A, R, 7);                \
+        else if (e_width == 5) ELL_LAUNCH_W(A, R, 5);           \
+        else if (e_width == 8) ELL_LAUNCH_W(A, R, 8);           \
         else ELL_LAUNCH_W(A, R, 0);                             \
     } while (0)
         if (sa.advanced) {
