@@ -127,6 +127,7 @@ struct Context {
     int gell_width = 0;
     bool gell_ready = false;
     label max_row_len_g = 0;     // longest row of the ghosted CSR
+    int64_t fuse_p = 0;          // CG: p-update fused into the ELL SpMV (spmv.cu:k_spmv_ell_cgp), one rank
     int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernel (spmv.cu:pick_variant); off: the
                                  // fused-dot ELL instantiation is slower than the CSR one (r01_ell_probe.jsonl)
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
@@ -306,6 +307,7 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
                   const double *dot_with, int nred, bool guard_done, int epi,
                   bool inline_epi);
 int spmv_setup(Context *ctx);
+int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q);
 
 // comm.cu ------------------------------------------------------------------------
 int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,

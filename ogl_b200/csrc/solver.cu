@@ -517,6 +517,14 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
     const double *zz = pk == 0 ? r_old : z;   // the residual this iteration starts from
     const bool ghost = ghost_p_mode(ctx);
     const bool pack = !ghost && fused_halo_ok(ctx) && ctx->n_send > 0;
+    bool fused_p = false;
+    if (ctx->fuse_p && ctx->n_ranks == 1 && ctx->profile_stride == 0) {
+        // p-update inside the ELL SpMV: one launch instead of two
+        const int rc = spmv_ell_cgp(ctx, zz, p_old, p, q);
+        if (rc == OGL_OK) fused_p = true;
+        else if (rc != OGL_ERR_UNSUPPORTED) return rc;
+    }
+    if (!fused_p) {
     {
         VecK a = base_args(ctx, EPI_NONE, true);
         a.in0 = zz;
@@ -547,6 +555,7 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
         if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);
         OGL_TRY(dist_spmv(ctx, s));
         if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);
+    }
     }
     {
         VecK a = base_args(ctx, pk == 2 ? EPI_NONE : EPI_CG_RHO_CHECK, true, pk == 2 ? 0 : 2);

@@ -34,6 +34,8 @@
 // Fused reductions (NRED): red[0] = <dot_with, y>, red[1] = <y, y>; reduced
 // deterministically (reduce.cuh) and, on one rank, followed in the same launch
 // by the scalar epilogue (e.g. CG: beta = <p,q>, alpha = rho / beta).
+#include <cstring>
+
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -898,6 +900,53 @@ k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__re
                                            a.inline_epi != 0, a.ea);
 }
 
+// ---------------------------------------------------------------------------
+// CG step_1 fused into the ELL SpMV (option fuse_p, one rank): instead of
+// gathering p' the kernel gathers z and p and forms p' = z + (rho/rho_prev) p
+// for every operand on the fly -- the same two operations the p-update kernel
+// would perform on the same two numbers, hence the same bits -- and the owner of
+// a row writes p'[row] (its diagonal slot) for the x/r-update and the next
+// iteration.  One launch and 8 B/row of HBM traffic less per iteration; the
+// price is a second (coalesced, cache-resident) gather per slot.
+//   x = z (or r), y_in = p (previous), y = q, p_new = the other p buffer
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256, 4)
+k_spmv_ell_cgp(const SpmvK a, const label *__restrict__ ell_cols, const double *__restrict__ ell_vals,
+               int64_t pitch, double *__restrict__ p_new)
+{
+    if (a.guard_done && a.state->done) return;
+    const bool p_is_z = a.state->flag_p_is_z != 0;
+    const double t = a.state->coef_p;
+    double red[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
+        label c[W];
+        double v[W], zc[W], pc[W];
+#pragma unroll
+        for (int u = 0; u < W; ++u) c[u] = ld_mat(&ell_cols[u * pitch + row], a.mat_policy);
+#pragma unroll
+        for (int u = 0; u < W; ++u) v[u] = ld_mat(&ell_vals[u * pitch + row], a.mat_policy);
+#pragma unroll
+        for (int u = 0; u < W; ++u) zc[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < W; ++u) pc[u] = (c[u] >= 0 && !p_is_z) ? __ldg(&a.y_in[c[u]]) : 0.0;
+        double sum = 0.0, mine = 0.0;
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+            if (c[u] >= 0) {
+                const double pv = p_is_z ? zc[u] : __dadd_rn(zc[u], __dmul_rn(t, pc[u]));
+                if (c[u] == (label)row) mine = pv;   // the diagonal slot: my own p'
+                sum = __dadd_rn(sum, __dmul_rn(v[u], pv));
+            }
+        }
+        p_new[row] = mine;
+        a.y[row] = sum;
+        red[0] = __dadd_rn(red[0], __dmul_rn(mine, sum));
+    }
+    grid_reduce<1>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+}
+
 __global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int rows_per_block,
                                 int *out)
 {
@@ -1331,6 +1380,40 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         DISPATCH(k_spmv_vector, grid, 256, 0);
     }
 #undef DISPATCH
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    return OGL_OK;
+}
+
+// q = A p', p' = z + coef_p p, <p',q>, CG_BETA epilogue -- one launch (see k_spmv_ell_cgp).
+// Returns OGL_ERR_UNSUPPORTED when the fused form does not apply (caller falls back).
+int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q)
+{
+    if (ctx->n_ranks != 1 || pick_variant(ctx) != 7) return OGL_ERR_UNSUPPORTED;
+    OGL_TRY(ell_prepare(ctx, false));
+    if (ctx->ell_width != 7 && ctx->ell_width != 5) return OGL_ERR_UNSUPPORTED;
+    SpmvK k;
+    std::memset(&k, 0, sizeof(k));
+    k.x = z;
+    k.y_in = p_old;
+    k.y = q;
+    k.n = ctx->n;
+    k.mat_policy = spmv_l2_policy(ctx);
+    k.partials = ctx->d_partials;
+    k.ticket = ctx->d_ticket;
+    k.state = ctx->d_state;
+    k.epi = EPI_CG_BETA;
+    k.inline_epi = 1;
+    k.guard_done = 1;
+    k.ea = make_epi_args(ctx, 0);
+    k.ea.trace_tag = 20;
+    const int64_t need = ((int64_t)ctx->n + 255) / 256;
+    const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;
+    const int grid = (int)(need < cap ? need : cap);
+    if (ctx->ell_width == 7)
+        k_spmv_ell_cgp<7><<<grid, 256, 0, ctx->stream>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_pitch, p_new);
+    else
+        k_spmv_ell_cgp<5><<<grid, 256, 0, ctx->stream>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_pitch, p_new);
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
     return OGL_OK;
