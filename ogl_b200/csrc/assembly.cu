@@ -221,6 +221,12 @@ __global__ void k_ghost_halo(label n, label n_groups, const label *__restrict__ 
     }
 }
 
+__global__ void k_row_len_max(label n, const label *__restrict__ row_ptrs, int *out)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < n) atomicMax(out, row_ptrs[r + 1] - row_ptrs[r]);
+}
+
 __global__ void k_block_span_max(label n, const label *__restrict__ row_ptrs, int rows_per_block,
                                  int *out)
 {
@@ -370,6 +376,8 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->have_pattern = true;
     ctx->ell_ready = false;
     ctx->ell_width = 0;
+    ctx->gell_ready = false;
+    ctx->gell_width = 0;
     ctx->have_values = false;
     ctx->have_precond = false;
     ctx->have_b = ctx->have_x = false;
@@ -452,13 +460,19 @@ static int build_ghosted(Context *ctx)
         ctx->d_g_row_ptrs, ctx->d_g_cols, ctx->d_g_map);
     const int64_t nblk = ((int64_t)n + 255) / 256;
     k_block_span_max<<<(int)((nblk + 255) / 256), 256, 0, st>>>(n, ctx->d_g_row_ptrs, 256, d_max);
-    int mx = 0;
+    int mx = 0, mx_row = 0;
     cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaMemsetAsync(d_max, 0, sizeof(int), st);
+    k_row_len_max<<<grid_for((int64_t)n), kThreads, 0, st>>>(n, ctx->d_g_row_ptrs, d_max);
+    cudaMemcpyAsync(&mx_row, d_max, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess)
         return fail(ctx, OGL_ERR_CUDA, std::string("build_ghosted: ") + cudaGetErrorString(e));
     ctx->max_block_nnz_g = mx;
+    ctx->max_row_len_g = mx_row;
+    ctx->gell_ready = false;
     ctx->have_ghosted = true;
     return OGL_OK;
 }
@@ -589,7 +603,8 @@ int values_update(Context *ctx, const double *diag, const double *upper,
     }
     OGL_CUDA(ctx, cudaGetLastError());
     ctx->have_values = true;
-    ctx->ell_ready = false;      // the ELL copy (if in use) is rebuilt from the new values on demand
+    ctx->ell_ready = false;      // the ELL copies (if in use) are rebuilt from the new values on demand
+    ctx->gell_ready = false;
     ctx->have_precond = false;   // regenerated every solve (caching 0, Preconditioner.H:416-422)
     return OGL_OK;
 }

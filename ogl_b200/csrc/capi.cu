@@ -129,7 +129,7 @@ static void destroy(Context *c)
                     c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
                     c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
                     c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar,        c->d_ell_cols,
-                    c->d_ell_vals};
+                    c->d_ell_vals,   c->d_gell_cols,  c->d_gell_vals};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)
@@ -333,6 +333,8 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->fused_halo = value;
     } else if (k == "ghost_p") {
         ctx->ghost_p = value != 0;
+    } else if (k == "fuse_p") {
+        ctx->fuse_p = value != 0;
     } else if (k == "ell_auto") {
         ctx->ell_auto = value != 0;
     } else if (k == "device_loop") {
@@ -393,6 +395,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "fused_pcg") *value = ctx->fused_pcg;
     else if (k == "device_loop") *value = ctx->device_loop;
     else if (k == "ell_auto") *value = ctx->ell_auto;
+    else if (k == "fuse_p") *value = ctx->fuse_p;
     else if (k == "spmv_variant_in_use") *value = spmv_variant_in_use(ctx);
     else if (k == "loop_iters") *value = ctx->loop_iters;
     else if (k == "device_loop_active") *value = ctx->graph_exec && ctx->graph_is_loop ? 1 : 0;

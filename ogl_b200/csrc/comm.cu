@@ -342,7 +342,7 @@ int comm_bench(Context *ctx, int mode, int reps, double *us)
 bool fused_halo_ok(const Context *ctx)
 {
     const int v = spmv_variant_in_use(ctx);
-    if (!use_p2p(ctx) || !(v == 1 || v == 6) || ctx->fused_halo == 0) return false;
+    if (!use_p2p(ctx) || !(v == 1 || v == 6 || v == 7) || ctx->fused_halo == 0) return false;
     // With the ghosted CSR (assembly.cu:build_ghosted) the halo costs the kernel
     // nothing per tile, so auto (2) == on (1).
     return true;

@@ -120,7 +120,15 @@ struct Context {
     int64_t ell_pitch = 0;
     int ell_width = 0;
     bool ell_ready = false;
-    int64_t ell_auto = 0;        // 1: spmv_variant 0 may pick the ELL kernel (spmv.cu:pick_variant); off: the
+    // ... and of the ghosted matrix (several ranks, CG ghost-p mode)
+    label *d_gell_cols = nullptr;
+    double *d_gell_vals = nullptr;
+    int64_t gell_pitch = 0;
+    int gell_width = 0;
+    bool gell_ready = false;
+    label max_row_len_g = 0;     // longest row of the ghosted CSR
+    int64_t fuse_p = 0;          // CG: p-update fused into the ELL SpMV (spmv.cu:k_spmv_ell_cgp), one rank
+    int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernel (spmv.cu:pick_variant); off: the
                                  // fused-dot ELL instantiation is slower than the CSR one (r01_ell_probe.jsonl)
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
     int64_t max_warp_nnz = 0;    // warp-tile kernel: max nnz of 32 consecutive rows
@@ -299,6 +307,7 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
                   const double *dot_with, int nred, bool guard_done, int epi,
                   bool inline_epi);
 int spmv_setup(Context *ctx);
+int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q);
 
 // comm.cu ------------------------------------------------------------------------
 int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,

@@ -119,6 +119,16 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
 {
     cudaGridDependencySynchronize();            // PDL: everything below reads the previous kernel's output
     cudaTriggerProgrammaticLaunchCompletion();  // the SpMV may start getting resident
+    // the first trip's vector loads need no scalar: in flight while `done` and the coefficient arrive
+    const double2 *__restrict__ z2 = reinterpret_cast<const double2 *>(a.in0);
+    const double2 *__restrict__ po2 = reinterpret_cast<const double2 *>(a.in1);
+    const int64_t n2 = a.n >> 1;
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double2 z_first = make_double2(0.0, 0.0), po_first = z_first;
+    if (i0 < n2) {
+        z_first = z2[i0];
+        po_first = po2[i0];
+    }
     if (a.guard_done && a.state->done) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(a.ea, 0);
     const bool p_is_z = a.state->flag_p_is_z != 0;
@@ -156,12 +166,18 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
             *dst = v;   // published by the SpMV kernel's release on entry
         }
     }
-    const double2 *__restrict__ z2 = reinterpret_cast<const double2 *>(a.in0);
-    const double2 *__restrict__ po2 = reinterpret_cast<const double2 *>(a.in1);
     double2 *__restrict__ p2 = reinterpret_cast<double2 *>(a.out0);
-    const int64_t n2 = a.n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (i0 < n2) {
+        double2 p = z_first;
+        if (!p_is_z) {
+            p.x = __dadd_rn(z_first.x, __dmul_rn(t, po_first.x));
+            p.y = __dadd_rn(z_first.y, __dmul_rn(t, po_first.y));
+        }
+        p2[i0] = p;
+    }
 #pragma unroll 2
-    GRID_STRIDE(i, n2) {
+    for (int64_t i = i0 + stride; i < n2; i += stride) {
         const double2 z = z2[i];
         double2 p = z;
         if (!p_is_z) {
@@ -202,6 +218,22 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
 {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
+    // the first trip's vector loads need no scalar: in flight while `done`, beta and alpha arrive
+    const double2 *__restrict__ p2 = reinterpret_cast<const double2 *>(a.in0);
+    const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(a.in1);
+    const double2 *__restrict__ d2 = reinterpret_cast<const double2 *>(a.in2);
+    double2 *__restrict__ x2 = reinterpret_cast<double2 *>(a.out0);
+    const double2 *__restrict__ ro2 = reinterpret_cast<const double2 *>(a.in3);
+    const int64_t n2 = a.n >> 1;
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double2 r_f = make_double2(0.0, 0.0), x_f = r_f, p_f = r_f, q_f = r_f, d_f = r_f;
+    if (i0 < n2) {
+        r_f = ro2[i0];
+        x_f = x2[i0];
+        p_f = p2[i0];
+        q_f = q2[i0];
+        if (PK == 1) d_f = d2[i0];
+    }
     if (a.guard_done && a.state->done) {
         // (also reached when the criterion fired before the loop, or in the first half of a body)
         if (a.cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
@@ -225,16 +257,19 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
             push_stamped(dst, PK == 1 ? __dmul_rn(r, a.in2[cell]) : r, stamp);
         }
     }
-    const double2 *__restrict__ p2 = reinterpret_cast<const double2 *>(a.in0);
-    const double2 *__restrict__ q2 = reinterpret_cast<const double2 *>(a.in1);
-    const double2 *__restrict__ d2 = reinterpret_cast<const double2 *>(a.in2);
-    double2 *__restrict__ x2 = reinterpret_cast<double2 *>(a.out0);
-    const double2 *__restrict__ ro2 = reinterpret_cast<const double2 *>(a.in3);
     double2 *__restrict__ r2 = reinterpret_cast<double2 *>(a.out1);
     double2 *__restrict__ z2 = reinterpret_cast<double2 *>(a.out2);
-    const int64_t n2 = a.n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (i0 < n2) {
+        double2 z = make_double2(0.0, 0.0);
+        cg_xr_elem<PK>(upd, t, x_f.x, r_f.x, p_f.x, q_f.x, d_f.x, z.x, red);
+        cg_xr_elem<PK>(upd, t, x_f.y, r_f.y, p_f.y, q_f.y, d_f.y, z.y, red);
+        if (upd) x2[i0] = x_f;
+        r2[i0] = r_f;
+        if (PK == 1) z2[i0] = z;
+    }
 #pragma unroll 2
-    GRID_STRIDE(i, n2) {
+    for (int64_t i = i0 + stride; i < n2; i += stride) {
         double2 r = ro2[i];
         double2 x = make_double2(0.0, 0.0), p = x, q = x, d = x, z = x;
         if (upd) {
@@ -482,6 +517,14 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
     const double *zz = pk == 0 ? r_old : z;   // the residual this iteration starts from
     const bool ghost = ghost_p_mode(ctx);
     const bool pack = !ghost && fused_halo_ok(ctx) && ctx->n_send > 0;
+    bool fused_p = false;
+    if (ctx->fuse_p && ctx->n_ranks == 1 && ctx->profile_stride == 0) {
+        // p-update inside the ELL SpMV: one launch instead of two
+        const int rc = spmv_ell_cgp(ctx, zz, p_old, p, q);
+        if (rc == OGL_OK) fused_p = true;
+        else if (rc != OGL_ERR_UNSUPPORTED) return rc;
+    }
+    if (!fused_p) {
     {
         VecK a = base_args(ctx, EPI_NONE, true);
         a.in0 = zz;
@@ -512,6 +555,7 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
         if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);
         OGL_TRY(dist_spmv(ctx, s));
         if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);
+    }
     }
     {
         VecK a = base_args(ctx, pk == 2 ? EPI_NONE : EPI_CG_RHO_CHECK, true, pk == 2 ? 0 : 2);

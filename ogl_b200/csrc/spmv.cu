@@ -34,6 +34,8 @@
 // Fused reductions (NRED): red[0] = <dot_with, y>, red[1] = <y, y>; reduced
 // deterministically (reduce.cuh) and, on one rank, followed in the same launch
 // by the scalar epilogue (e.g. CG: beta = <p,q>, alpha = rho / beta).
+#include <cstring>
+
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -840,7 +842,11 @@ __global__ void k_ell_build(label n, const label *__restrict__ row_ptrs, const l
     }
 }
 
-template <bool ADV, int NRED>
+// W > 0: compile-time row width.  With the run-time slot loop (W == 0) ptxas peels the first
+// two slots of the instantiation with the fused dot and puts their DMUL/DADD between the loads,
+// so an in-order warp waits two extra memory round trips per row; with the width known all
+// 3 W loads of a row are issued before the first dependent instruction (cuobjdump -sass).
+template <bool ADV, int NRED, int W>
 __global__ void __launch_bounds__(256, 4)
 k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__restrict__ ell_vals,
            int width, int64_t pitch)
@@ -856,20 +862,34 @@ k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__re
         double dw = 0.0;
         if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
         double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
-        for (int j0 = 0; j0 < width; j0 += kEllBatch) {
-            label c[kEllBatch];
-            double v[kEllBatch], xv[kEllBatch];
+        if (W > 0) {
+            label c[W > 0 ? W : 1];
+            double v[W > 0 ? W : 1], xv[W > 0 ? W : 1];
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u)
-                c[u] = j0 + u < width ? ld_mat(&ell_cols[(j0 + u) * pitch + row], a.mat_policy) : -1;
+            for (int u = 0; u < W; ++u) c[u] = ld_mat(&ell_cols[u * pitch + row], a.mat_policy);
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u)
-                v[u] = j0 + u < width ? ld_mat(&ell_vals[(j0 + u) * pitch + row], a.mat_policy) : 0.0;
+            for (int u = 0; u < W; ++u) v[u] = ld_mat(&ell_vals[u * pitch + row], a.mat_policy);
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+            for (int u = 0; u < W; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
 #pragma unroll
-            for (int u = 0; u < kEllBatch; ++u)
+            for (int u = 0; u < W; ++u)
                 if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
+        } else {
+            for (int j0 = 0; j0 < width; j0 += kEllBatch) {
+                label c[kEllBatch];
+                double v[kEllBatch], xv[kEllBatch];
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u)
+                    c[u] = j0 + u < width ? ld_mat(&ell_cols[(j0 + u) * pitch + row], a.mat_policy) : -1;
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u)
+                    v[u] = j0 + u < width ? ld_mat(&ell_vals[(j0 + u) * pitch + row], a.mat_policy) : 0.0;
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < kEllBatch; ++u)
+                    if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
+            }
         }
         a.y[row] = sum;
         if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
@@ -878,6 +898,53 @@ k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__re
     if (NRED > 0)
         grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
                                            a.inline_epi != 0, a.ea);
+}
+
+// ---------------------------------------------------------------------------
+// CG step_1 fused into the ELL SpMV (option fuse_p, one rank): instead of
+// gathering p' the kernel gathers z and p and forms p' = z + (rho/rho_prev) p
+// for every operand on the fly -- the same two operations the p-update kernel
+// would perform on the same two numbers, hence the same bits -- and the owner of
+// a row writes p'[row] (its diagonal slot) for the x/r-update and the next
+// iteration.  One launch and 8 B/row of HBM traffic less per iteration; the
+// price is a second (coalesced, cache-resident) gather per slot.
+//   x = z (or r), y_in = p (previous), y = q, p_new = the other p buffer
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256, 4)
+k_spmv_ell_cgp(const SpmvK a, const label *__restrict__ ell_cols, const double *__restrict__ ell_vals,
+               int64_t pitch, double *__restrict__ p_new)
+{
+    if (a.guard_done && a.state->done) return;
+    const bool p_is_z = a.state->flag_p_is_z != 0;
+    const double t = a.state->coef_p;
+    double red[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
+        label c[W];
+        double v[W], zc[W], pc[W];
+#pragma unroll
+        for (int u = 0; u < W; ++u) c[u] = ld_mat(&ell_cols[u * pitch + row], a.mat_policy);
+#pragma unroll
+        for (int u = 0; u < W; ++u) v[u] = ld_mat(&ell_vals[u * pitch + row], a.mat_policy);
+#pragma unroll
+        for (int u = 0; u < W; ++u) zc[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < W; ++u) pc[u] = (c[u] >= 0 && !p_is_z) ? __ldg(&a.y_in[c[u]]) : 0.0;
+        double sum = 0.0, mine = 0.0;
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+            if (c[u] >= 0) {
+                const double pv = p_is_z ? zc[u] : __dadd_rn(zc[u], __dmul_rn(t, pc[u]));
+                if (c[u] == (label)row) mine = pv;   // the diagonal slot: my own p'
+                sum = __dadd_rn(sum, __dmul_rn(v[u], pv));
+            }
+        }
+        p_new[row] = mine;
+        a.y[row] = sum;
+        red[0] = __dadd_rn(red[0], __dmul_rn(mine, sum));
+    }
+    grid_reduce<1>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
 }
 
 __global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int rows_per_block,
@@ -1013,8 +1080,9 @@ static int pick_variant(const Context *ctx)
     // fastest kernel here (profiles/r01_ell_probe.jsonl: 124.6 us = 6.65 TB/s at 8 M rows against
     // 142.9 us CSR; 16.4 vs 20.5 us at 1 M), but its instantiation with the fused <p,q> is not
     // (167 vs 155 us; 24.6-26.6 vs 24.6 us), so the PCG iteration loses (39.9 vs 38.6 us).
-    // Several ranks keep the CSR kernels: the ghosted matrix has no ELL copy yet.
-    if (ctx->ell_auto && ctx->n_ranks == 1 && ctx->n > 262144 && ctx->max_row_len <= 16 &&
+    // Several ranks: the CG loop's SpMV (ghost_x) runs over an ELL copy of the ghosted matrix; the
+    // flag-handshake SpMV of the other solvers stays on the pipelined CSR kernel.
+    if (ctx->ell_auto && ctx->n > 262144 && ctx->max_row_len <= 16 &&
         (double)ctx->max_row_len * ctx->n <= 1.25 * (double)ctx->nnz)
         return 7;
     // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
@@ -1025,29 +1093,36 @@ static int pick_variant(const Context *ctx)
 int spmv_variant_in_use(const Context *ctx) { return pick_variant(ctx); }
 
 // (re)build the ELL copy from the current CSR values; never inside a graph capture
-static int ell_prepare(Context *ctx)
+static int ell_prepare(Context *ctx, bool ghosted)
 {
-    if (ctx->ell_ready) return OGL_OK;
+    bool &ready = ghosted ? ctx->gell_ready : ctx->ell_ready;
+    if (ready) return OGL_OK;
     if (ctx->capturing) return fail(ctx, OGL_ERR_INVALID, "ELL matrix not built before the graph capture");
-    const int width = (int)ctx->max_row_len;
-    if (width < 1 || width > 64 || (int64_t)width * ctx->n > 3 * ctx->nnz)
+    const int width = (int)(ghosted ? ctx->max_row_len_g : ctx->max_row_len);
+    const int64_t nnz = ghosted ? ctx->nnz + ctx->n_halo : ctx->nnz;
+    if (width < 1 || width > 64 || (int64_t)width * ctx->n > 3 * nnz)
         return fail(ctx, OGL_ERR_UNSUPPORTED, "rows too long or too irregular for the ELL format");
     const int64_t pitch = ((int64_t)ctx->n + 31) / 32 * 32;
-    if (ctx->ell_width != width || ctx->ell_pitch != pitch || !ctx->d_ell_cols) {
-        OGL_TRY(dev_alloc(ctx, &ctx->d_ell_cols, (size_t)(width * pitch)));
-        OGL_TRY(dev_alloc(ctx, &ctx->d_ell_vals, (size_t)(width * pitch)));
-        ctx->ell_width = width;
-        ctx->ell_pitch = pitch;
+    label *&cols = ghosted ? ctx->d_gell_cols : ctx->d_ell_cols;
+    double *&vals = ghosted ? ctx->d_gell_vals : ctx->d_ell_vals;
+    int &w = ghosted ? ctx->gell_width : ctx->ell_width;
+    int64_t &pt = ghosted ? ctx->gell_pitch : ctx->ell_pitch;
+    if (w != width || pt != pitch || !cols) {
+        OGL_TRY(dev_alloc(ctx, &cols, (size_t)(width * pitch)));
+        OGL_TRY(dev_alloc(ctx, &vals, (size_t)(width * pitch)));
+        w = width;
+        pt = pitch;
         if (ctx->graph_exec) {   // a captured chunk holds the old addresses
             cudaGraphExecDestroy(ctx->graph_exec);
             ctx->graph_exec = nullptr;
         }
     }
-    k_ell_build<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->n, ctx->d_row_ptrs, ctx->d_cols, ctx->d_vals,
-                                                              width, pitch, ctx->d_ell_cols, ctx->d_ell_vals);
+    k_ell_build<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->n, ghosted ? ctx->d_g_row_ptrs : ctx->d_row_ptrs, ghosted ? ctx->d_g_cols : ctx->d_cols,
+        ghosted ? ctx->d_g_vals : ctx->d_vals, width, pitch, cols, vals);
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
-    ctx->ell_ready = true;
+    ready = true;
     return OGL_OK;
 }
 
@@ -1080,7 +1155,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     k.ea.trace_tag = 20;
     const int nred = sa.nred;
     if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
-    const int variant = pick_variant(ctx);
+    int variant = pick_variant(ctx);
+    if (variant == 7 && sa.fused_halo) variant = 6;   // the flag-handshake kernel exists for CSR only
     // a rank without halo rows (n_halo == 0) runs the halo kernel on its local matrix
     const bool ghosted = (sa.fused_halo || sa.ghost_x) && ctx->have_ghosted;
     cudaStream_t st = ctx->stream;
@@ -1267,12 +1343,24 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         }
 #undef TMA_LAUNCH
     } else if (variant == 7) {
-        OGL_TRY(ell_prepare(ctx));
+        OGL_TRY(ell_prepare(ctx, ghosted));
+        if (sa.ghost_x) k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;   // all-reduce inside the launch
+        const label *e_cols = ghosted ? ctx->d_gell_cols : ctx->d_ell_cols;
+        const double *e_vals = ghosted ? ctx->d_gell_vals : ctx->d_ell_vals;
+        const int e_width = ghosted ? ctx->gell_width : ctx->ell_width;
+        const int64_t e_pitch = ghosted ? ctx->gell_pitch : ctx->ell_pitch;
         const int64_t need = ((int64_t)ctx->n + 255) / 256;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;   // resident: persistent
         const int grid = (int)(need < cap ? need : cap);
-#define ELL_LAUNCH(A, R) \
-    k_spmv_ell<A, R><<<grid, 256, 0, st>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_width, ctx->ell_pitch)
+#define ELL_LAUNCH_W(A, R, W) \
+    k_spmv_ell<A, R, W><<<grid, 256, 0, st>>>(k, e_cols, e_vals, e_width, e_pitch)
+#define ELL_LAUNCH(A, R)                                        \
+    do {                                                        \
+        if (e_width == 7) ELL_LAUNCH_W(A, R, 7);                \
+        else if (e_width == 5) ELL_LAUNCH_W(A, R, 5);           \
+        else if (e_width == 8) ELL_LAUNCH_W(A, R, 8);           \
+        else ELL_LAUNCH_W(A, R, 0);                             \
+    } while (0)
         if (sa.advanced) {
             if (nred == 0) ELL_LAUNCH(true, 0);
             else if (nred == 1) ELL_LAUNCH(true, 1);
@@ -1282,6 +1370,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
             else if (nred == 1) ELL_LAUNCH(false, 1);
             else ELL_LAUNCH(false, 2);
         }
+#undef ELL_LAUNCH_W
 #undef ELL_LAUNCH
     } else if (variant == 2) {
         const int grid = (ctx->n + 255) / 256;
@@ -1291,6 +1380,40 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         DISPATCH(k_spmv_vector, grid, 256, 0);
     }
 #undef DISPATCH
+    ctx->launches++;
+    OGL_CUDA(ctx, cudaGetLastError());
+    return OGL_OK;
+}
+
+// q = A p', p' = z + coef_p p, <p',q>, CG_BETA epilogue -- one launch (see k_spmv_ell_cgp).
+// Returns OGL_ERR_UNSUPPORTED when the fused form does not apply (caller falls back).
+int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q)
+{
+    if (ctx->n_ranks != 1 || pick_variant(ctx) != 7) return OGL_ERR_UNSUPPORTED;
+    OGL_TRY(ell_prepare(ctx, false));
+    if (ctx->ell_width != 7 && ctx->ell_width != 5) return OGL_ERR_UNSUPPORTED;
+    SpmvK k;
+    std::memset(&k, 0, sizeof(k));
+    k.x = z;
+    k.y_in = p_old;
+    k.y = q;
+    k.n = ctx->n;
+    k.mat_policy = spmv_l2_policy(ctx);
+    k.partials = ctx->d_partials;
+    k.ticket = ctx->d_ticket;
+    k.state = ctx->d_state;
+    k.epi = EPI_CG_BETA;
+    k.inline_epi = 1;
+    k.guard_done = 1;
+    k.ea = make_epi_args(ctx, 0);
+    k.ea.trace_tag = 20;
+    const int64_t need = ((int64_t)ctx->n + 255) / 256;
+    const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;
+    const int grid = (int)(need < cap ? need : cap);
+    if (ctx->ell_width == 7)
+        k_spmv_ell_cgp<7><<<grid, 256, 0, ctx->stream>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_pitch, p_new);
+    else
+        k_spmv_ell_cgp<5><<<grid, 256, 0, ctx->stream>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_pitch, p_new);
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
     return OGL_OK;
