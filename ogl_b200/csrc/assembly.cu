@@ -367,6 +367,8 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
         return fail(ctx, OGL_ERR_CUDA, std::string("pattern_from_ldu: ") + cudaGetErrorString(e));
     (void)bad;
 
+    const label n_before = ctx->n;
+    ctx->have_pattern_before = ctx->have_pattern;
     ctx->n = n;
     ctx->n_faces = nf;
     ctx->n_local_iface = n_if;
@@ -379,8 +381,10 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->gell_ready = false;
     ctx->gell_width = 0;
     ctx->have_values = false;
-    ctx->have_precond = false;
-    ctx->have_b = ctx->have_x = false;
+    // `regenerate true` rebuilds the pattern of the same mesh every solve; the reference's
+    // PersistentVector b / x survive that (lduLduBase.H:217-237), so do these
+    const bool keep_vectors = n_before == n && ctx->have_pattern_before && ctx->d_b && ctx->d_x;
+    if (!keep_vectors) ctx->have_b = ctx->have_x = ctx->have_precond = false;
     // a new local pattern invalidates the halo description built on the old one
     ctx->have_nonlocal = false;
     ctx->have_ghosted = false;
@@ -390,11 +394,13 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->n_targets = 0;
     ctx->n_send = 0;
     ctx->global_n = n;
-    ctx->n_blocks = 0;
-    ctx->bj_pattern_mbs = 0;
-    if (ctx->d_inv_diag) {
-        cudaFree(ctx->d_inv_diag);   // sized for the previous pattern
-        ctx->d_inv_diag = nullptr;
+    if (!keep_vectors) {
+        ctx->n_blocks = 0;
+        ctx->bj_pattern_mbs = 0;
+        if (ctx->d_inv_diag) {
+            cudaFree(ctx->d_inv_diag);   // sized for the previous pattern
+            ctx->d_inv_diag = nullptr;
+        }
     }
     if (ctx->graph_exec) {
         cudaGraphExecDestroy(ctx->graph_exec);
@@ -404,8 +410,10 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->staging_len = (size_t)nf * (sym ? 1 : 2) + n + n_if;
     OGL_TRY(dev_alloc(ctx, &ctx->d_staging, ctx->staging_len));
     OGL_TRY(dev_alloc(ctx, &ctx->d_vals, nnz));
-    OGL_TRY(dev_alloc(ctx, &ctx->d_b, n));
-    OGL_TRY(dev_alloc(ctx, &ctx->d_x, n));
+    if (!keep_vectors) {
+        OGL_TRY(dev_alloc(ctx, &ctx->d_b, n));
+        OGL_TRY(dev_alloc(ctx, &ctx->d_x, n));
+    }
     for (auto &w : ctx->work) {
         if (w) cudaFree(w);
         w = nullptr;
@@ -605,7 +613,8 @@ int values_update(Context *ctx, const double *diag, const double *upper,
     ctx->have_values = true;
     ctx->ell_ready = false;      // the ELL copies (if in use) are rebuilt from the new values on demand
     ctx->gell_ready = false;
-    ctx->have_precond = false;   // regenerated every solve (caching 0, Preconditioner.H:416-422)
+    // the preconditioner is NOT invalidated here: the host layer regenerates it every solve
+    // unless `caching N` keeps the (intentionally stale) one for N solves, Preconditioner.H:384-422
     return OGL_OK;
 }
 

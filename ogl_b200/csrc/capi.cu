@@ -28,6 +28,14 @@ int fail(Context *ctx, int code, const std::string &msg)
     return code;
 }
 
+void invalidate_graph(Context *ctx)
+{
+    if (ctx && ctx->graph_exec) {
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+    }
+}
+
 int upload(Context *ctx, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return OGL_OK;
@@ -313,6 +321,11 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     CHECK_CTX(ctx);
     if (!key) return fail(ctx, OGL_ERR_INVALID, "null option key");
     const std::string k(key);
+    // a cached chunk graph survives a call that does not change anything (the host layers
+    // re-apply their keywords on every solver construction, i.e. once per solve)
+    int64_t before = 0;
+    const bool known = ogl_get_option(ctx, key, &before) == OGL_OK;
+    if (known && before == value && k != "trace") return OGL_OK;
     if (k == "spmv_variant") {
         if (value < 0 || value > 7) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,7]");
         ctx->spmv_variant = value;
@@ -407,6 +420,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "max_row_len") *value = ctx->max_row_len;
     else if (k == "max_block_nnz") *value = ctx->max_block_nnz;
     else if (k == "launches") *value = ctx->launches;
+    else if (k == "precond_setups") *value = ctx->precond_setups;
     else return fail(ctx, OGL_ERR_INVALID, "unknown option: " + k);
     return OGL_OK;
 }

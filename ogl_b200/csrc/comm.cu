@@ -236,6 +236,7 @@ static int p2p_setup(Context *ctx)
     for (int q = 0; q < R; ++q) h.mbox[q] = reinterpret_cast<double *>(base_of(q) + all[q].off_mbox);
     for (int t = 0; t <= ctx->n_targets; ++t) h.send_offs[t] = ctx->send_offs[t];
     std::vector<long long> peer_block_off((size_t)ctx->n_targets, 0);   // my block inside q's recv buffer
+    int sym_ok = 1;
     for (int t = 0; t < ctx->n_targets; ++t) {
         const int q = ctx->target_ids[t];
         const Directory &dq = all[q];
@@ -243,9 +244,10 @@ static int p2p_setup(Context *ctx)
         for (int k = 0; k < dq.n_targets; ++k)
             if (dq.target_ids[k] == ctx->rank) u = k;
         if (u < 0 || dq.send_offs[u + 1] - dq.send_offs[u] != ctx->target_sizes[t]) {
-            p2p_teardown(ctx);
-            return fail(ctx, OGL_ERR_INVALID,
-                        "neighbour lists of the ranks are not symmetric (processor patches)");
+            // no rank-local return inside a collective sequence: the verdict is agreed on by
+            // the all-reduce(min) below, so that every rank leaves together
+            sym_ok = 0;
+            continue;
         }
         // my values land in the neighbour's recv block reserved for me: same offset
         // as the neighbour's own send block towards me (blocked by ascending rank)
@@ -278,12 +280,19 @@ static int p2p_setup(Context *ctx)
     // nobody may touch a window before every rank has finished zeroing/mapping
     int *d_bar = nullptr;
     OGL_TRY(dev_alloc(ctx, &d_bar, 1));
-    cudaMemsetAsync(d_bar, 0, sizeof(int), ctx->stream);
-    ncclResult_t r4 = ncclAllReduce(d_bar, d_bar, 1, ncclInt, ncclSum, ctx->comm, ctx->stream);
+    cudaMemcpyAsync(d_bar, &sym_ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r4 = ncclAllReduce(d_bar, d_bar, 1, ncclInt, ncclMin, ctx->comm, ctx->stream);
+    int sym_all = 0;
+    cudaMemcpyAsync(&sym_all, d_bar, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_bar);
     if (r4 != ncclSuccess || e != cudaSuccess)
         return fail(ctx, OGL_ERR_NCCL, "window bootstrap: final barrier failed");
+    if (!sym_all) {
+        p2p_teardown(ctx);
+        return fail(ctx, OGL_ERR_INVALID,
+                    "neighbour lists of the ranks are not symmetric (processor patches)");
+    }
     ctx->p2p_ready = true;
     return OGL_OK;
 }

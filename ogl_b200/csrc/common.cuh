@@ -110,7 +110,7 @@ struct Context {
 
     // local pattern (a4/a5) -- resident across solves
     label n = 0, n_faces = 0, n_local_iface = 0;
-    bool symmetric = true, have_pattern = false;
+    bool symmetric = true, have_pattern = false, have_pattern_before = false;
     int64_t nnz = 0;
     label *d_rows = nullptr, *d_cols = nullptr, *d_map = nullptr, *d_row_ptrs = nullptr;
     label max_row_len = 0;
@@ -227,6 +227,7 @@ struct Context {
     unsigned long long cond_handle = 0;   // cudaGraphConditionalHandle while the loop body is captured
 
     int64_t launches = 0;
+    int64_t precond_setups = 0;   // ogl_precond_setup calls (tests of the `caching` keyword)
 
     // sampled SpMV timing inside the solve loop (profile_stride > 0)
     std::vector<cudaEvent_t> profile_events;
@@ -257,10 +258,15 @@ inline cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaSt
 }
 
 // memory helpers ---------------------------------------------------------------
+void invalidate_graph(Context *ctx);
+
+// (Re)allocate a device buffer.  Replacing a live buffer drops the cached chunk graph: its
+// kernel nodes hold the old address (residual history, block-Jacobi arrays, halo patterns ...).
 template <typename T>
 int dev_alloc(Context *ctx, T **p, size_t count)
 {
     if (*p) {
+        invalidate_graph(ctx);
         cudaFree(*p);
         *p = nullptr;
     }

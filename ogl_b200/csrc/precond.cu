@@ -172,6 +172,7 @@ int precond_setup(Context *ctx, int kind, label mbs)
     ctx->precond_kind = kind;
     ctx->max_block_size = mbs;
     ctx->have_precond = true;
+    ctx->precond_setups++;
     if (kind == OGL_PRECOND_NONE || ctx->n == 0) return OGL_OK;
     cudaStream_t st = ctx->stream;
     const label n = ctx->n;

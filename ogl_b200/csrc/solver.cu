@@ -673,6 +673,7 @@ int init_state(Context *ctx, const ogl_solve_params *p)
     if (p->export_res) {
         const int cap = p->max_iter + 2;
         if (cap > ctx->history_cap) {
+            invalidate_graph(ctx);   // a chunk captured without history holds a null pointer
             OGL_TRY(dev_alloc(ctx, &ctx->d_history, cap));
             ctx->history_cap = cap;
         }

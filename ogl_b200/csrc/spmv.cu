@@ -1130,7 +1130,9 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
 {
     if (!ctx->have_pattern || !ctx->have_values)
         return fail(ctx, OGL_ERR_INVALID, "SpMV without assembled matrix");
-    if (ctx->n == 0) return OGL_OK;
+    // an empty rank of a decomposed case still launches: the kernel carries the halo
+    // handshake and the all-reduce its peers are waiting in
+    if (ctx->n == 0 && ctx->n_ranks == 1) return OGL_OK;
     SpmvK k;
     k.row_ptrs = ctx->d_row_ptrs;
     k.cols = ctx->d_cols;
@@ -1190,7 +1192,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
         k.n_row_blocks = nblk;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
-        const int grid = nblk < cap ? nblk : (int)cap;
+        const int grid = nblk < 1 ? 1 : (nblk < cap ? nblk : (int)cap);
 #define STREAM_LAUNCH(H)                                                                          \
     do {                                                                                          \
         if (sa.advanced) {                                                                        \
@@ -1242,7 +1244,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         const int nblk = (ctx->n + kRowsPerBlock - 1) / kRowsPerBlock;
         k.n_row_blocks = nblk;
         const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kStreamCtasPerSM;
-        const int grid = nblk < cap ? nblk : (int)cap;
+        const int grid = nblk < 1 ? 1 : (nblk < cap ? nblk : (int)cap);
 #define PIPE_ONE(A, R, H) \
     launch_pdl(k_spmv_pipe<A, R, H>, grid, kStreamThreads, smem, st, ctx->use_pdl != 0 && sa.guard_done, k)
 #define PIPE_LAUNCH(H)                                                      \

@@ -133,11 +133,14 @@ class GKOlduBaseSolver:
         fmt = str(controls.get("matrixFormat", "Coo"))
         if fmt not in ("Coo", "Csr", "Ell"):
             raise FatalError(f"unknown matrixFormat {fmt}\nValid choices are: Coo, Csr, Ell")
-        self.ctx.set_option("spmv_variant", 7 if fmt == "Ell" else 0)
+        # one set_option per key with its final value: an unchanged value keeps the cached chunk graph
+        opts = {"spmv_variant": 7 if fmt == "Ell" else 0}
         for opt in ("spmv_variant", "chunk_iters", "use_graph", "comm_mode", "fused_halo", "ghost_p",
-                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb", "ell_auto"):
+                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb", "ell_auto", "fuse_p"):
             if opt in controls:
-                self.ctx.set_option(opt, int(controls[opt]))
+                opts[opt] = int(controls[opt])
+        for opt, val in opts.items():
+            self.ctx.set_option(opt, val)
         # preconditioner keyword: word or sub-dict (Preconditioner.H:363-382)
         pre = controls.get("preconditioner")
         if pre is None:

@@ -354,3 +354,54 @@ def test_solve_call_order_errors(ctx):
     ctx.pattern_from_ldu(s.n, s.lower_addr, s.upper_addr, True)
     with pytest.raises(OglError):
         ctx.solve(L.OGL_SOLVER_CG)          # no values / vectors yet
+
+
+def test_preconditioner_caching_keyword(oracle):
+    """`preconditioner { caching N }` reuses the (stale) preconditioner for N solves while the matrix
+    values are refreshed (Preconditioner.H:384-422); ADVICE r1: this used to abort the second solve."""
+    db = ObjectRegistry()
+    controls = {"solver": "GKOCG", "executor": "cuda", "tolerance": 1e-8, "relTol": 0.0,
+                "adaptMinIter": False, "updateInitGuess": True,
+                "preconditioner": {"preconditioner": "BJ", "caching": 2}}
+    s = cases.pressure_3d(16)[0]
+    setups = []
+    for step in range(4):
+        s.diag = s.diag * (1.0 + 0.05 * step)     # new coefficients every step
+        sol = lduMatrix_solver_New("p", s, controls, db)
+        before = sol.ctx.get_option("precond_setups")
+        psi = s.psi.copy()
+        perf = sol.solve(psi, s.source)
+        setups.append(sol.ctx.get_option("precond_setups") - before)
+        true_res = np.abs(sol.ctx.spmv(psi) - s.source).sum() / sol.last_result.norm_factor
+        assert true_res < 1e-8 and perf.n_iterations > 0
+    assert setups == [1, 0, 0, 1]     # generated, cached twice, regenerated
+
+
+def test_regenerate_keyword_keeps_the_device_vectors(oracle):
+    """`regenerate true` rebuilds the pattern every solve; b / x persist."""
+    db = ObjectRegistry()
+    controls = {"solver": "GKOCG", "preconditioner": "BJ", "executor": "cuda", "tolerance": 1e-8,
+                "relTol": 0.0, "adaptMinIter": False, "regenerate": True}
+    s = cases.pressure_3d(16)[0]
+    psi = s.psi.copy()
+    p1 = lduMatrix_solver_New("p", s, controls, db).solve(psi, s.source)
+    # second solve of the same system: x0 = previous device solution -> converged at once
+    psi2 = np.zeros(s.n)
+    p2 = lduMatrix_solver_New("p", s, controls, db).solve(psi2, s.source)
+    assert p1.n_iterations > 10 and p2.n_iterations <= 2
+    assert rel_l2(psi2, psi) < 1e-7
+
+
+def test_export_after_a_cached_graph(ctx, oracle):
+    """A chunk graph captured without residual history must not be replayed with it."""
+    s = cases.pressure_3d(16)[0]
+    upload_system(ctx, s, partition=False)
+    ctx.set_option("fused_pcg", 0)
+    r0, _ = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-8)
+    for max_iter in (1000, 3000):     # the second one reallocates the history buffer
+        ctx.vector_upload(L.OGL_VEC_X, s.psi)
+        r1, _ = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-8, export_res=True, max_iter=max_iter)
+        h = ctx.residual_history(4096)
+        assert r1.n_iterations == r0.n_iterations
+        assert len(h) == r1.criterion_calls and h[-1] == r1.final_residual and np.all(h > 0)
+    ctx.set_option("fused_pcg", 2)
