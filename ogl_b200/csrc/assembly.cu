@@ -376,10 +376,7 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->nnz = nnz;
     ctx->max_row_len = max_len;
     ctx->have_pattern = true;
-    ctx->ell_ready = false;
-    ctx->ell_width = 0;
-    ctx->gell_ready = false;
-    ctx->gell_width = 0;
+    ell_invalidate(ctx, /*structure=*/true);
     ctx->have_values = false;
     // `regenerate true` rebuilds the pattern of the same mesh every solve; the reference's
     // PersistentVector b / x survive that (lduLduBase.H:217-237), so do these
@@ -480,7 +477,7 @@ static int build_ghosted(Context *ctx)
         return fail(ctx, OGL_ERR_CUDA, std::string("build_ghosted: ") + cudaGetErrorString(e));
     ctx->max_block_nnz_g = mx;
     ctx->max_row_len_g = mx_row;
-    ctx->gell_ready = false;
+    ctx->gell.structure_ready = ctx->gell.ready = false;
     ctx->have_ghosted = true;
     return OGL_OK;
 }
@@ -611,8 +608,7 @@ int values_update(Context *ctx, const double *diag, const double *upper,
     }
     OGL_CUDA(ctx, cudaGetLastError());
     ctx->have_values = true;
-    ctx->ell_ready = false;      // the ELL copies (if in use) are rebuilt from the new values on demand
-    ctx->gell_ready = false;
+    ell_invalidate(ctx, /*structure=*/false);   // the ELL copies (if in use) take the new values on demand
     // the preconditioner is NOT invalidated here: the host layer regenerates it every solve
     // unless `caching N` keeps the (intentionally stale) one for N solves, Preconditioner.H:384-422
     return OGL_OK;

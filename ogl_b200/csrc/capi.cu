@@ -136,8 +136,9 @@ static void destroy(Context *c)
                     c->d_inv_diag,   c->d_block_ptrs, c->d_row_block,  c->d_block_offs,
                     c->d_inv_blocks, c->d_partials,   c->d_ticket,     c->d_state,
                     c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
-                    c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar,        c->d_ell_cols,
-                    c->d_ell_vals,   c->d_gell_cols,  c->d_gell_vals};
+                    c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar,
+                    c->ell.cols,     c->ell.vals,     c->ell.code,     c->ell.ptab,
+                    c->gell.cols,    c->gell.vals,    c->gell.code,    c->gell.ptab};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)
@@ -350,6 +351,10 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->fuse_p = value != 0;
     } else if (k == "ell_auto") {
         ctx->ell_auto = value != 0;
+    } else if (k == "ell_coded") {
+        if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "ell_coded in {0,1,2}");
+        ctx->ell_coded = value;
+        ell_invalidate(ctx, /*structure=*/true);
     } else if (k == "device_loop") {
         ctx->device_loop = value != 0;
     } else if (k == "loop_iters") {
@@ -408,6 +413,12 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "fused_pcg") *value = ctx->fused_pcg;
     else if (k == "device_loop") *value = ctx->device_loop;
     else if (k == "ell_auto") *value = ctx->ell_auto;
+    else if (k == "ell_coded") *value = ctx->ell_coded;
+    else if (k == "ell_coded_active") *value = (ctx->ell.coded ? 1 : 0) | (ctx->gell.coded ? 2 : 0);
+    else if (k == "ell_patterns") *value = ctx->ell.n_patterns;
+    else if (k == "ell_escape_rows") *value = ctx->ell.n_escape;
+    else if (k == "gell_patterns") *value = ctx->gell.n_patterns;
+    else if (k == "gell_escape_rows") *value = ctx->gell.n_escape;
     else if (k == "fuse_p") *value = ctx->fuse_p;
     else if (k == "spmv_variant_in_use") *value = spmv_variant_in_use(ctx);
     else if (k == "loop_iters") *value = ctx->loop_iters;

@@ -114,22 +114,27 @@ struct Context {
     int64_t nnz = 0;
     label *d_rows = nullptr, *d_cols = nullptr, *d_map = nullptr, *d_row_ptrs = nullptr;
     label max_row_len = 0;
-    // ELL copy of the local matrix (spmv_variant 7 / `matrixFormat Ell`): slot j of row r at [j * pitch + r]
-    label *d_ell_cols = nullptr;
-    double *d_ell_vals = nullptr;
-    int64_t ell_pitch = 0;
-    int ell_width = 0;
-    bool ell_ready = false;
-    // ... and of the ghosted matrix (several ranks, CG ghost-p mode)
-    label *d_gell_cols = nullptr;
-    double *d_gell_vals = nullptr;
-    int64_t gell_pitch = 0;
-    int gell_width = 0;
-    bool gell_ready = false;
+    // ELL copies (spmv_variant 7 / `matrixFormat Ell`, ell.cu): `ell` of the local matrix, `gell` of
+    // the ghosted one (several ranks, CG ghost-p mode)
+    struct EllMatrix {
+        label *cols = nullptr;        // slot j of row r at [j * pitch + r], -1 = padding
+        double *vals = nullptr;
+        int64_t pitch = 0;
+        int width = 0;
+        bool structure_ready = false; // cols / codes match the current pattern
+        bool ready = false;           // vals match the current coefficients
+        // pattern-coded columns: rows whose (column - row) tuple is one of <= 255 distinct
+        // patterns carry a 1-byte code instead of `width` 4-byte columns
+        unsigned char *code = nullptr;   // [pitch], 255 = escape: read `cols`
+        label *ptab = nullptr;           // [256 * width] deltas, kPadDelta = no entry
+        int n_patterns = 0;
+        int64_t n_escape = 0;
+        bool coded = false;
+    } ell, gell;
     label max_row_len_g = 0;     // longest row of the ghosted CSR
-    int64_t fuse_p = 0;          // CG: p-update fused into the ELL SpMV (spmv.cu:k_spmv_ell_cgp), one rank
-    int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernel (spmv.cu:pick_variant); off: the
-                                 // fused-dot ELL instantiation is slower than the CSR one (r01_ell_probe.jsonl)
+    int64_t ell_coded = 1;       // 0 off, 1 auto (when <= 25% of the rows escape), 2 whenever a table exists
+    int64_t fuse_p = 1;          // CG: p-update fused into the ELL SpMV (ell.cu:k_spmv_ell_cgp)
+    int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernels (spmv.cu:pick_variant)
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
     int64_t max_warp_nnz = 0;    // warp-tile kernel: max nnz of 32 consecutive rows
 
@@ -313,7 +318,8 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
                   const double *dot_with, int nred, bool guard_done, int epi,
                   bool inline_epi);
 int spmv_setup(Context *ctx);
-int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q);
+int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q, bool ghost);
+void ell_invalidate(Context *ctx, bool structure);
 
 // comm.cu ------------------------------------------------------------------------
 int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,

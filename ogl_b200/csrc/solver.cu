@@ -517,12 +517,25 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
     const double *zz = pk == 0 ? r_old : z;   // the residual this iteration starts from
     const bool ghost = ghost_p_mode(ctx);
     const bool pack = !ghost && fused_halo_ok(ctx) && ctx->n_send > 0;
+    // profile_stride > 0 (graphs off): bracket every stride-th SpMV of the real loop with CUDA
+    // events on the launching stream
+    const bool sample = ctx->profile_stride > 0 && !ctx->capturing &&
+                        (ctx->profile_iter++ % ctx->profile_stride) == 0 &&
+                        ctx->profile_used + 2 <= (int)ctx->profile_events.size();
     bool fused_p = false;
-    if (ctx->fuse_p && ctx->n_ranks == 1 && ctx->profile_stride == 0) {
-        // p-update inside the ELL SpMV: one launch instead of two
-        const int rc = spmv_ell_cgp(ctx, zz, p_old, p, q);
-        if (rc == OGL_OK) fused_p = true;
-        else if (rc != OGL_ERR_UNSUPPORTED) return rc;
+    if (ctx->fuse_p && (ctx->n_ranks == 1 || ghost)) {
+        // p-update inside the ELL SpMV (ell.cu): two launches per iteration instead of three
+        if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used], ctx->stream);
+        const int rc = spmv_ell_cgp(ctx, zz, p_old, p, q, ghost);
+        if (rc == OGL_OK) {
+            fused_p = true;
+            if (sample) {
+                cudaEventRecord(ctx->profile_events[ctx->profile_used + 1], ctx->stream);
+                ctx->profile_used += 2;
+            }
+        } else if (rc != OGL_ERR_UNSUPPORTED) {
+            return rc;
+        }
     }
     if (!fused_p) {
     {
@@ -547,11 +560,6 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
         s.epi = EPI_CG_BETA;
         s.halo_stored = pack;
         s.ghost_x = ghost;
-        // profile_stride > 0 (graphs off): bracket every stride-th SpMV of the real
-        // loop with CUDA events on the launching stream
-        const bool sample = ctx->profile_stride > 0 && !ctx->capturing &&
-                            (ctx->profile_iter++ % ctx->profile_stride) == 0 &&
-                            ctx->profile_used + 2 <= (int)ctx->profile_events.size();
         if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);
         OGL_TRY(dist_spmv(ctx, s));
         if (sample) cudaEventRecord(ctx->profile_events[ctx->profile_used++], ctx->stream);

@@ -38,6 +38,7 @@
 
 #include "common.cuh"
 #include "reduce.cuh"
+#include "spmv.cuh"
 
 namespace ogl {
 
@@ -49,52 +50,7 @@ constexpr int kBatchStream = 7;      // stream kernel: 48-register budget (5 CTA
 constexpr int kStreamCtasPerSM = 5;  // <= 51 registers per thread
 constexpr int kMaxTilesPerCta = 1024; // row-block extents cached in shared memory
 
-struct SpmvK {
-    const label *row_ptrs;
-    const label *cols;
-    const double *vals;
-    const double *x;
-    const double *y_in;   // advanced: y = alpha*A*x + beta*y_in
-    double *y;
-    label n;
-    label n_row_blocks;   // stream kernel: ceil(n / kRowsPerBlock)
-    int blocked;          // 1: each CTA walks a CONTIGUOUS range of tiles (x reuse in L1)
-    unsigned long long mat_policy;   // L2 cache policy of the (column, value) stream, see l2_policy()
-    double alpha, beta;
-    const double *dot_with;
-    double *partials;
-    unsigned int *ticket;
-    SolveState *state;
-    int epi, inline_epi, guard_done;
-    EpiArgs ea;
-};
-
 namespace {
-
-__device__ __forceinline__ double prod_of(double v, double xv, double alpha, bool adv)
-{
-    // reference kernels: `alpha * val * b` (advanced) or `val * b`
-    return adv ? __dmul_rn(__dmul_rn(alpha, v), xv) : __dmul_rn(v, xv);
-}
-
-
-// (column, value) stream of the pipelined kernel: read-only path, no L1
-// allocation, L2 priority from the policy the host picked -- evict-first for a
-// matrix much larger than L2, evict-last (for all or an address-hashed fraction
-// of the lines) when that share of the matrix can stay L2-resident from one
-// Krylov iteration to the next.
-__device__ __forceinline__ label ld_mat(const label *p, unsigned long long pol)
-{
-    label r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ double ld_mat(const double *p, unsigned long long pol)
-{
-    double r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
-    return r;
-}
 
 // x operand of one entry.  HALO (ghosted CSR, multi-GPU): columns >= n address
 // the receive window the neighbours store into over NVLink -- read with a
@@ -820,133 +776,6 @@ __global__ void __launch_bounds__(256) k_spmv_nonlocal(const NonLocalK a)
                                            a.inline_epi != 0, a.ea, /*accumulate=*/true);
 }
 
-// ---------------------------------------------------------------------------
-// Variant 7: ELL (`matrixFormat Ell`).  Slot j of row r lives at [j * pitch + r],
-// so a warp reads 32 consecutive columns / values per slot and gathers x from
-// (for a stencil) 32 consecutive addresses; no row pointers, no shared memory,
-// no barrier.  Slots are added left to right in the row's CSR order and padding
-// slots (column -1) are skipped: bit-identical to the CSR kernels.
-// ---------------------------------------------------------------------------
-constexpr int kEllBatch = 8;
-
-__global__ void k_ell_build(label n, const label *__restrict__ row_ptrs, const label *__restrict__ cols,
-                            const double *__restrict__ vals, int width, int64_t pitch,
-                            label *__restrict__ ell_cols, double *__restrict__ ell_vals)
-{
-    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (row >= n) return;
-    const label rs = row_ptrs[row], len = row_ptrs[row + 1] - rs;
-    for (int j = 0; j < width; ++j) {
-        ell_cols[j * pitch + row] = j < len ? cols[rs + j] : -1;
-        ell_vals[j * pitch + row] = j < len ? vals[rs + j] : 0.0;
-    }
-}
-
-// W > 0: compile-time row width.  With the run-time slot loop (W == 0) ptxas peels the first
-// two slots of the instantiation with the fused dot and puts their DMUL/DADD between the loads,
-// so an in-order warp waits two extra memory round trips per row; with the width known all
-// 3 W loads of a row are issued before the first dependent instruction (cuobjdump -sass).
-template <bool ADV, int NRED, int W>
-__global__ void __launch_bounds__(256, 4)
-k_spmv_ell(const SpmvK a, const label *__restrict__ ell_cols, const double *__restrict__ ell_vals,
-           int width, int64_t pitch)
-{
-    if (a.guard_done && a.state->done) return;
-    double red[NRED > 0 ? NRED : 1];
-#pragma unroll
-    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
-        // everything the row needs is requested up front: a warp issues in order, so a load
-        // placed behind the row sum would add its whole latency to every trip
-        double dw = 0.0;
-        if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
-        double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
-        if (W > 0) {
-            label c[W > 0 ? W : 1];
-            double v[W > 0 ? W : 1], xv[W > 0 ? W : 1];
-#pragma unroll
-            for (int u = 0; u < W; ++u) c[u] = ld_mat(&ell_cols[u * pitch + row], a.mat_policy);
-#pragma unroll
-            for (int u = 0; u < W; ++u) v[u] = ld_mat(&ell_vals[u * pitch + row], a.mat_policy);
-#pragma unroll
-            for (int u = 0; u < W; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
-#pragma unroll
-            for (int u = 0; u < W; ++u)
-                if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
-        } else {
-            for (int j0 = 0; j0 < width; j0 += kEllBatch) {
-                label c[kEllBatch];
-                double v[kEllBatch], xv[kEllBatch];
-#pragma unroll
-                for (int u = 0; u < kEllBatch; ++u)
-                    c[u] = j0 + u < width ? ld_mat(&ell_cols[(j0 + u) * pitch + row], a.mat_policy) : -1;
-#pragma unroll
-                for (int u = 0; u < kEllBatch; ++u)
-                    v[u] = j0 + u < width ? ld_mat(&ell_vals[(j0 + u) * pitch + row], a.mat_policy) : 0.0;
-#pragma unroll
-                for (int u = 0; u < kEllBatch; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
-#pragma unroll
-                for (int u = 0; u < kEllBatch; ++u)
-                    if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
-            }
-        }
-        a.y[row] = sum;
-        if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
-        if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
-    }
-    if (NRED > 0)
-        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
-                                           a.inline_epi != 0, a.ea);
-}
-
-// ---------------------------------------------------------------------------
-// CG step_1 fused into the ELL SpMV (option fuse_p, one rank): instead of
-// gathering p' the kernel gathers z and p and forms p' = z + (rho/rho_prev) p
-// for every operand on the fly -- the same two operations the p-update kernel
-// would perform on the same two numbers, hence the same bits -- and the owner of
-// a row writes p'[row] (its diagonal slot) for the x/r-update and the next
-// iteration.  One launch and 8 B/row of HBM traffic less per iteration; the
-// price is a second (coalesced, cache-resident) gather per slot.
-//   x = z (or r), y_in = p (previous), y = q, p_new = the other p buffer
-// ---------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(256, 4)
-k_spmv_ell_cgp(const SpmvK a, const label *__restrict__ ell_cols, const double *__restrict__ ell_vals,
-               int64_t pitch, double *__restrict__ p_new)
-{
-    if (a.guard_done && a.state->done) return;
-    const bool p_is_z = a.state->flag_p_is_z != 0;
-    const double t = a.state->coef_p;
-    double red[1] = {0.0};
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
-        label c[W];
-        double v[W], zc[W], pc[W];
-#pragma unroll
-        for (int u = 0; u < W; ++u) c[u] = ld_mat(&ell_cols[u * pitch + row], a.mat_policy);
-#pragma unroll
-        for (int u = 0; u < W; ++u) v[u] = ld_mat(&ell_vals[u * pitch + row], a.mat_policy);
-#pragma unroll
-        for (int u = 0; u < W; ++u) zc[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < W; ++u) pc[u] = (c[u] >= 0 && !p_is_z) ? __ldg(&a.y_in[c[u]]) : 0.0;
-        double sum = 0.0, mine = 0.0;
-#pragma unroll
-        for (int u = 0; u < W; ++u) {
-            if (c[u] >= 0) {
-                const double pv = p_is_z ? zc[u] : __dadd_rn(zc[u], __dmul_rn(t, pc[u]));
-                if (c[u] == (label)row) mine = pv;   // the diagonal slot: my own p'
-                sum = __dadd_rn(sum, __dmul_rn(v[u], pv));
-            }
-        }
-        p_new[row] = mine;
-        a.y[row] = sum;
-        red[0] = __dadd_rn(red[0], __dmul_rn(mine, sum));
-    }
-    grid_reduce<1>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
-}
-
 __global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int rows_per_block,
                                 int *out)
 {
@@ -1091,40 +920,6 @@ static int pick_variant(const Context *ctx)
 }
 
 int spmv_variant_in_use(const Context *ctx) { return pick_variant(ctx); }
-
-// (re)build the ELL copy from the current CSR values; never inside a graph capture
-static int ell_prepare(Context *ctx, bool ghosted)
-{
-    bool &ready = ghosted ? ctx->gell_ready : ctx->ell_ready;
-    if (ready) return OGL_OK;
-    if (ctx->capturing) return fail(ctx, OGL_ERR_INVALID, "ELL matrix not built before the graph capture");
-    const int width = (int)(ghosted ? ctx->max_row_len_g : ctx->max_row_len);
-    const int64_t nnz = ghosted ? ctx->nnz + ctx->n_halo : ctx->nnz;
-    if (width < 1 || width > 64 || (int64_t)width * ctx->n > 3 * nnz)
-        return fail(ctx, OGL_ERR_UNSUPPORTED, "rows too long or too irregular for the ELL format");
-    const int64_t pitch = ((int64_t)ctx->n + 31) / 32 * 32;
-    label *&cols = ghosted ? ctx->d_gell_cols : ctx->d_ell_cols;
-    double *&vals = ghosted ? ctx->d_gell_vals : ctx->d_ell_vals;
-    int &w = ghosted ? ctx->gell_width : ctx->ell_width;
-    int64_t &pt = ghosted ? ctx->gell_pitch : ctx->ell_pitch;
-    if (w != width || pt != pitch || !cols) {
-        OGL_TRY(dev_alloc(ctx, &cols, (size_t)(width * pitch)));
-        OGL_TRY(dev_alloc(ctx, &vals, (size_t)(width * pitch)));
-        w = width;
-        pt = pitch;
-        if (ctx->graph_exec) {   // a captured chunk holds the old addresses
-            cudaGraphExecDestroy(ctx->graph_exec);
-            ctx->graph_exec = nullptr;
-        }
-    }
-    k_ell_build<<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(
-        ctx->n, ghosted ? ctx->d_g_row_ptrs : ctx->d_row_ptrs, ghosted ? ctx->d_g_cols : ctx->d_cols,
-        ghosted ? ctx->d_g_vals : ctx->d_vals, width, pitch, cols, vals);
-    ctx->launches++;
-    OGL_CUDA(ctx, cudaGetLastError());
-    ready = true;
-    return OGL_OK;
-}
 
 int spmv_local(Context *ctx, const SpmvArgs &sa)
 {
@@ -1345,35 +1140,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         }
 #undef TMA_LAUNCH
     } else if (variant == 7) {
-        OGL_TRY(ell_prepare(ctx, ghosted));
-        if (sa.ghost_x) k.ea = make_epi_args(ctx, nred), k.ea.trace_tag = 20;   // all-reduce inside the launch
-        const label *e_cols = ghosted ? ctx->d_gell_cols : ctx->d_ell_cols;
-        const double *e_vals = ghosted ? ctx->d_gell_vals : ctx->d_ell_vals;
-        const int e_width = ghosted ? ctx->gell_width : ctx->ell_width;
-        const int64_t e_pitch = ghosted ? ctx->gell_pitch : ctx->ell_pitch;
-        const int64_t need = ((int64_t)ctx->n + 255) / 256;
-        const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;   // resident: persistent
-        const int grid = (int)(need < cap ? need : cap);
-#define ELL_LAUNCH_W(A, R, W) \
-    k_spmv_ell<A, R, W><<<grid, 256, 0, st>>>(k, e_cols, e_vals, e_width, e_pitch)
-#define ELL_LAUNCH(A, R)                                        \
-    do {                                                        \
-        if (e_width == 7) ELL_LAUNCH_W(A, R, 7);                \
-        else if (e_width == 5) ELL_LAUNCH_W(A, R, 5);           \
-        else if (e_width == 8) ELL_LAUNCH_W(A, R, 8);           \
-        else ELL_LAUNCH_W(A, R, 0);                             \
-    } while (0)
-        if (sa.advanced) {
-            if (nred == 0) ELL_LAUNCH(true, 0);
-            else if (nred == 1) ELL_LAUNCH(true, 1);
-            else ELL_LAUNCH(true, 2);
-        } else {
-            if (nred == 0) ELL_LAUNCH(false, 0);
-            else if (nred == 1) ELL_LAUNCH(false, 1);
-            else ELL_LAUNCH(false, 2);
-        }
-#undef ELL_LAUNCH_W
-#undef ELL_LAUNCH
+        OGL_TRY(spmv_ell(ctx, k, sa, ghosted));
+        return OGL_OK;
     } else if (variant == 2) {
         const int grid = (ctx->n + 255) / 256;
         DISPATCH(k_spmv_scalar, grid, 256, 0);
@@ -1382,40 +1150,6 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         DISPATCH(k_spmv_vector, grid, 256, 0);
     }
 #undef DISPATCH
-    ctx->launches++;
-    OGL_CUDA(ctx, cudaGetLastError());
-    return OGL_OK;
-}
-
-// q = A p', p' = z + coef_p p, <p',q>, CG_BETA epilogue -- one launch (see k_spmv_ell_cgp).
-// Returns OGL_ERR_UNSUPPORTED when the fused form does not apply (caller falls back).
-int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q)
-{
-    if (ctx->n_ranks != 1 || pick_variant(ctx) != 7) return OGL_ERR_UNSUPPORTED;
-    OGL_TRY(ell_prepare(ctx, false));
-    if (ctx->ell_width != 7 && ctx->ell_width != 5) return OGL_ERR_UNSUPPORTED;
-    SpmvK k;
-    std::memset(&k, 0, sizeof(k));
-    k.x = z;
-    k.y_in = p_old;
-    k.y = q;
-    k.n = ctx->n;
-    k.mat_policy = spmv_l2_policy(ctx);
-    k.partials = ctx->d_partials;
-    k.ticket = ctx->d_ticket;
-    k.state = ctx->d_state;
-    k.epi = EPI_CG_BETA;
-    k.inline_epi = 1;
-    k.guard_done = 1;
-    k.ea = make_epi_args(ctx, 0);
-    k.ea.trace_tag = 20;
-    const int64_t need = ((int64_t)ctx->n + 255) / 256;
-    const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * 4;
-    const int grid = (int)(need < cap ? need : cap);
-    if (ctx->ell_width == 7)
-        k_spmv_ell_cgp<7><<<grid, 256, 0, ctx->stream>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_pitch, p_new);
-    else
-        k_spmv_ell_cgp<5><<<grid, 256, 0, ctx->stream>>>(k, ctx->d_ell_cols, ctx->d_ell_vals, ctx->ell_pitch, p_new);
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
     return OGL_OK;

@@ -405,3 +405,26 @@ def test_export_after_a_cached_graph(ctx, oracle):
         assert r1.n_iterations == r0.n_iterations
         assert len(h) == r1.criterion_calls and h[-1] == r1.final_residual and np.all(h > 0)
     ctx.set_option("fused_pcg", 2)
+
+
+@pytest.mark.parametrize("precond", ["none", "BJ"])
+def test_cg_p_update_fused_into_the_spmv_is_bit_identical(ctx, oracle, precond):
+    """fuse_p: the ELL SpMV forms p' = z + beta p per operand itself (two launches per iteration);
+    same operations on the same operands -> same bits as the three-kernel iteration."""
+    s = cases.pressure_3d(24)[0]
+    out = {}
+    for fuse_p, coded in ((0, 0), (1, 0), (1, 1)):
+        upload_system(ctx, s, partition=False)
+        for k, v in (("spmv_variant", 7), ("fused_pcg", 0), ("fuse_p", fuse_p), ("ell_coded", coded)):
+            ctx.set_option(k, v)
+        r, x = gpu_solve(ctx, "GKOCG", precond, tolerance=1e-9)
+        out[(fuse_p, coded)] = (r.n_iterations, r.final_residual, x, r.kernel_launches)
+    base = out[(0, 0)]
+    for key in ((1, 0), (1, 1)):
+        assert out[key][0] == base[0] and out[key][1] == base[1]
+        assert np.array_equal(out[key][2], base[2])
+        assert out[key][3] < base[3]          # one launch less per iteration
+    o = oracle.solve([oracle.assemble(s)], "GKOCG", precond, tolerance=1e-9)
+    assert abs(base[0] - o.n_iterations) <= ITER_TOL and rel_l2(base[2], o.x[0]) <= L2_TOL
+    for k, v in (("spmv_variant", 0), ("fused_pcg", 2), ("fuse_p", 1), ("ell_coded", 1)):
+        ctx.set_option(k, v)

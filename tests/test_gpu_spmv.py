@@ -101,3 +101,57 @@ def test_spmv_bench_entry_point(ctx):
     upload_system(ctx, s, partition=False)
     assert ctx.spmv_bench(5) > 0
     assert ctx.spmv_bench(5, fused_dot=True) > 0
+
+
+@pytest.mark.parametrize("builder,patterns", [(lambda: cases.pressure_3d(20)[0], 27),
+                                              (lambda: cases.momentum_3d(17)[0], 27),
+                                              (lambda: cases.cavity_2d((1, 1, 1))[0], 9),
+                                              (lambda: cases.channel((16, 8, 8), (1, 1, 1))[0], None)])
+def test_ell_pattern_coded_columns(ctx, oracle, builder, patterns):
+    """ELL with 1-byte row-pattern codes instead of 4-byte columns: same bits as plain ELL and as
+    the oracle; a structured box has 27 (3-D) / 9 (2-D) distinct (column - row) tuples."""
+    s = builder()
+    x = np.random.default_rng(5).normal(size=s.n)
+    ys = {}
+    for coded in (0, 1):
+        upload_system(ctx, s, partition=False)
+        ctx.set_option("spmv_variant", 7)
+        ctx.set_option("ell_coded", coded)
+        ys[coded] = ctx.spmv(x)
+        assert (ctx.get_option("ell_coded_active") & 1) == coded
+        if coded:
+            assert ctx.get_option("ell_escape_rows") == 0
+            if patterns is not None:
+                assert ctx.get_option("ell_patterns") == patterns
+    assert np.array_equal(ys[0], ys[1])
+    assert np.array_equal(ys[1], oracle.dist_spmv([oracle.assemble(s)], [x])[0])
+    ctx.set_option("spmv_variant", 0)
+    ctx.set_option("ell_coded", 1)
+
+
+def test_ell_codes_fall_back_on_an_unstructured_pattern(ctx, oracle):
+    """> 255 distinct tuples: the rows beyond the table escape to their 4-byte columns; with most
+    rows escaping the format stays plain ELL.  Either way the result is the oracle's."""
+    from conftest import random_ldu_mesh
+    rng = np.random.default_rng(11)
+    n = 2500
+    lower, upper = random_ldu_mesh(rng, n, 1200)
+    ctx.pattern_from_ldu(n, lower, upper, True)
+    if ctx.get_option("max_row_len") > 8:
+        pytest.skip("random mesh drew a row longer than the tuple table holds")
+    diag, up = rng.uniform(4, 5, n), rng.normal(size=lower.size)
+    x = rng.normal(size=n)
+    ref = diag * x
+    np.add.at(ref, lower, up * x[upper])
+    np.add.at(ref, upper, up * x[lower])
+    for coded in (1, 2):
+        ctx.pattern_from_ldu(n, lower, upper, True)
+        ctx.values_update(diag, up)
+        ctx.set_option("spmv_variant", 7)
+        ctx.set_option("ell_coded", coded)
+        y = ctx.spmv(x)
+        assert np.allclose(y, ref, rtol=1e-12, atol=1e-12)
+        assert ctx.get_option("ell_escape_rows") > n // 4
+        assert (ctx.get_option("ell_coded_active") & 1) == (1 if coded == 2 else 0)
+    ctx.set_option("spmv_variant", 0)
+    ctx.set_option("ell_coded", 1)
