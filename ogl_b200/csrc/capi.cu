@@ -351,6 +351,15 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->fuse_p = value != 0;
     } else if (k == "ell_auto") {
         ctx->ell_auto = value != 0;
+    } else if (k == "ell_chunk") {
+        if (value < 1 || value > 4096) return fail(ctx, OGL_ERR_INVALID, "ell_chunk in [1,4096]");
+        ctx->ell_chunk = value;
+    } else if (k == "ell_minb") {
+        if (value < 3 || value > 4) return fail(ctx, OGL_ERR_INVALID, "ell_minb in {3,4}");
+        ctx->ell_minb = value;
+    } else if (k == "ell_minb_cgp") {
+        if (value < 2 || value > 4) return fail(ctx, OGL_ERR_INVALID, "ell_minb_cgp in {2,3,4}");
+        ctx->ell_minb_cgp = value;
     } else if (k == "ell_coded") {
         if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "ell_coded in {0,1,2}");
         ctx->ell_coded = value;
@@ -414,6 +423,9 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "device_loop") *value = ctx->device_loop;
     else if (k == "ell_auto") *value = ctx->ell_auto;
     else if (k == "ell_coded") *value = ctx->ell_coded;
+    else if (k == "ell_chunk") *value = ctx->ell_chunk;
+    else if (k == "ell_minb") *value = ctx->ell_minb;
+    else if (k == "ell_minb_cgp") *value = ctx->ell_minb_cgp;
     else if (k == "ell_coded_active") *value = (ctx->ell.coded ? 1 : 0) | (ctx->gell.coded ? 2 : 0);
     else if (k == "ell_patterns") *value = ctx->ell.n_patterns;
     else if (k == "ell_escape_rows") *value = ctx->ell.n_escape;

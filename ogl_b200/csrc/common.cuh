@@ -133,7 +133,11 @@ struct Context {
     } ell, gell;
     label max_row_len_g = 0;     // longest row of the ghosted CSR
     int64_t ell_coded = 1;       // 0 off, 1 auto (when <= 25% of the rows escape), 2 whenever a table exists
-    int64_t fuse_p = 1;          // CG: p-update fused into the ELL SpMV (ell.cu:k_spmv_ell_cgp)
+    int64_t ell_chunk = 1;       // consecutive 256-row tiles per CTA visit (ell.cu:TileWalk)
+    int64_t ell_minb = 4;        // resident CTAs per SM the coded ELL SpMV is compiled for (3: 85 registers, 4: 64)
+    int64_t ell_minb_cgp = 3;    // ... and the fused CG kernel (2, 3 or 4)
+    int64_t fuse_p = 0;          // CG: p-update fused into the ELL SpMV (ell.cu:k_spmv_ell_cgp); measured slower than
+                                 // the separate k_cg_p at 1 M and 8 M rows on 1 and 2 GPUs (profiles/r02_*probe*), so off
     int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernels (spmv.cu:pick_variant)
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
     int64_t max_warp_nnz = 0;    // warp-tile kernel: max nnz of 32 consecutive rows
@@ -320,6 +324,7 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
 int spmv_setup(Context *ctx);
 int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q, bool ghost);
 void ell_invalidate(Context *ctx, bool structure);
+int ell_prepare_for_loop(Context *ctx, bool ghost);
 
 // comm.cu ------------------------------------------------------------------------
 int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,

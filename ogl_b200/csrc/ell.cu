@@ -12,9 +12,11 @@
 //   * pattern-coded columns.  On a mesh-ordered matrix almost every row has one of a handful of
 //     (column - row) tuples (7-point stencil: interior, 6 faces, 12 edges, 8 corners = 27).  A
 //     device-side hash table finds the distinct tuples once per sparsity pattern; rows whose tuple
-//     is among the first 255 carry a ONE-BYTE code, the kernel rebuilds the columns from a table in
-//     shared memory: 8 B values + 1/width B per entry instead of 12 B.  Other rows (ghost columns of
-//     a decomposed case, irregular rows) keep their 4-byte columns behind the escape code 255.
+//     is among the first 127 carry a ONE-BYTE code, the kernel rebuilds the columns from a table in
+//     shared memory: 8 B values + 1/width B per entry instead of 12 B.  Bit 7 of the code says the
+//     row also has ghost entries (columns >= n of a decomposed case, stored behind the local
+//     ones): those few slots are read with their 4-byte columns, as are all slots of a row whose
+//     tuple is not in the table (code 127).
 //     Nothing about the arithmetic changes.  Unstructured patterns (> 25% escapes) stay plain ELL.
 //   * CG step_1 fused into the SpMV (k_spmv_ell_cgp): the kernel gathers z and p, forms
 //     p' = z + (rho/rho_prev) p per operand on the fly -- the same two operations on the same two
@@ -36,7 +38,8 @@ namespace {
 constexpr label kPadDelta = INT_MIN;   // table entry of a padding slot
 constexpr int kPatSlots = 1024;        // open-addressing hash table of tuples
 constexpr int kPatMaxW = 8;            // widest row the tuple table holds
-constexpr int kEscape = 255;
+constexpr int kEscape = 127;           // low 7 bits of a code: row not in the table
+constexpr int kGhostBit = 128;         // the row has ghost entries (columns >= n) behind its local ones
 constexpr int kEllBatch = 8;
 constexpr int kEllThreads = 256;
 constexpr int kEllCtasPerSM = 4;
@@ -70,23 +73,26 @@ __global__ void k_ell_values(label n, const label *__restrict__ row_ptrs, const 
     for (int j = 0; j < width; ++j) ell_vals[j * pitch + row] = j < len ? vals[rs + j] : 0.0;
 }
 
-// (column - row) tuple of a row; false when the row references a ghost column (>= n)
-__device__ __forceinline__ bool row_tuple(label n, int64_t row, const label *__restrict__ ell_cols, int width,
-                                          int64_t pitch, label (&d)[kPatMaxW], unsigned long long &h)
+// (column - row) tuple of the LOCAL entries of a row (a ghosted row keeps its ghost entries,
+// columns >= n, behind them: they do not belong to the pattern); `ghost`: the row has some
+__device__ __forceinline__ void row_tuple(label n, int64_t row, const label *__restrict__ ell_cols, int width,
+                                          int64_t pitch, label (&d)[kPatMaxW], unsigned long long &h, bool &ghost)
 {
-    bool local = true;
+    ghost = false;
     h = 0xcbf29ce484222325ull;
 #pragma unroll
     for (int u = 0; u < kPatMaxW; ++u) {
         label c = -1;
         if (u < width) c = ell_cols[u * pitch + row];
+        if (c >= n) {
+            ghost = true;
+            c = -1;
+        }
         d[u] = c < 0 ? kPadDelta : c - (label)row;
-        if (c >= n) local = false;
         h = (h ^ (unsigned long long)(unsigned int)d[u]) * 0x100000001b3ull;
         h ^= h >> 29;
     }
     if (h == 0) h = 1;   // 0 marks an empty slot
-    return local;
 }
 
 // pass 1: every distinct tuple takes a slot (the CAS winner stores the tuple)
@@ -97,7 +103,8 @@ __global__ void k_pat_insert(label n, const label *__restrict__ ell_cols, int wi
     if (row >= n) return;
     label d[kPatMaxW];
     unsigned long long h;
-    if (!row_tuple(n, row, ell_cols, width, pitch, d, h)) return;
+    bool ghost;
+    row_tuple(n, row, ell_cols, width, pitch, d, h, ghost);
     unsigned int slot = (unsigned int)(h % kPatSlots);
     for (int probe = 0; probe < kPatSlots; ++probe, slot = (slot + 1) % kPatSlots) {
         unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&keys[slot]);
@@ -112,7 +119,7 @@ __global__ void k_pat_insert(label n, const label *__restrict__ ell_cols, int wi
     *overflow = 1;
 }
 
-// pass 2 (one thread): codes 0..254 for the occupied slots in slot order, compact table
+// pass 2 (one thread): codes 0..126 for the occupied slots in slot order, compact table
 __global__ void k_pat_ids(const unsigned long long *keys, const label *tuples, int width, int *ids,
                           label *ptab, int *n_patterns)
 {
@@ -144,23 +151,23 @@ __global__ void k_pat_assign(label n, const label *__restrict__ ell_cols, int wi
     if (row < n) {
         label d[kPatMaxW];
         unsigned long long h;
-        if (row_tuple(n, row, ell_cols, width, pitch, d, h)) {
-            unsigned int slot = (unsigned int)(h % kPatSlots);
-            for (int probe = 0; probe < kPatSlots; ++probe, slot = (slot + 1) % kPatSlots) {
-                const unsigned long long cur = keys[slot];
-                if (cur == 0) break;
-                if (cur == h) {
-                    bool same = true;
+        bool ghost;
+        row_tuple(n, row, ell_cols, width, pitch, d, h, ghost);
+        unsigned int slot = (unsigned int)(h % kPatSlots);
+        for (int probe = 0; probe < kPatSlots; ++probe, slot = (slot + 1) % kPatSlots) {
+            const unsigned long long cur = keys[slot];
+            if (cur == 0) break;
+            if (cur == h) {
+                bool same = true;
 #pragma unroll
-                    for (int u = 0; u < kPatMaxW; ++u) same = same && tuples[slot * kPatMaxW + u] == d[u];
-                    if (same) cd = ids[slot];
-                    break;
-                }
+                for (int u = 0; u < kPatMaxW; ++u) same = same && tuples[slot * kPatMaxW + u] == d[u];
+                if (same) cd = ids[slot];
+                break;
             }
         }
-        code[row] = (unsigned char)cd;
+        code[row] = (unsigned char)(cd | (ghost ? kGhostBit : 0));
     }
-    const unsigned int esc = __ballot_sync(0xffffffffu, row < n && cd == kEscape);
+    const unsigned int esc = __ballot_sync(0xffffffffu, row < n && cd == kEscape);   // (ghost rows with a coded local part do not count)
     if ((threadIdx.x & 31) == 0 && esc) atomicAdd(n_escape, (unsigned long long)__popc(esc));
 }
 
@@ -173,31 +180,71 @@ __device__ __forceinline__ unsigned int ld_code(const unsigned char *p)
     return r;
 }
 
-// columns of a row: from the pattern table (PC, code != escape) or from the column array
-template <int W, bool PC>
-__device__ __forceinline__ void ell_columns(label (&c)[W], int64_t row, unsigned int cd, const EllK &m,
-                                            const label *tab, unsigned long long pol)
-{
-    if (PC && cd != (unsigned int)kEscape) {
-#pragma unroll
-        for (int u = 0; u < W; ++u) {
-            const label d = tab[cd * W + u];
-            c[u] = d == kPadDelta ? -1 : (label)row + d;
-        }
-    } else {
-#pragma unroll
-        for (int u = 0; u < W; ++u) c[u] = ld_mat(&m.cols[u * m.pitch + row], pol);
+// Row schedule of a persistent CTA: tiles of kEllThreads rows; `chunk` consecutive tiles per visit
+// (consecutive tiles share most of the x lines they gather, so those come from L1 instead of L2),
+// visits strided over the grid.  chunk == 1: plain grid-stride.
+struct TileWalk {
+    int64_t first, step, n_tiles;
+    int chunk, k;
+    __device__ __forceinline__ TileWalk(label n, int chunk_)
+    {
+        chunk = chunk_ < 1 ? 1 : chunk_;
+        first = (int64_t)blockIdx.x * chunk;
+        step = (int64_t)gridDim.x * chunk;
+        n_tiles = ((int64_t)n + kEllThreads - 1) / kEllThreads;
+        k = 0;
     }
+    __device__ __forceinline__ int64_t tile() const { return first + k; }
+    __device__ __forceinline__ bool done() const { return first + k >= n_tiles; }
+    __device__ __forceinline__ void next()
+    {
+        if (++k == chunk) {
+            k = 0;
+            first += step;
+        }
+    }
+};
+
+// Local columns of a pattern-coded row from the shared-memory table.  Padding slots, ghost slots
+// and every slot of an escape row get the row's own index (a valid address: the gather is
+// unconditional, the slot is skipped in the sum) and a cleared bit in `live`.  The live slots are
+// the leading ones of the row.
+template <int W>
+__device__ __forceinline__ unsigned int coded_columns(label (&c)[W], label row, unsigned int cd, const label *tab)
+{
+    unsigned int live = 0;
+    const unsigned int id = cd & (unsigned int)kEscape;
+    const label *t = tab + (id == (unsigned int)kEscape ? 0u : id) * W;
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+        const label d = t[u];
+        const bool on = d != kPadDelta && id != (unsigned int)kEscape;
+        c[u] = on ? row + d : row;
+        live |= on ? (1u << u) : 0u;
+    }
+    return live;
+}
+
+// does the row owe slots to the tail loop?  (ghost entries behind the coded local ones, or an
+// escape row: everything)
+__device__ __forceinline__ bool coded_tail(unsigned int cd)
+{
+    return (cd & (unsigned int)kGhostBit) != 0 || (cd & (unsigned int)kEscape) == (unsigned int)kEscape;
 }
 
 // W > 0: compile-time row width -- all loads of a row are issued before the first dependent
-// instruction (with a run-time slot loop ptxas interleaves DMUL/DADD with the loads of the fused
-// instantiation: two extra memory round trips per row for an in-order warp).  W == 0: any width.
-template <bool ADV, int NRED, int W, bool PC>
-__global__ void __launch_bounds__(kEllThreads, kEllCtasPerSM)
-k_spmv_ell(const SpmvK a, const EllK m)
+// instruction.  W == 0: any width (plain columns only).
+//
+// PC (pattern-coded columns), the hot configuration, is software-pipelined: the code and the W
+// values of the thread's NEXT row are requested while this row's operands are gathered, so a
+// trip costs one L2 round trip (the gather) with the HBM stream running underneath; the code of
+// the current row arrived a trip ago, so the gather addresses need no HBM round trip either.
+// Rows behind the escape code (ghost columns, irregular rows) are rare and take a plain loop.
+template <bool ADV, int NRED, int W, bool PC, int MINB>
+__global__ void __launch_bounds__(kEllThreads, MINB)
+k_spmv_ell(const SpmvK a, const EllK m, const int chunk)
 {
-    __shared__ label tab[PC ? 256 * (W > 0 ? W : 1) : 1];
+    __shared__ label tab[PC ? 128 * (W > 0 ? W : 1) : 1];
     if (a.guard_done && a.state->done) return;
     if (PC) {
         for (int i = threadIdx.x; i < m.n_patterns * W; i += kEllThreads) tab[i] = m.ptab[i];
@@ -206,28 +253,103 @@ k_spmv_ell(const SpmvK a, const EllK m)
     double red[NRED > 0 ? NRED : 1];
 #pragma unroll
     for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
-        // everything the row needs is requested up front: a warp issues in order, so a load
-        // placed behind the row sum would add its whole latency to every trip
-        unsigned int cd = kEscape;
-        if (PC) cd = ld_code(m.code + row);
-        double dw = 0.0;
-        if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
-        double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
-        if (W > 0) {
-            constexpr int WW = W > 0 ? W : 1;
+    if (W > 0 && PC) {
+        constexpr int WW = W > 0 ? W : 1;
+        TileWalk w(a.n, chunk);
+        double vn[WW];
+        unsigned int cdn = kEscape;
+        int64_t row = w.tile() * kEllThreads + threadIdx.x;
+        bool ok = !w.done() && row < a.n;
+        if (ok) {
+            cdn = ld_code(m.code + row);
+#pragma unroll
+            for (int u = 0; u < WW; ++u) vn[u] = ld_mat(&m.vals[u * m.pitch + row], a.mat_policy);
+        }
+        while (!w.done()) {
+            const int64_t row_c = row;
+            const bool ok_c = ok;
+            const unsigned int cd = cdn;
+            double v[WW], xv[WW];
+            label c[WW];
+            // gather for this row: the addresses come from the code that arrived a trip ago
+            unsigned int live = 0;
+            if (ok_c) {
+                live = coded_columns<WW>(c, (label)row_c, cd, tab);
+#pragma unroll
+                for (int u = 0; u < WW; ++u) xv[u] = __ldg(&a.x[c[u]]);
+            }
+#pragma unroll
+            for (int u = 0; u < WW; ++u) v[u] = vn[u];
+            // next row: code + values on their way while the gather is in flight
+            w.next();
+            row = w.tile() * kEllThreads + threadIdx.x;
+            ok = !w.done() && row < a.n;
+            if (ok) {
+                cdn = ld_code(m.code + row);
+#pragma unroll
+                for (int u = 0; u < WW; ++u) vn[u] = ld_mat(&m.vals[u * m.pitch + row], a.mat_policy);
+            }
+            if (!ok_c) continue;
+            double dw = 0.0;
+            if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row_c));
+            double sum = ADV ? __dmul_rn(a.beta, a.y_in[row_c]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < WW; ++u) {
+                const double s2 = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
+                sum = (live >> u) & 1u ? s2 : sum;
+            }
+            if (coded_tail(cd)) {
+                // the slots behind the coded ones (x carries its ghost part here), all requested
+                // at once; rare (rows on a processor boundary, irregular rows)
+                const int first = __popc(live);
+                label ce[WW];
+                double ve[WW], xe[WW];
+#pragma unroll
+                for (int u = 0; u < WW; ++u) ce[u] = u >= first ? m.cols[u * m.pitch + row_c] : -1;
+#pragma unroll
+                for (int u = 0; u < WW; ++u) ve[u] = u >= first ? m.vals[u * m.pitch + row_c] : 0.0;
+#pragma unroll
+                for (int u = 0; u < WW; ++u) xe[u] = ce[u] >= 0 ? a.x[ce[u]] : 0.0;
+#pragma unroll
+                for (int u = 0; u < WW; ++u)
+                    if (ce[u] >= 0) sum = __dadd_rn(sum, prod_of(ve[u], xe[u], a.alpha, ADV));
+            }
+            a.y[row_c] = sum;
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
+            if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+        }
+    } else if (W > 0) {
+        constexpr int WW = W > 0 ? W : 1;
+        TileWalk w(a.n, chunk);
+        for (; !w.done(); w.next()) {
+            const int64_t row = w.tile() * kEllThreads + threadIdx.x;
+            if (row >= a.n) continue;
+            // everything the row needs is requested up front: a warp issues in order, so a load
+            // placed behind the row sum would add its whole latency to every trip
+            double dw = 0.0;
+            if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
+            double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             label c[WW];
             double v[WW], xv[WW];
 #pragma unroll
+            for (int u = 0; u < WW; ++u) c[u] = ld_mat(&m.cols[u * m.pitch + row], a.mat_policy);
+#pragma unroll
             for (int u = 0; u < WW; ++u) v[u] = ld_mat(&m.vals[u * m.pitch + row], a.mat_policy);
-            ell_columns<WW, PC>(c, row, cd, m, tab, a.mat_policy);
 #pragma unroll
             for (int u = 0; u < WW; ++u) xv[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
 #pragma unroll
             for (int u = 0; u < WW; ++u)
                 if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
-        } else {
+            a.y[row] = sum;
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
+            if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+        }
+    } else {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
+            double dw = 0.0;
+            if (NRED >= 1) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
+            double sum = ADV ? __dmul_rn(a.beta, a.y_in[row]) : 0.0;
             for (int j0 = 0; j0 < m.width; j0 += kEllBatch) {
                 label c[kEllBatch];
                 double v[kEllBatch], xv[kEllBatch];
@@ -243,10 +365,10 @@ k_spmv_ell(const SpmvK a, const EllK m)
                 for (int u = 0; u < kEllBatch; ++u)
                     if (c[u] >= 0) sum = __dadd_rn(sum, prod_of(v[u], xv[u], a.alpha, ADV));
             }
+            a.y[row] = sum;
+            if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
+            if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
         }
-        a.y[row] = sum;
-        if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
-        if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
     }
     if (NRED > 0)
         grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
@@ -257,12 +379,14 @@ k_spmv_ell(const SpmvK a, const EllK m)
 // buffer.  GHOST (several ranks, peer-memory path): columns >= n are ghost operands -- z from the
 // stamped words in slot 2 of this rank's window (pushed by the neighbours' k_cg_xr, stamped with
 // the number of the all-reduce that kernel ended with), p from / to the ghost part of the p
-// buffers, which the one row referencing the column keeps up to date.
-template <int W, bool PC, bool GHOST>
-__global__ void __launch_bounds__(kEllThreads, kEllCtasPerSM)
-k_spmv_ell_cgp(const SpmvK a, const EllK m, double *__restrict__ p_new)
+// buffers, which the one row referencing the column keeps up to date.  Rows with ghost columns
+// are escape rows of the pattern code; like all escape rows they take the plain loop at the end
+// of a trip (ghost entries sit BEHIND the local ones in a row: the same left-to-right sum).
+template <int W, bool PC, bool GHOST, int MINB>
+__global__ void __launch_bounds__(kEllThreads, MINB)
+k_spmv_ell_cgp(const SpmvK a, const EllK m, double *__restrict__ p_new, const int chunk)
 {
-    __shared__ label tab[PC ? 256 * W : 1];
+    __shared__ label tab[PC ? 128 * W : 1];
     if (a.guard_done && a.state->done) return;
     if (PC) {
         for (int i = threadIdx.x; i < m.n_patterns * W; i += kEllThreads) tab[i] = m.ptab[i];
@@ -281,52 +405,99 @@ k_spmv_ell_cgp(const SpmvK a, const EllK m, double *__restrict__ p_new)
         t0 = clock64();
     }
     double red[1] = {0.0};
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
-        unsigned int cd = kEscape;
-        if (PC) cd = ld_code(m.code + row);
-        label c[W];
+    TileWalk w(a.n, chunk);
+    double vn[W];
+    unsigned int cdn = kEscape;
+    int64_t row = w.tile() * kEllThreads + threadIdx.x;
+    bool ok = !w.done() && row < a.n;
+    if (PC && ok) {
+        cdn = ld_code(m.code + row);
+#pragma unroll
+        for (int u = 0; u < W; ++u) vn[u] = ld_mat(&m.vals[u * m.pitch + row], a.mat_policy);
+    }
+    while (!w.done()) {
+        const int64_t row_c = row;
+        const bool ok_c = ok;
+        const unsigned int cd = cdn;
         double v[W], zc[W], pc[W];
+        label c[W];
+        unsigned int live = 0;
+        if (PC) {
+            if (ok_c) {
+                live = coded_columns<W>(c, (label)row_c, cd, tab);
 #pragma unroll
-        for (int u = 0; u < W; ++u) v[u] = ld_mat(&m.vals[u * m.pitch + row], a.mat_policy);
-        ell_columns<W, PC>(c, row, cd, m, tab, a.mat_policy);
-        // ghost columns (GHOST: c >= n) sit BEHIND the local ones in a row of the ghosted matrix:
-        // the unrolled part handles the local operands, the rare rows with ghost entries append
-        // theirs below in slot order -- the same left-to-right sum
-        bool has_ghost = false;
+                for (int u = 0; u < W; ++u) zc[u] = __ldg(&a.x[c[u]]);
+                if (!p_is_z) {
 #pragma unroll
-        for (int u = 0; u < W; ++u) {
-            if (GHOST && c[u] >= a.n) {
-                has_ghost = true;
-                c[u] = -1;
+                    for (int u = 0; u < W; ++u) pc[u] = a.y_in[c[u]];
+                }
             }
-            zc[u] = c[u] >= 0 ? __ldg(&a.x[c[u]]) : 0.0;
-        }
 #pragma unroll
-        for (int u = 0; u < W; ++u) pc[u] = (c[u] >= 0 && !p_is_z) ? a.y_in[c[u]] : 0.0;
+            for (int u = 0; u < W; ++u) v[u] = vn[u];
+        }
+        w.next();
+        row = w.tile() * kEllThreads + threadIdx.x;
+        ok = !w.done() && row < a.n;
+        if (PC && ok) {
+            cdn = ld_code(m.code + row);
+#pragma unroll
+            for (int u = 0; u < W; ++u) vn[u] = ld_mat(&m.vals[u * m.pitch + row], a.mat_policy);
+        }
+        if (!ok_c) continue;
+        bool tail = PC && coded_tail(cd);   // slots the tail below still owes
+        if (!PC) {
+#pragma unroll
+            for (int u = 0; u < W; ++u) c[u] = ld_mat(&m.cols[u * m.pitch + row_c], a.mat_policy);
+#pragma unroll
+            for (int u = 0; u < W; ++u) v[u] = ld_mat(&m.vals[u * m.pitch + row_c], a.mat_policy);
+#pragma unroll
+            for (int u = 0; u < W; ++u) {
+                bool on = c[u] >= 0;
+                if (GHOST && c[u] >= a.n) {   // ghost entries follow the local ones: the tail takes them
+                    on = false;
+                    tail = true;
+                }
+                live |= on ? (1u << u) : 0u;
+                if (!on) c[u] = (label)row_c;
+                zc[u] = __ldg(&a.x[c[u]]);
+            }
+            if (!p_is_z) {
+#pragma unroll
+                for (int u = 0; u < W; ++u) pc[u] = a.y_in[c[u]];
+            }
+        }
         double sum = 0.0, mine = 0.0;
 #pragma unroll
         for (int u = 0; u < W; ++u) {
-            if (c[u] >= 0) {
-                const double pv = p_is_z ? zc[u] : __dadd_rn(zc[u], __dmul_rn(t, pc[u]));
-                if (c[u] == (label)row) mine = pv;                 // the diagonal slot: my own p'
-                sum = __dadd_rn(sum, __dmul_rn(v[u], pv));
-            }
+            const double pv = p_is_z ? zc[u] : __dadd_rn(zc[u], __dmul_rn(t, pc[u]));
+            const bool on = (live >> u) & 1u;
+            if (on && c[u] == (label)row_c) mine = pv;               // the diagonal slot: my own p'
+            const double s2 = __dadd_rn(sum, __dmul_rn(v[u], pv));
+            sum = on ? s2 : sum;
         }
-        if (GHOST && has_ghost) {
+        if (tail) {
+            // the slots behind the handled ones: ghost operands (z from the stamped words of the
+            // window, p from / to the ghost part of the p buffers) and, for an escape row, its local
+            // ones.  A face row of a decomposed stencil has ONE such slot, so a plain loop that
+            // stops at the first padding slot is as fast as it gets and costs no registers.
 #pragma unroll 1
-            for (int u = 0; u < W; ++u) {
-                const label cg = m.cols[u * m.pitch + row];
-                if (cg < a.n) continue;
-                double zgv = 0.0;
-                if (!pull_stamped(zg + 2 * (size_t)(cg - a.n), stamp, t0, zgv)) a.state->comm_error = 1;
-                const double pv = p_is_z ? zgv : __dadd_rn(zgv, __dmul_rn(t, a.y_in[cg]));
-                p_new[cg] = pv;   // ghost entry of p: referenced by this row only
-                sum = __dadd_rn(sum, __dmul_rn(m.vals[u * m.pitch + row], pv));
+            for (int u = __popc(live); u < W; ++u) {
+                const label ce = m.cols[u * m.pitch + row_c];
+                if (ce < 0) break;
+                double zv = 0.0;
+                if (GHOST && ce >= a.n) {
+                    if (!pull_stamped(zg + 2 * (size_t)(ce - a.n), stamp, t0, zv)) a.state->comm_error = 1;
+                } else {
+                    zv = a.x[ce];
+                }
+                const double pv = p_is_z ? zv : __dadd_rn(zv, __dmul_rn(t, a.y_in[ce]));
+                if (ce == (label)row_c) mine = pv;
+                if (GHOST && ce >= a.n) p_new[ce] = pv;   // ghost entry of p: referenced by this row only
+                sum = __dadd_rn(sum, __dmul_rn(m.vals[u * m.pitch + row_c], pv));
             }
         }
-        p_new[row] = mine;
-        a.y[row] = sum;
+        p_new[row_c] = mine;
+        a.y[row_c] = sum;
         red[0] = __dadd_rn(red[0], __dmul_rn(mine, sum));
     }
     grid_reduce<1>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
@@ -435,6 +606,15 @@ static int ell_prepare(Context *ctx, bool ghosted)
     return OGL_OK;
 }
 
+// Build whatever ELL copy the CG loop is going to use, outside the graph capture (on several
+// ranks the prologue's SpMVs run over the CSR with the flag handshake and would not build it).
+int ell_prepare_for_loop(Context *ctx, bool ghost)
+{
+    if (spmv_variant_in_use(ctx) != 7) return OGL_OK;
+    const int rc = ell_prepare(ctx, ghost && ctx->have_ghosted);
+    return rc == OGL_ERR_UNSUPPORTED ? OGL_OK : rc;   // the launch reports it if it really needs the copy
+}
+
 static EllK ell_args(const Context::EllMatrix &e)
 {
     EllK m;
@@ -448,10 +628,10 @@ static EllK ell_args(const Context::EllMatrix &e)
     return m;
 }
 
-static int ell_grid(const Context *ctx)
+static int ell_grid(const Context *ctx, int ctas_per_sm = kEllCtasPerSM)
 {
     const int64_t need = ((int64_t)ctx->n + kEllThreads - 1) / kEllThreads;
-    const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * kEllCtasPerSM;   // persistent
+    const int64_t cap = ctx->stream_ctas > 0 ? ctx->stream_ctas : (int64_t)kNumSM * ctas_per_sm;   // persistent
     const int64_t g = need < cap ? need : cap;
     return g < 1 ? 1 : (int)g;
 }
@@ -462,24 +642,28 @@ int spmv_ell(Context *ctx, SpmvK &k, const SpmvArgs &sa, bool ghosted)
     const Context::EllMatrix &e = ghosted ? ctx->gell : ctx->ell;
     if (sa.ghost_x) k.ea = make_epi_args(ctx, sa.nred), k.ea.trace_tag = 20;   // all-reduce inside the launch
     const EllK m = ell_args(e);
-    const int grid = ell_grid(ctx);
     cudaStream_t st = ctx->stream;
     const int nred = sa.nred;
     const bool pc = e.coded && (e.width == 7 || e.width == 5);
-#define ELL_GO(A, R, W, P) k_spmv_ell<A, R, W, P><<<grid, kEllThreads, 0, st>>>(k, m)
+    const int chunk = (int)ctx->ell_chunk;
+    const int minb = (int)ctx->ell_minb;
+    const int grid = ell_grid(ctx, pc ? minb : kEllCtasPerSM);
+#define ELL_GO(A, R, W, P, B) k_spmv_ell<A, R, W, P, B><<<grid, kEllThreads, 0, st>>>(k, m, chunk)
+#define ELL_WP(A, R, W)                                       \
+    do {                                                      \
+        if (pc) {                                             \
+            if (minb == 3) ELL_GO(A, R, W, true, 3);          \
+            else ELL_GO(A, R, W, true, 4);                    \
+        } else {                                              \
+            ELL_GO(A, R, W, false, 4);                        \
+        }                                                     \
+    } while (0)
 #define ELL_W(A, R)                                           \
     do {                                                      \
-        if (e.width == 7) {                                   \
-            if (pc) ELL_GO(A, R, 7, true);                    \
-            else ELL_GO(A, R, 7, false);                      \
-        } else if (e.width == 5) {                            \
-            if (pc) ELL_GO(A, R, 5, true);                    \
-            else ELL_GO(A, R, 5, false);                      \
-        } else if (e.width == 8) {                            \
-            ELL_GO(A, R, 8, false);                           \
-        } else {                                              \
-            ELL_GO(A, R, 0, false);                           \
-        }                                                     \
+        if (e.width == 7) ELL_WP(A, R, 7);                    \
+        else if (e.width == 5) ELL_WP(A, R, 5);               \
+        else if (e.width == 8) ELL_GO(A, R, 8, false, 4);     \
+        else ELL_GO(A, R, 0, false, 4);                       \
     } while (0)
     if (sa.advanced) {
         if (nred == 0) ELL_W(true, 0);
@@ -491,6 +675,7 @@ int spmv_ell(Context *ctx, SpmvK &k, const SpmvArgs &sa, bool ghosted)
         else ELL_W(false, 2);
     }
 #undef ELL_W
+#undef ELL_WP
 #undef ELL_GO
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());
@@ -528,22 +713,31 @@ int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_n
     k.ea = make_epi_args(ctx, ghost ? 1 : 0);
     k.ea.trace_tag = 20;
     const EllK m = ell_args(e);
-    const int grid = ell_grid(ctx);
+    const int minb = (int)ctx->ell_minb_cgp;
+    const int grid = ell_grid(ctx, minb);
+    const int chunk = (int)ctx->ell_chunk;
     cudaStream_t st = ctx->stream;
-#define CGP_GO(W, P, G) k_spmv_ell_cgp<W, P, G><<<grid, kEllThreads, 0, st>>>(k, m, p_new)
+#define CGP_GO(W, P, G, B) k_spmv_ell_cgp<W, P, G, B><<<grid, kEllThreads, 0, st>>>(k, m, p_new, chunk)
+#define CGP_Q(W, P, G)                             \
+    do {                                           \
+        if (minb == 2) CGP_GO(W, P, G, 2);         \
+        else if (minb == 3) CGP_GO(W, P, G, 3);    \
+        else CGP_GO(W, P, G, 4);                   \
+    } while (0)
 #define CGP_W(W)                                   \
     do {                                           \
         if (e.coded) {                             \
-            if (ghost) CGP_GO(W, true, true);      \
-            else CGP_GO(W, true, false);           \
+            if (ghost) CGP_Q(W, true, true);       \
+            else CGP_Q(W, true, false);            \
         } else {                                   \
-            if (ghost) CGP_GO(W, false, true);     \
-            else CGP_GO(W, false, false);          \
+            if (ghost) CGP_Q(W, false, true);      \
+            else CGP_Q(W, false, false);           \
         }                                          \
     } while (0)
     if (e.width == 7) CGP_W(7);
     else CGP_W(5);
 #undef CGP_W
+#undef CGP_Q
 #undef CGP_GO
     ctx->launches++;
     OGL_CUDA(ctx, cudaGetLastError());

@@ -838,6 +838,7 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
         OGL_CUDA(ctx, cudaMemsetAsync(pv, 0, sizeof(double) * ctx->work_len, st));
         OGL_CUDA(ctx, cudaMemsetAsync(pv2, 0, sizeof(double) * ctx->work_len, st));
         const bool fused = pcg_fused_ok(ctx);
+        if (!fused) OGL_TRY(ell_prepare_for_loop(ctx, ghost_p_mode(ctx)));
         if (ghost_p_mode(ctx)) OGL_TRY(push_boundary(ctx, pk_of(ctx) == 0 ? r : z));   // boundary z0
         double *r_alt;   // r is ping-ponged like p: the x/r-update writes the other buffer
         OGL_TRY(get_work(ctx, 10, &r_alt));

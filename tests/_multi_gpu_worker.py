@@ -24,7 +24,7 @@ CASES = {
     "cavity_cg_none": (lambda p: cases.cavity_2d((p[0] * p[2], p[1], 1)), "GKOCG", "none", 1, 1e-11),
 }
 
-MODES = (0, 1, 2, 3)
+MODES = (0, 1, 2, 3, 4, 5)
 
 
 def main():
@@ -34,7 +34,10 @@ def main():
     results = {}
     # every case on the four data paths: 0 peer-memory windows, halo fused into the SpMV, CG
     # in ghost-p mode (default); 1 NCCL; 2 peer-memory windows with separate pack / non-local
-    # kernels; 3 like 0 but CG with the flag handshake instead of ghost p
+    # kernels; 3 like 0 but CG with the flag handshake instead of ghost p; 4 / 5 the large-system
+    # configuration forced onto these small cases: pattern-coded ELL copy of the ghosted matrix,
+    # no persistent loop kernel, CG with (4) / without (5) the p-update fused into the SpMV (ghost
+    # z pulled from the window inside the SpMV)
     for name, (builder, solver, precond, mbs, tol), mode in (
             (n, c, m) for n, c in CASES.items() for m in MODES):
         s = builder(procs)[ps.rank]
@@ -42,6 +45,8 @@ def main():
                     "adaptMinIter": False, "krylovDim": 30, "comm_mode": 1 if mode == 1 else 0,
                     "fused_halo": 0 if mode == 2 else 1, "ghost_p": 0 if mode == 3 else 1,
                     "preconditioner": {"preconditioner": precond, "maxBlockSize": mbs}}
+        if mode >= 4:
+            controls.update({"spmv_variant": 7, "ell_coded": 2, "fused_pcg": 0, "fuse_p": 1 if mode == 4 else 0})
         name = f"{name}@{mode}"
         sol = lduMatrix_solver_New(name, s, controls, db, ps)
         psi = s.psi.copy()

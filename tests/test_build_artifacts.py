@@ -52,8 +52,8 @@ def test_hot_kernels_fit_their_occupancy_budget(table):
         regs, st, ld = find(table, *parts)
         assert regs <= 51 and st == 0 and ld == 0, (parts, regs, st, ld)
     # 4 CTAs x 256 threads per SM: <= 64 registers
-    for parts in (("k_cg_xr<1>",), ("k_cg_xr<0>",), ("k_cg_p(",), ("k_spmv_ell<false, 1, 7, true>",),
-                  ("k_spmv_ell_cgp<7, true, false>",), ("k_spmv_ell_cgp<7, true, true>",)):
+    for parts in (("k_cg_xr<1>",), ("k_cg_xr<0>",), ("k_cg_p(",), ("k_spmv_ell<false, 1, 7, true, 4>",),
+                  ("k_spmv_ell<false, 0, 7, true, 4>",), ("k_spmv_ell_cgp<7, false, false, 4>",)):
         regs, st, ld = find(table, *parts)
         assert regs <= 64 and st == 0 and ld == 0, (parts, regs, st, ld)
 

@@ -47,7 +47,7 @@ def test_decomposed_solves_match_oracle(oracle, tmp_path, procs):
     res = [json.load(open(f"{out}.{r}")) for r in range(world)]
     assert res[0]["pressure_cg@0"]["p2p"] == 1, "peer-memory path not active on an NVLink box"
     assert res[0]["pressure_cg@1"]["p2p"] == 0 and res[0]["pressure_cg@2"]["p2p"] == 1
-    assert res[0]["pressure_cg@3"]["p2p"] == 1
+    assert res[0]["pressure_cg@3"]["p2p"] == 1 and res[0]["pressure_cg@4"]["p2p"] == 1
     for name, (builder, solver, precond, mbs, tol) in (
             (f"{n}@{m}", c) for n, c in CASES.items() for m in MODES):
         systems = builder(procs)

@@ -426,5 +426,5 @@ def test_cg_p_update_fused_into_the_spmv_is_bit_identical(ctx, oracle, precond):
         assert out[key][3] < base[3]          # one launch less per iteration
     o = oracle.solve([oracle.assemble(s)], "GKOCG", precond, tolerance=1e-9)
     assert abs(base[0] - o.n_iterations) <= ITER_TOL and rel_l2(base[2], o.x[0]) <= L2_TOL
-    for k, v in (("spmv_variant", 0), ("fused_pcg", 2), ("fuse_p", 1), ("ell_coded", 1)):
+    for k, v in (("spmv_variant", 0), ("fused_pcg", 2), ("fuse_p", 0), ("ell_coded", 1)):
         ctx.set_option(k, v)

@@ -40,6 +40,9 @@ def main():
     for combo in itertools.product(*[v for _, v in opts]):
         for (k, _), v in zip(opts, combo):
             ctx.set_option(k, v)
+        ctx.spmv_bench(20, True)
+        spmv_us = min(ctx.spmv_bench(200, False) for _ in range(2)) / 200 * 1e3
+        fused_us = min(ctx.spmv_bench(200, True) for _ in range(2)) / 200 * 1e3
         ctx.vector_fill(L.OGL_VEC_X, 0.0)
         ctx.pcg_bench(64)
         best = []
@@ -51,6 +54,11 @@ def main():
             us = min(best)
             print(json.dumps({"cells": cells, "n_gpus": n_ranks, **{k: v for (k, _), v in zip(opts, combo)},
                               "fused_active": ctx.get_option("fused_pcg_active"),
+                              "variant": ctx.get_option("spmv_variant_in_use"),
+                              "coded": ctx.get_option("ell_coded_active"),
+                              "patterns": [ctx.get_option("ell_patterns"), ctx.get_option("gell_patterns")],
+                              "escapes": [ctx.get_option("ell_escape_rows"), ctx.get_option("gell_escape_rows")],
+                              "spmv_us": round(spmv_us, 2), "spmv_dot_us": round(fused_us, 2),
                               "pcg_us": round(us, 2), "pcg_us_all": [round(b, 2) for b in best],
                               "pcg_gbs": round(b_pcg / us / 1e3, 1)}), flush=True)
     ctx.close()
