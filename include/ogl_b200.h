@@ -96,6 +96,16 @@ int ogl_partition_create(ogl_ctx *ctx, int32_t n_local, int32_t n_targets,
                          const int32_t *target_ids, const int32_t *target_sizes,
                          const int32_t *send_idxs);
 int ogl_partition_sizes(ogl_ctx *ctx, int64_t *local_size, int64_t *global_size);
+/* Host-driven bootstrap of the peer-memory windows, for contexts created with
+ * n_ranks > 1 and nccl_id == NULL: the caller owns the communicator, as OGL's
+ * host layer owns MPI_COMM_WORLD (DevicePersistent/ExecutorHandler/
+ * ExecutorHandler.H:140-144, Partition.H:118-121 all_reduce of the local size).
+ * After ogl_partition_create: export this rank's directory (an opaque blob;
+ * blob == NULL queries its size), all-gather the blobs in rank order with the
+ * host's communicator, connect, then run a host barrier before the first solve.
+ * Works with several ranks per device (CUDA IPC), which NCCL does not. */
+int ogl_partition_export(ogl_ctx *ctx, void *blob, int64_t capacity, int64_t *size);
+int ogl_partition_connect(ogl_ctx *ctx, const void *blobs_all_ranks, int64_t n_blobs);
 
 /* ---- non-local (halo) pattern ----------------------------------------------
  * replaces init_non_local_sparsity_pattern (HostMatrix.C:438-466) +

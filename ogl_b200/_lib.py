@@ -55,6 +55,8 @@ SYMBOLS = {
     "ogl_partition_create": (C.c_int, [ctx_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "ogl_partition_sizes": (C.c_int, [ctx_p, i64p, i64p]),
+    "ogl_partition_export": (C.c_int, [ctx_p, C.c_void_p, C.c_int64, i64p]),
+    "ogl_partition_connect": (C.c_int, [ctx_p, C.c_void_p, C.c_int64]),
     "ogl_nonlocal_pattern": (C.c_int, [ctx_p, C.c_int32, C.c_void_p]),
     "ogl_nonlocal_pattern_download": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ogl_values_update": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -115,6 +115,20 @@ class Context:
         t, s, i = _i32(target_ids), _i32(target_sizes), _i32(send_idxs)
         self._check(self.lib.ogl_partition_create(self.h, n_local, t.size, _ptr(t), _ptr(s), _ptr(i)))
 
+    def partition_export(self) -> bytes:
+        """This rank's window directory (host-driven bootstrap, contexts without an NCCL id)."""
+        size = C.c_int64(0)
+        self._check(self.lib.ogl_partition_export(self.h, None, 0, C.byref(size)))
+        buf = C.create_string_buffer(size.value)
+        self._check(self.lib.ogl_partition_export(self.h, buf, size.value, C.byref(size)))
+        return buf.raw
+
+    def partition_connect(self, blobs):
+        """`blobs`: every rank's directory in rank order (after an all-gather by the caller)."""
+        raw = b"".join(blobs)
+        buf = C.create_string_buffer(raw, len(raw))
+        self._check(self.lib.ogl_partition_connect(self.h, buf, len(blobs)))
+
     def partition_sizes(self):
         a, b = C.c_int64(0), C.c_int64(0)
         self._check(self.lib.ogl_partition_sizes(self.h, C.byref(a), C.byref(b)))

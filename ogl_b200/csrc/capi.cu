@@ -244,8 +244,8 @@ int ogl_ctx_create(int device_id, int rank, int n_ranks, const void *nccl_id, vo
     *out = nullptr;
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
         return ogl::fail(nullptr, OGL_ERR_INVALID, "bad rank / n_ranks");
-    if (n_ranks > 1 && !nccl_id)
-        return ogl::fail(nullptr, OGL_ERR_INVALID, "n_ranks > 1 needs an NCCL unique id");
+    // n_ranks > 1 without an NCCL id: host-driven bootstrap of the peer-memory windows
+    // (ogl_partition_export / ogl_partition_connect), no NCCL fallback path
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -293,7 +293,7 @@ int ogl_ctx_create(int device_id, int rank, int n_ranks, const void *nccl_id, vo
     cudaMemset(c->d_state, 0, sizeof(SolveState));
     cudaMemset(c->d_ticket, 0, sizeof(unsigned int));
     std::memset(c->h_state, 0, 3 * sizeof(SolveState));
-    if (n_ranks > 1) {
+    if (n_ranks > 1 && nccl_id) {
         std::string err;
         const int rc = ogl::acquire_comm(nccl_id, n_ranks, rank, &c->comm, &c->comm_key, &err);
         if (rc != OGL_OK) {
@@ -485,6 +485,18 @@ int ogl_partition_create(ogl_ctx *ctx, int32_t n_local, int32_t n_targets,
 {
     CHECK_CTX(ctx);
     return partition_create(ctx, n_local, n_targets, target_ids, target_sizes, send_idxs);
+}
+
+int ogl_partition_export(ogl_ctx *ctx, void *blob, int64_t capacity, int64_t *size)
+{
+    CHECK_CTX(ctx);
+    return partition_export(ctx, blob, capacity, size);
+}
+
+int ogl_partition_connect(ogl_ctx *ctx, const void *blobs, int64_t n_blobs)
+{
+    CHECK_CTX(ctx);
+    return partition_connect(ctx, blobs, n_blobs);
 }
 
 int ogl_partition_sizes(ogl_ctx *ctx, int64_t *local_size, int64_t *global_size)

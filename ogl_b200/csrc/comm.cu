@@ -116,7 +116,11 @@ k_push_boundary(label n_send, const label *__restrict__ idx, const double *__res
 // stamped with the number of the all-reduce that follows it" for the first push
 __global__ void k_rank_barrier(SolveState *state, CommDev *c) { p2p_allreduce(state, 0, c); }
 
+constexpr int kDirectoryMagic = 0x4f474c44;   // "OGLD"
+
 struct Directory {
+    int magic, pad;
+    long long n_local;
     int n_targets;
     int n_halo;
     int target_ids[kMaxTargets];
@@ -143,17 +147,14 @@ static void p2p_teardown(Context *ctx)
 
 void comm_teardown(Context *ctx) { p2p_teardown(ctx); }
 
-// Build the peer-memory windows.  Collective.  Returns OGL_OK with
-// ctx->p2p_ready == false when the topology does not allow it (caller falls
-// back to NCCL).
-static int p2p_setup(Context *ctx)
+// Step 1 of the window bootstrap (rank-local): allocate and zero this rank's window, describe it.
+// Returns false when the allocation / IPC export fails (the caller agrees with its peers on that).
+static bool p2p_make_window(Context *ctx, Directory &mine)
 {
-    p2p_teardown(ctx);
-    if (ctx->n_ranks > kMaxPeers || ctx->n_targets > kMaxTargets) return OGL_OK;
     const int R = ctx->n_ranks;
-    // ---- my window
-    Directory mine;
     std::memset(&mine, 0, sizeof(mine));
+    mine.magic = kDirectoryMagic;
+    mine.n_local = ctx->n;
     mine.n_targets = ctx->n_targets;
     mine.n_halo = ctx->n_send;
     for (int t = 0; t < ctx->n_targets; ++t) mine.target_ids[t] = ctx->target_ids[t];
@@ -166,13 +167,101 @@ static int p2p_setup(Context *ctx)
     mine.off_ack_flag = (long long)off;
     off = align_up(off + sizeof(unsigned long long) * kMaxTargets, 256);
     mine.off_recv = (long long)off;
-    off = align_up(off + sizeof(double) * 4 * (size_t)(ctx->n_send > 0 ? ctx->n_send : 1), 256);   // parity 0/1 + slot 2: boundary z of the CG ghost-p mode, 16 B per (stamped) value
+    // parity 0/1 + slot 2: boundary z of the CG ghost-p mode, 16 B per (stamped) value
+    off = align_up(off + sizeof(double) * 4 * (size_t)(ctx->n_send > 0 ? ctx->n_send : 1), 256);
     ctx->window_bytes = off;
-    int ok_local = 1;
-    if (cudaMalloc(&ctx->d_window, off) != cudaSuccess) ok_local = 0;
-    if (ok_local) cudaMemset(ctx->d_window, 0, off);
-    if (ok_local && cudaIpcGetMemHandle(&mine.handle, ctx->d_window) != cudaSuccess) ok_local = 0;
+    bool ok = cudaMalloc(&ctx->d_window, off) == cudaSuccess;
+    if (ok) ok = cudaMemset(ctx->d_window, 0, off) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine.handle, ctx->d_window) == cudaSuccess;
     cudaGetLastError();
+    return ok;
+}
+
+// Step 2a (rank-local): map the peers' windows.  false when a peer is not reachable.
+static bool p2p_map_peers(Context *ctx, const Directory *all)
+{
+    const int R = ctx->n_ranks;
+    ctx->peer_windows.assign(R, nullptr);
+    for (int q = 0; q < R; ++q) {
+        if (q == ctx->rank) continue;
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        ctx->peer_windows[q] = p;
+    }
+    return true;
+}
+
+// Step 2b (rank-local): the device-side description of the windows.  *sym_ok = 0 when the
+// neighbour lists of the ranks do not match (the caller agrees with its peers on the verdict).
+static int p2p_describe(Context *ctx, const Directory *all, int *sym_ok)
+{
+    const int R = ctx->n_ranks;
+    const Directory &mine = all[ctx->rank];
+    CommDev h;
+    std::memset(&h, 0, sizeof(h));
+    h.rank = ctx->rank;
+    h.n_ranks = R;
+    h.n_targets = ctx->n_targets;
+    auto base_of = [&](int q) -> char * {
+        return static_cast<char *>(q == ctx->rank ? ctx->d_window : ctx->peer_windows[q]);
+    };
+    for (int q = 0; q < R; ++q) h.mbox[q] = reinterpret_cast<double *>(base_of(q) + all[q].off_mbox);
+    for (int t = 0; t <= ctx->n_targets; ++t) h.send_offs[t] = ctx->send_offs[t];
+    std::vector<long long> peer_block_off((size_t)ctx->n_targets, 0);   // my block inside q's recv buffer
+    *sym_ok = 1;
+    for (int t = 0; t < ctx->n_targets; ++t) {
+        const int q = ctx->target_ids[t];
+        const Directory &dq = all[q];
+        int u = -1;
+        for (int k = 0; k < dq.n_targets; ++k)
+            if (dq.target_ids[k] == ctx->rank) u = k;
+        if (u < 0 || dq.send_offs[u + 1] - dq.send_offs[u] != ctx->target_sizes[t]) {
+            // no rank-local return inside a collective sequence: the verdict is agreed on by
+            // the caller, so that every rank leaves together
+            *sym_ok = 0;
+            continue;
+        }
+        // my values land in the neighbour's recv block reserved for me: same offset
+        // as the neighbour's own send block towards me (blocked by ascending rank)
+        h.peer_recv[t] = reinterpret_cast<double *>(base_of(q) + dq.off_recv) + dq.send_offs[u];
+        peer_block_off[(size_t)t] = dq.send_offs[u];
+        h.peer_recv_stride[t] = dq.n_halo > 0 ? dq.n_halo : 1;
+        h.peer_data_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_data_flag) + u;
+        h.peer_ack_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_ack_flag) + u;
+    }
+    char *me = static_cast<char *>(ctx->d_window);
+    h.my_data_flag = reinterpret_cast<unsigned long long *>(me + mine.off_data_flag);
+    h.my_ack_flag = reinterpret_cast<unsigned long long *>(me + mine.off_ack_flag);
+    h.my_recv = reinterpret_cast<double *>(me + mine.off_recv);
+    h.my_recv_stride = ctx->n_send > 0 ? ctx->n_send : 1;
+    OGL_TRY(dev_alloc(ctx, &ctx->d_commdev, 1));
+    OGL_CUDA(ctx, cudaMemcpy(ctx->d_commdev, &h, sizeof(h), cudaMemcpyHostToDevice));
+    // CG ghost-p mode: destination of every send entry in slot 2 of its neighbour's window
+    std::vector<double *> dst((size_t)ctx->n_send, nullptr);
+    for (label t = 0; t < ctx->n_targets; ++t)
+        for (label k = ctx->send_offs[t]; k < ctx->send_offs[t + 1]; ++k)
+            // slot 2 holds 16 B per entry: my block starts at 2 * (its offset in q's buffer);
+            // peer_recv[t] already contains that offset once
+            dst[(size_t)k] = h.peer_recv[t] + 2 * h.peer_recv_stride[t] + peer_block_off[(size_t)t] +
+                             2 * (size_t)(k - ctx->send_offs[t]);
+    OGL_TRY(dev_alloc(ctx, &ctx->d_push_dst, (size_t)ctx->n_send));
+    OGL_CUDA(ctx, cudaMemcpy(ctx->d_push_dst, dst.data(), sizeof(double *) * dst.size(),
+                             cudaMemcpyHostToDevice));
+    return OGL_OK;
+}
+
+// Build the peer-memory windows with NCCL as the bootstrap channel.  Collective.  Returns OGL_OK
+// with ctx->p2p_ready == false when the topology does not allow it (caller falls back to NCCL).
+static int p2p_setup(Context *ctx)
+{
+    p2p_teardown(ctx);
+    if (ctx->n_ranks > kMaxPeers || ctx->n_targets > kMaxTargets) return OGL_OK;
+    const int R = ctx->n_ranks;
+    Directory mine;
+    int ok_local = p2p_make_window(ctx, mine) ? 1 : 0;
     // ---- all-gather the directories (and whether everyone got this far)
     Directory *d_all = nullptr;
     OGL_TRY(dev_alloc(ctx, &d_all, (size_t)R));
@@ -194,22 +283,8 @@ static int p2p_setup(Context *ctx)
         return fail(ctx, OGL_ERR_NCCL, "window bootstrap: NCCL all-gather failed");
     if (e != cudaSuccess)
         return fail(ctx, OGL_ERR_CUDA, std::string("window bootstrap: ") + cudaGetErrorString(e));
-    // ---- map the peers' windows
-    int mapped = ok_all;
-    ctx->peer_windows.assign(R, nullptr);
-    if (mapped) {
-        for (int q = 0; q < R && mapped; ++q) {
-            if (q == ctx->rank) continue;
-            void *p = nullptr;
-            if (cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                cudaGetLastError();
-                mapped = 0;
-                break;
-            }
-            ctx->peer_windows[q] = p;
-        }
-    }
-    // everyone must agree before the first kernel relies on it
+    // ---- map the peers' windows; everyone must agree before the first kernel relies on it
+    int mapped = ok_all && p2p_map_peers(ctx, all.data()) ? 1 : 0;
     int *d_flag = nullptr;
     OGL_TRY(dev_alloc(ctx, &d_flag, 1));
     cudaMemcpyAsync(d_flag, &mapped, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
@@ -224,60 +299,10 @@ static int p2p_setup(Context *ctx)
         p2p_teardown(ctx);
         return OGL_OK;   // NCCL path
     }
-    // ---- device-side description
-    CommDev h;
-    std::memset(&h, 0, sizeof(h));
-    h.rank = ctx->rank;
-    h.n_ranks = R;
-    h.n_targets = ctx->n_targets;
-    auto base_of = [&](int q) -> char * {
-        return static_cast<char *>(q == ctx->rank ? ctx->d_window : ctx->peer_windows[q]);
-    };
-    for (int q = 0; q < R; ++q) h.mbox[q] = reinterpret_cast<double *>(base_of(q) + all[q].off_mbox);
-    for (int t = 0; t <= ctx->n_targets; ++t) h.send_offs[t] = ctx->send_offs[t];
-    std::vector<long long> peer_block_off((size_t)ctx->n_targets, 0);   // my block inside q's recv buffer
     int sym_ok = 1;
-    for (int t = 0; t < ctx->n_targets; ++t) {
-        const int q = ctx->target_ids[t];
-        const Directory &dq = all[q];
-        int u = -1;
-        for (int k = 0; k < dq.n_targets; ++k)
-            if (dq.target_ids[k] == ctx->rank) u = k;
-        if (u < 0 || dq.send_offs[u + 1] - dq.send_offs[u] != ctx->target_sizes[t]) {
-            // no rank-local return inside a collective sequence: the verdict is agreed on by
-            // the all-reduce(min) below, so that every rank leaves together
-            sym_ok = 0;
-            continue;
-        }
-        // my values land in the neighbour's recv block reserved for me: same offset
-        // as the neighbour's own send block towards me (blocked by ascending rank)
-        h.peer_recv[t] = reinterpret_cast<double *>(base_of(q) + dq.off_recv) + dq.send_offs[u];
-        peer_block_off[(size_t)t] = dq.send_offs[u];
-        h.peer_recv_stride[t] = dq.n_halo > 0 ? dq.n_halo : 1;
-        h.peer_data_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_data_flag) + u;
-        h.peer_ack_flag[t] = reinterpret_cast<unsigned long long *>(base_of(q) + dq.off_ack_flag) + u;
-    }
-    char *me = static_cast<char *>(ctx->d_window);
-    h.my_data_flag = reinterpret_cast<unsigned long long *>(me + mine.off_data_flag);
-    h.my_ack_flag = reinterpret_cast<unsigned long long *>(me + mine.off_ack_flag);
-    h.my_recv = reinterpret_cast<double *>(me + mine.off_recv);
-    h.my_recv_stride = ctx->n_send > 0 ? ctx->n_send : 1;
-    OGL_TRY(dev_alloc(ctx, &ctx->d_commdev, 1));
-    OGL_CUDA(ctx, cudaMemcpy(ctx->d_commdev, &h, sizeof(h), cudaMemcpyHostToDevice));
-    {
-        // CG ghost-p mode: destination of every send entry in slot 2 of its neighbour's window
-        std::vector<double *> dst((size_t)ctx->n_send, nullptr);
-        for (label t = 0; t < ctx->n_targets; ++t)
-            for (label k = ctx->send_offs[t]; k < ctx->send_offs[t + 1]; ++k)
-                // slot 2 holds 16 B per entry: my block starts at 2 * (its offset in q's buffer);
-                // peer_recv[t] already contains that offset once
-                dst[(size_t)k] = h.peer_recv[t] + 2 * h.peer_recv_stride[t] + peer_block_off[(size_t)t] +
-                                 2 * (size_t)(k - ctx->send_offs[t]);
-        OGL_TRY(dev_alloc(ctx, &ctx->d_push_dst, (size_t)ctx->n_send));
-        OGL_CUDA(ctx, cudaMemcpy(ctx->d_push_dst, dst.data(), sizeof(double *) * dst.size(),
-                                 cudaMemcpyHostToDevice));
-    }
-    // nobody may touch a window before every rank has finished zeroing/mapping
+    OGL_TRY(p2p_describe(ctx, all.data(), &sym_ok));
+    // nobody may touch a window before every rank has finished zeroing/mapping; the same
+    // all-reduce carries the verdict on the neighbour lists
     int *d_bar = nullptr;
     OGL_TRY(dev_alloc(ctx, &d_bar, 1));
     cudaMemcpyAsync(d_bar, &sym_ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
@@ -294,6 +319,54 @@ static int p2p_setup(Context *ctx)
                     "neighbour lists of the ranks are not symmetric (processor patches)");
     }
     ctx->p2p_ready = true;
+    return OGL_OK;
+}
+
+// ---- host-driven bootstrap (no NCCL): the caller moves the directories with whatever
+// communicator it has (MPI in an OpenFOAM run, gloo in the tests).  This is also what lets several
+// ranks share ONE device (NCCL refuses duplicate GPUs; CUDA IPC does not care).
+int partition_export(Context *ctx, void *blob, int64_t capacity, int64_t *size)
+{
+    if (size) *size = (int64_t)sizeof(Directory);
+    if (!blob) return OGL_OK;   // size query
+    if (capacity < (int64_t)sizeof(Directory)) return fail(ctx, OGL_ERR_INVALID, "directory buffer too small");
+    if (!ctx->have_partition) return fail(ctx, OGL_ERR_INVALID, "ogl_partition_export before ogl_partition_create");
+    if (ctx->n_ranks > kMaxPeers || ctx->n_targets > kMaxTargets)
+        return fail(ctx, OGL_ERR_UNSUPPORTED, "too many ranks / neighbours for the peer-memory windows");
+    p2p_teardown(ctx);
+    Directory mine;
+    if (!p2p_make_window(ctx, mine)) {
+        p2p_teardown(ctx);
+        return fail(ctx, OGL_ERR_CUDA, "could not allocate / export the peer-memory window");
+    }
+    std::memcpy(blob, &mine, sizeof(mine));
+    return OGL_OK;
+}
+
+int partition_connect(Context *ctx, const void *blobs, int64_t n_blobs)
+{
+    if (!blobs || n_blobs != ctx->n_ranks) return fail(ctx, OGL_ERR_INVALID, "need one directory per rank");
+    if (!ctx->d_window) return fail(ctx, OGL_ERR_INVALID, "ogl_partition_connect before ogl_partition_export");
+    std::vector<Directory> all((size_t)ctx->n_ranks);
+    std::memcpy(all.data(), blobs, sizeof(Directory) * all.size());
+    long long global_n = 0;
+    for (const Directory &d : all) {
+        if (d.magic != kDirectoryMagic) return fail(ctx, OGL_ERR_INVALID, "bad directory blob");
+        global_n += d.n_local;
+    }
+    if (!p2p_map_peers(ctx, all.data())) {
+        p2p_teardown(ctx);
+        return fail(ctx, OGL_ERR_CUDA, "a peer's window cannot be mapped (no P2P path between the devices)");
+    }
+    int sym_ok = 1;
+    OGL_TRY(p2p_describe(ctx, all.data(), &sym_ok));
+    if (!sym_ok) {
+        p2p_teardown(ctx);
+        return fail(ctx, OGL_ERR_INVALID, "neighbour lists of the ranks are not symmetric (processor patches)");
+    }
+    ctx->global_n = global_n;
+    ctx->p2p_ready = true;   // the caller runs a barrier of its own before the first solve
+    invalidate_graph(ctx);
     return OGL_OK;
 }
 
@@ -418,8 +491,11 @@ int partition_create(Context *ctx, label n_local, label n_targets, const label *
     OGL_TRY(upload(ctx, ctx->d_send_idxs, send_idxs, sizeof(label) * ctx->n_send));
     // global size (Partition.H:118-121): sum of the local sizes over all ranks
     ctx->global_n = ctx->n;
-    if (ctx->n_ranks > 1) {
-        if (!ctx->comm) return fail(ctx, OGL_ERR_NCCL, "context has no NCCL communicator");
+    if (ctx->n_ranks > 1 && !ctx->comm) {
+        // host-driven bootstrap: ogl_partition_export / ogl_partition_connect finish the job
+        p2p_teardown(ctx);
+        ctx->global_n = -1;
+    } else if (ctx->n_ranks > 1) {
         long long *d_cnt = nullptr;
         OGL_TRY(dev_alloc(ctx, &d_cnt, 1));
         long long h = ctx->n;

@@ -329,6 +329,8 @@ int ell_prepare_for_loop(Context *ctx, bool ghost);
 // comm.cu ------------------------------------------------------------------------
 int partition_create(Context *ctx, label n_local, label n_targets, const label *target_ids,
                      const label *target_sizes, const label *send_idxs);
+int partition_export(Context *ctx, void *blob, int64_t capacity, int64_t *size);
+int partition_connect(Context *ctx, const void *blobs, int64_t n_blobs);
 int halo_begin(Context *ctx, const double *x, bool guard_done);   // pack (+ NCCL send/recv)
 int halo_end(Context *ctx);                                       // compute stream waits for recv
 int allreduce_red(Context *ctx, int count);                      // state->red[0..count) summed over ranks

@@ -809,6 +809,10 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
         return fail(ctx, OGL_ERR_INVALID, "ogl_solve before ogl_precond_setup");
     if (ctx->n_ranks > 1 && !ctx->have_partition)
         return fail(ctx, OGL_ERR_INVALID, "ogl_solve on several ranks before ogl_partition_create");
+    if (ctx->n_ranks > 1 && !ctx->comm && !use_p2p(ctx))
+        return fail(ctx, OGL_ERR_INVALID,
+                    "context without NCCL id: ogl_partition_export / ogl_partition_connect must set up the "
+                    "peer-memory windows before ogl_solve (comm_mode 1 is not available)");
     if (p->frequency < 1) return fail(ctx, OGL_ERR_INVALID, "frequency must be >= 1");
     if (p->solver == OGL_SOLVER_GMRES) return solve_gmres(ctx, p, res);
     if (p->solver != OGL_SOLVER_CG && p->solver != OGL_SOLVER_BICGSTAB)

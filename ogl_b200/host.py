@@ -81,8 +81,9 @@ class HostMatrixWrapper:
     persistent state lives in the registry-held Context."""
 
     def __init__(self, db: ObjectRegistry, system: LduSystem, controls: dict, field_name: str,
-                 ctx: Context):
+                 ctx: Context, pstream=None):
         self.db, self.system, self.field_name, self.ctx = db, system, field_name, ctx
+        self.pstream = pstream
         self.verbose = int(controls.get("verbose", 0))
         self.scaling = float(controls.get("scaling", 1.0))
         if controls.get("reorderOnHost", False):
@@ -115,6 +116,12 @@ class HostMatrixWrapper:
     def init_non_local_sparsity_pattern(self):
         tid, tsz, sidx = create_communication_pattern(self.system)
         self.ctx.partition_create(self.system.n, tid, tsz, sidx)
+        ps = self.pstream
+        if ps is not None and ps.n_ranks > 1 and ps.nccl_id is None:
+            # the library has no communicator of its own: move the window directories with the
+            # host's (Pstream in an OpenFOAM build), connect, and rendezvous before anyone solves
+            self.ctx.partition_connect(ps.all_gather_bytes(self.ctx.partition_export()))
+            ps.barrier()
         self.ctx.nonlocal_pattern(collect_cells_on_non_local_interface(self.system))
 
     # HostMatrix.C:592-732 -> ogl_values_update

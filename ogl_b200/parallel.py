@@ -15,7 +15,7 @@ class Pstream:
     rank: int = 0
     n_ranks: int = 1
     local_rank: int = 0
-    nccl_id: Optional[bytes] = None
+    nccl_id: Optional[bytes] = None   # None on several ranks: host-driven window bootstrap (below)
 
     @property
     def par_run(self) -> bool:
@@ -25,10 +25,24 @@ class Pstream:
     def master(self) -> bool:
         return self.rank == 0
 
+    # the two collectives the host layer needs when the library has no communicator of its own
+    # (Pstream::gatherList / Pstream::barrier in an OpenFOAM build)
+    def all_gather_bytes(self, blob: bytes):
+        import torch.distributed as dist
+        out = [None] * self.n_ranks
+        dist.all_gather_object(out, blob)
+        return out
 
-def init_from_env(backend: Optional[str] = None) -> Pstream:
+    def barrier(self):
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def init_from_env(backend: Optional[str] = None, nccl: bool = True) -> Pstream:
     """Join the job described by RANK/WORLD_SIZE/LOCAL_RANK/MASTER_* (torchrun)
-    and agree on an NCCL unique id for the solver library."""
+    and agree on an NCCL unique id for the solver library.  nccl=False: no id -- the library's
+    peer-memory windows are bootstrapped through this process group instead (several ranks may
+    then share one device; set OGL_B200_DEVICE to pin them)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
@@ -45,6 +59,8 @@ def init_from_env(backend: Optional[str] = None) -> Pstream:
         if backend == "nccl":
             torch.cuda.set_device(local)
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    if not nccl:
+        return Pstream(rank, world, int(os.environ.get("OGL_B200_DEVICE", local)), None)
     return Pstream(rank, world, local, broadcast_nccl_id(rank))
 
 

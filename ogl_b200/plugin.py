@@ -150,7 +150,7 @@ class GKOlduBaseSolver:
         if self.precond_name not in ("none", "BJ"):
             raise FatalError(f"OGL does not support the preconditioner: {self.precond_name}\n"
                              "Valid Choices: none, BJ")
-        self.host_matrix = HostMatrixWrapper(db, matrix, controls, field_name, self.ctx)
+        self.host_matrix = HostMatrixWrapper(db, matrix, controls, field_name, self.ctx, self.pstream)
 
     # lduLduBase.H:189-308
     def solve(self, psi: np.ndarray, source: np.ndarray) -> SolverPerformance:

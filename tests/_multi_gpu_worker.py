@@ -25,13 +25,29 @@ CASES = {
 }
 
 MODES = (0, 1, 2, 3, 4, 5)
+SHARED_MODES = (0, 2, 3, 4, 5)    # ranks sharing one device: no NCCL data path (mode 1)
+BIG = 72                          # cells per direction per rank of the "beyond toy size" case
+
+
+def big_dims(procs):
+    return tuple(BIG * p for p in procs)
+
+
+def big_rank_system(procs, rank):
+    """>= 64^3 cells per rank: the automatic kernel selection of the benchmark sizes (pattern-coded
+    ELL copy of the ghosted matrix, ghost-p CG, no persistent loop kernel)."""
+    dims = big_dims(procs)
+    return cases.build_rank_system(cases.PressureModel(dims, coef=1e-5), dims, procs, rank)
 
 
 def main():
     out, procs = sys.argv[1], tuple(int(v) for v in sys.argv[2].split(","))
-    ps = init_from_env("nccl")
+    shared = len(sys.argv) > 3 and sys.argv[3] == "shared"
+    # shared: every rank on ONE device, gloo for the rendezvous and the window bootstrap
+    ps = init_from_env("gloo", nccl=False) if shared else init_from_env("nccl")
     db = ObjectRegistry()
     results = {}
+    modes = SHARED_MODES if shared else MODES
     # every case on the four data paths: 0 peer-memory windows, halo fused into the SpMV, CG
     # in ghost-p mode (default); 1 NCCL; 2 peer-memory windows with separate pack / non-local
     # kernels; 3 like 0 but CG with the flag handshake instead of ghost p; 4 / 5 the large-system
@@ -39,7 +55,7 @@ def main():
     # no persistent loop kernel, CG with (4) / without (5) the p-update fused into the SpMV (ghost
     # z pulled from the window inside the SpMV)
     for name, (builder, solver, precond, mbs, tol), mode in (
-            (n, c, m) for n, c in CASES.items() for m in MODES):
+            (n, c, m) for n, c in CASES.items() for m in modes):
         s = builder(procs)[ps.rank]
         controls = {"solver": solver, "executor": "cuda", "tolerance": tol, "relTol": 0.0,
                     "adaptMinIter": False, "krylovDim": 30, "comm_mode": 1 if mode == 1 else 0,
@@ -57,6 +73,18 @@ def main():
                          "final": perf.final_residual, "x": psi.tolist(), "y": y.tolist(),
                          "global_n": sol.ctx.partition_sizes()[1],
                          "p2p": sol.ctx.get_option("p2p_active")}
+    # the benchmark-size configuration with everything on automatic
+    s = big_rank_system(procs, ps.rank)
+    controls = {"solver": "GKOCG", "executor": "cuda", "tolerance": 1e-7, "relTol": 0.0, "adaptMinIter": False,
+                "preconditioner": "BJ"}
+    sol = lduMatrix_solver_New("big", s, controls, db, ps)
+    psi = s.psi.copy()
+    perf = sol.solve(psi, s.source)
+    results["big"] = {"iters": perf.n_iterations, "init": perf.initial_residual, "final": perf.final_residual,
+                      "variant": sol.ctx.get_option("spmv_variant_in_use"),
+                      "coded": sol.ctx.get_option("ell_coded_active"),
+                      "fused_loop": sol.ctx.get_option("fused_pcg_active")}
+    np.save(f"{out}.big.{ps.rank}.npy", psi)
     json.dump(results, open(f"{out}.{ps.rank}", "w"))
     import torch.distributed as dist
     dist.barrier()

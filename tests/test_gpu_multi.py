@@ -28,28 +28,56 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("procs", [(2, 1, 1), (2, 2, 1), (2, 2, 2)])
-def test_decomposed_solves_match_oracle(oracle, tmp_path, procs):
+def run_workers(tmp_path, procs, shared):
     world = int(np.prod(procs))
-    if n_gpus() < world:
-        pytest.skip(f"needs {world} GPUs")
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from _multi_gpu_worker import CASES, MODES
     out = str(tmp_path / "res")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
            str(world), "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "tests", "_multi_gpu_worker.py"), out, ",".join(map(str, procs))]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ)
+    if shared:
+        cmd.append("shared")
+        env["OGL_B200_DEVICE"] = "0"
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     if p.returncode != 0:
         import glob
         errs = "".join(open(f).read()[-1500:] for f in sorted(glob.glob(out + ".err.*"))[:2])
         raise AssertionError(errs + p.stderr[-1500:])
-    res = [json.load(open(f"{out}.{r}")) for r in range(world)]
-    assert res[0]["pressure_cg@0"]["p2p"] == 1, "peer-memory path not active on an NVLink box"
-    assert res[0]["pressure_cg@1"]["p2p"] == 0 and res[0]["pressure_cg@2"]["p2p"] == 1
+    return out, [json.load(open(f"{out}.{r}")) for r in range(world)]
+
+
+# `shared`: all ranks of the decomposition on device 0 (one process each, CUDA-IPC windows inside
+# the device, gloo for the bootstrap) -- the decomposed path runs on a single-GPU box too.
+@pytest.mark.parametrize("procs,shared", [((2, 1, 1), True), ((2, 2, 1), True),
+                                          ((2, 1, 1), False), ((2, 2, 1), False), ((2, 2, 2), False)])
+def test_decomposed_solves_match_oracle(oracle, tmp_path, procs, shared):
+    world = int(np.prod(procs))
+    if not shared and n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _multi_gpu_worker import CASES, MODES, SHARED_MODES, big_dims
+    from ogl_b200 import cases
+    out, res = run_workers(tmp_path, procs, shared)
+    modes = SHARED_MODES if shared else MODES
+    assert res[0]["pressure_cg@0"]["p2p"] == 1, "peer-memory path not active"
+    if not shared:
+        assert res[0]["pressure_cg@1"]["p2p"] == 0
+    assert res[0]["pressure_cg@2"]["p2p"] == 1
     assert res[0]["pressure_cg@3"]["p2p"] == 1 and res[0]["pressure_cg@4"]["p2p"] == 1
+    # the benchmark-size case: automatic selection = coded ELL copy of the ghosted matrix + ghost-p CG
+    dims = big_dims(procs)
+    systems = cases.build_case(cases.PressureModel(dims, coef=1e-5), dims, procs)
+    o = oracle.solve([oracle.assemble(s) for s in systems], "GKOCG", "BJ", tolerance=1e-7,
+                     threads=os.cpu_count() or 1)
+    assert {r["big"]["variant"] for r in res} == {7} and all(r["big"]["coded"] & 2 for r in res)
+    assert all(r["big"]["fused_loop"] == 0 for r in res)
+    assert {abs(r["big"]["iters"] - o.n_iterations) <= 2 for r in res} == {True}
+    x = gather_global(systems, [np.load(f"{out}.big.{r}.npy") for r in range(world)])
+    xo = gather_global(systems, o.x)
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= 1e-8
+    del systems, o, x, xo
     for name, (builder, solver, precond, mbs, tol) in (
-            (f"{n}@{m}", c) for n, c in CASES.items() for m in MODES):
+            (f"{n}@{m}", c) for n, c in CASES.items() for m in modes):
         systems = builder(procs)
         asms = [oracle.assemble(s) for s in systems]
         o = oracle.solve(asms, solver, precond, max_block_size=mbs, tolerance=tol, krylov_dim=30)
