@@ -48,6 +48,10 @@ struct SolveState {
     int restart_iter, final_iter, krylov_dim, need_restart;
     double res_norm2;
     int comm_error, pad2;   // peer synchronisation timed out (multi-GPU)
+    // device time of the last EVALUATED criterion call (globaltimer ns around the epilogue that
+    // ran it): what the reference measures on the host around its norm1 + D2H
+    // (StoppingCriterion.C:89,145-149) and feeds into the adaptive minIter / frequency
+    unsigned long long crit_ns;
 };
 
 struct DeviceBuffer {

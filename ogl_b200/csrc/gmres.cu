@@ -384,6 +384,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     res->criterion_calls = hs.iter;
     res->n_iterations = hs.iter;
     res->solve_us = ms * 1e3;
+    res->resnorm_us = hs.crit_ns > 0 ? (double)hs.crit_ns * 1e-3 : 0.0;   // see solver.cu:solve
     res->kernel_launches = ctx->launches - launches0;
     if (hs.comm_error)
         return fail(ctx, OGL_ERR_NCCL, "peer synchronisation timed out (a rank left the solve?)");

@@ -36,8 +36,32 @@ enum Epilogue : int {
 // StoppingCriterion.C:71-151, evaluated by one thread on the device.
 // `norm1` is the (already globally summed) L1 norm of the residual handed to
 // the criterion.  Returns true when the solver must stop.
-__device__ __forceinline__ bool criterion_check(SolveState *s, double norm1,
-                                                double *history)
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ bool criterion_check_untimed(SolveState *s, double norm1, double *history);
+
+// timed wrapper: an evaluated call records its own duration (skipped calls cost nothing and
+// leave the record alone, like the early returns of StoppingCriterion.C:77-87)
+__device__ __forceinline__ bool criterion_check(SolveState *s, double norm1, double *history)
+{
+    const int it = s->iter;
+    const bool evaluated = !(it > 0 && it < s->min_iter) && (it % s->frequency == 0);
+    const unsigned long long t0 = evaluated ? globaltimer_ns() : 0ull;
+    const bool stop = criterion_check_untimed(s, norm1, history);
+    if (evaluated) {
+        const unsigned long long dt = globaltimer_ns() - t0;
+        s->crit_ns = dt > 0 ? dt : 1ull;   // globaltimer ticks in steps of up to 1 us on some parts
+    }
+    return stop;
+}
+
+__device__ __forceinline__ bool criterion_check_untimed(SolveState *s, double norm1,
+                                                        double *history)
 {
     const int it = s->iter;
     if (it > 0 && it < s->min_iter) {  // :77-81

@@ -892,8 +892,12 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     // GKOBiCGStab.H:112-115: two criterion calls per iteration
     res->n_iterations = p->solver == OGL_SOLVER_BICGSTAB ? hs.iter / 2 : hs.iter;
     res->solve_us = ms * 1e3;
-    // the L1 norm rides inside the fused update kernel: no separate evaluation
-    res->resnorm_us = 0.0;
+    // The L1 norm rides inside the fused update kernel; what a criterion evaluation costs here is
+    // the scalar epilogue that runs it, timed on the device (reduce.cuh:criterion_check).  The host
+    // layers divide the time per iteration by it exactly as lduLduBase.H:286-293 does, so the
+    // reference's adaptive minIter / evaluation frequency is live (a cheap evaluation gives
+    // frequency 1 and minIter = relaxationFactor * previous iterations).
+    res->resnorm_us = hs.crit_ns > 0 ? (double)hs.crit_ns * 1e-3 : 0.0;
     if (ctx->loop_body_iters > 0) {
         // device-side loop: whole bodies ran, up to and including the one the criterion fired in
         const int64_t calls = hs.iter > 0 ? hs.iter - 1 : 0;   // minus the prologue's criterion call

@@ -37,6 +37,12 @@ class Pstream:
         import torch.distributed as dist
         dist.barrier()
 
+    def broadcast_scalar(self, value: float, src: int = 0) -> float:
+        import torch.distributed as dist
+        box = [float(value)]
+        dist.broadcast_object_list(box, src=src)
+        return float(box[0])
+
 
 def init_from_env(backend: Optional[str] = None, nccl: bool = True) -> Pstream:
     """Join the job described by RANK/WORLD_SIZE/LOCAL_RANK/MASTER_* (torchrun)

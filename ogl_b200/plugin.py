@@ -183,6 +183,7 @@ class GKOlduBaseSolver:
         min_iter, frequency = crit.effective(
             export_res, get_solve_prev_iters(f, db, crit.is_final),
             get_solve_prev_rel_res_cost(f, db))
+        self.last_min_iter, self.last_frequency = min_iter, frequency
         res = ctx.solve(self.solver_id, crit.tolerance, crit.rel_tol, min_iter, crit.max_iter,
                         frequency, int(c.get("krylovDim", 100)), export_res)
         ctx.vector_download(L.OGL_VEC_X, psi)   # copy_back, Vector.H:144-167
@@ -193,6 +194,10 @@ class GKOlduBaseSolver:
         set_solve_prev_iters(f, db, res.criterion_calls, crit.is_final)
         t_iter = res.solve_us / max(res.n_iterations, 1)
         rel_cost = t_iter / res.resnorm_us if res.resnorm_us > 0 else 0.0
+        if self.pstream.par_run:
+            # every rank must derive the same minIter / frequency next time: rank 0's figure
+            # (lduLduBase.H:290-291 broadcasts it over the host communicator)
+            rel_cost = self.pstream.broadcast_scalar(rel_cost)
         set_solve_prev_rel_res_cost(f, db, rel_cost)
         self.last_result = res
         return perf

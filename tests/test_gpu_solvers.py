@@ -428,3 +428,79 @@ def test_cg_p_update_fused_into_the_spmv_is_bit_identical(ctx, oracle, precond):
     assert abs(base[0] - o.n_iterations) <= ITER_TOL and rel_l2(base[2], o.x[0]) <= L2_TOL
     for k, v in (("spmv_variant", 0), ("fused_pcg", 2), ("fuse_p", 0), ("ell_coded", 1)):
         ctx.set_option(k, v)
+
+
+# ---- oracle comparisons AT the benchmarked sizes (slow: the oracle runs on the host cores) ----
+
+def _check_big(ctx, oracle, s, solver, precond, tol, **kw):
+    import os
+    upload_system(ctx, s, partition=False)
+    r, x = gpu_solve(ctx, solver, precond, 1, tolerance=tol, **kw)
+    o = oracle.solve([oracle.assemble(s)], solver, precond, tolerance=tol, threads=os.cpu_count() or 1, **kw)
+    assert abs(r.n_iterations - o.n_iterations) <= ITER_TOL, (r.n_iterations, o.n_iterations)
+    assert rel_l2(x, o.x[0]) <= L2_TOL
+    assert r.norm_factor == pytest.approx(o.norm_factor, rel=1e-10)
+    assert r.final_residual < tol
+    return r, o
+
+
+def test_oracle_parity_at_100_cubed_pressure_cg(ctx, oracle):
+    """BASELINE configs[1] at full size against the oracle (and its pinned count)."""
+    import json, os
+    r, o = _check_big(ctx, oracle, cases.pressure_3d(100)[0], "GKOCG", "BJ", 1e-6)
+    exp = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bench_expected.json")))
+    assert abs(r.n_iterations - exp["pressure_100_x1"]["iterations"]) <= ITER_TOL
+    assert ctx.get_option("spmv_variant_in_use") == 7 and ctx.get_option("ell_coded_active") & 1
+
+
+def test_oracle_parity_at_200_cubed_momentum_bicgstab(ctx, oracle):
+    """BASELINE configs[2] at full size (8 M cells, asymmetric): 21 iterations."""
+    import json, os
+    r, o = _check_big(ctx, oracle, cases.momentum_3d(200)[0], "GKOBiCGStab", "BJ", 1e-5)
+    exp = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bench_expected.json")))
+    assert abs(r.n_iterations - exp["momentum_200_x1"]["iterations"]) <= ITER_TOL
+
+
+def test_oracle_parity_channel_gmres_half_million_cells(ctx, oracle):
+    """BASELINE configs[3] at a realistic size on one rank: 128x64x64, cyclic in x and z, GMRES(100)."""
+    r, o = _check_big(ctx, oracle, cases.channel((128, 64, 64), (1, 1, 1))[0], "GKOGMRES", "BJ", 1e-6,
+                      krylov_dim=100)
+    assert r.criterion_calls == o.criterion_calls
+
+
+def test_adaptive_criterion_is_live_over_a_time_loop(oracle):
+    """The reference's DEFAULT keywords (adaptMinIter true, relaxationFactor 0.6): from the second
+    solve of a field on, minIter = 0.6 * previous criterion calls and the evaluation frequency
+    follows the measured cost ratio (StoppingCriterion.H:199-209 fed by lduLduBase.H:286-293).
+    The library reports the device-side cost of a criterion evaluation, so the rule fires; the
+    oracle is driven with the same adapted numbers and must give the same iterations."""
+    db = ObjectRegistry()
+    controls = {"solver": "GKOCG", "preconditioner": "BJ", "executor": "cuda", "tolerance": 1e-8, "relTol": 0.0}
+    s = cases.pressure_3d(20)[0]
+    a = oracle.assemble(s)
+    rng = np.random.default_rng(4)
+    used = []
+    for step in range(4):
+        source = s.source * (1.0 + 0.3 * step) + 1e-7 * rng.normal(size=s.n)
+        sol = lduMatrix_solver_New("p", s, controls, db)
+        psi = np.zeros(s.n)               # ignored after the first step (updateInitGuess false)
+        perf = sol.solve(psi, source)
+        used.append((sol.last_min_iter, sol.last_frequency))
+        assert sol.last_result.resnorm_us > 0
+        a.b = source.copy()               # the oracle continues from ITS previous solution
+        o = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-8, min_iter=sol.last_min_iter,
+                         frequency=sol.last_frequency)
+        a.x = o.x[0].copy()
+        assert abs(perf.n_iterations - o.n_iterations) <= ITER_TOL, (step, perf.n_iterations, o.n_iterations)
+        assert rel_l2(psi, o.x[0]) <= L2_TOL
+        if step > 0:
+            prev_calls = used_calls
+            assert sol.last_min_iter == int(prev_calls * 0.6) > 0      # adaptation fired
+            assert 1 <= sol.last_frequency <= 100
+            assert perf.n_iterations >= sol.last_min_iter
+        used_calls = sol.last_result.criterion_calls
+    assert used[0] == (0, 1)
+    # export disables the adaptation (StoppingCriterion.H:201)
+    sol = lduMatrix_solver_New("p", s, dict(controls, export=True), db)
+    sol.solve(np.zeros(s.n), s.source)
+    assert (sol.last_min_iter, sol.last_frequency) == (0, 1)
