@@ -206,6 +206,7 @@ struct Context {
     int precond_kind = OGL_PRECOND_NONE;
     label max_block_size = 1;
     label bj_pattern_mbs = 0;    // block pointers were built for this maxBlockSize
+    bool bj_uniform = false;     // every block has exactly maxBlockSize rows (the last one may be shorter)
     bool have_precond = false;
     double *d_inv_diag = nullptr;
     label n_blocks = 0;

@@ -238,6 +238,9 @@ int precond_setup(Context *ctx, int kind, label mbs)
             const int64_t sz = bp[b + 1] - bp[b];
             offs[b + 1] = offs[b] + sz * sz;
         }
+        bool uniform = true;
+        for (label b = 0; b + 1 < nb && uniform; ++b) uniform = (bp[b + 1] - bp[b]) == mbs;
+        ctx->bj_uniform = uniform && nb > 0 && (bp[nb] - bp[nb - 1]) <= mbs;
         ctx->n_blocks = nb;
         ctx->inv_blocks_len = offs[nb];
         ctx->bj_pattern_mbs = mbs;

@@ -46,6 +46,10 @@ struct VecK {
     int pack;                // k_cg_p: 1 store boundary p', 2 update ghost p; k_cg_xr: 1 push boundary z
     double *const *push_dst;   // k_cg_xr: destination of every send entry (slot 2 of the peer windows)
     cudaGraphConditionalHandle cond;   // k_cg_xr inside a WHILE-node body: cleared when the solve is done
+    // block Jacobi (k_cg_xr_bj): block of a row, block row ranges, offsets of the inverse blocks
+    const label *bj_row_block, *bj_block_ptrs;
+    const int64_t *bj_block_offs;
+    const double *bj_inv;
 };
 
 #define GRID_STRIDE(i, n)                                                             \
@@ -294,6 +298,102 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr(const VecK a)
     }
     const int last = grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
     // device-side loop (CUDA-graph WHILE node): the criterion ends it
+    if (a.cond && last == 2 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
+}
+
+// cg::step_2 fused with the BLOCK-Jacobi apply (maxBlockSize > 1) + <r,z> + |r|_1 + criterion:
+//   z_i = sum_j Minv[i][j] r'_j over the rows j of i's block.  The block-mates' r' = r - alpha q are
+//   recomputed from the OLD r buffer and q (adjacent rows: L1 hits) -- the same operation on the same
+//   operands as the stored r', so z has the bits of the separate apply kernel -- and r' goes to the
+//   other r buffer, so no thread reads what another one writes.  One pass instead of two, and the
+//   iteration keeps its in-kernel criterion (device-side loop).
+//   in0 = p, in1 = q, in3 = r ; out0 = x, out1 = r', out2 = z
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr_bj(const VecK a)
+{
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (a.guard_done && a.state->done) {
+        if (a.cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(a.ea, 0);
+    const bool upd = a.state->beta != 0.0;
+    const double t = a.state->coef_x;
+    double red[2] = {0.0, 0.0};
+    GRID_STRIDE(i, a.n) {
+        double r = a.in3[i];
+        if (upd) {
+            a.out0[i] = __dadd_rn(a.out0[i], __dmul_rn(t, a.in0[i]));
+            r = __dsub_rn(r, __dmul_rn(t, a.in1[i]));
+        }
+        a.out1[i] = r;
+        red[1] = __dadd_rn(red[1], fabs(r));
+        const label b = a.bj_row_block[i];
+        const label lo = a.bj_block_ptrs[b], sz = a.bj_block_ptrs[b + 1] - lo;
+        const double *m = a.bj_inv + a.bj_block_offs[b] + (int64_t)(i - lo) * sz;
+        double z = 0.0;
+        for (label j = 0; j < sz; ++j) {
+            double rj = a.in3[lo + j];
+            if (upd) rj = __dsub_rn(rj, __dmul_rn(t, a.in1[lo + j]));
+            z = __dadd_rn(z, __dmul_rn(m[j], rj));
+        }
+        a.out2[i] = z;
+        red[0] = __dadd_rn(red[0], __dmul_rn(r, z));
+    }
+    const int last = grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+    if (a.cond && last == 2 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
+}
+
+// The same for the common case of UNIFORM blocks (every block has exactly BS rows, the last one
+// possibly fewer: what find_blocks + agglomeration give for a mesh-ordered stencil matrix): block and
+// inverse-row addresses follow from the row index, so all 3 BS loads of a row are independent and
+// issued together instead of chasing row -> block -> offset -> entries.
+template <int BS>
+__global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr_bj_uniform(const VecK a)
+{
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (a.guard_done && a.state->done) {
+        if (a.cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(a.ea, 0);
+    const bool upd = a.state->beta != 0.0;
+    const double t = a.state->coef_x;
+    double red[2] = {0.0, 0.0};
+    const int64_t n_full = (int64_t)a.n / BS * BS;   // rows in complete blocks
+    GRID_STRIDE(i, a.n) {
+        const int64_t lo = i / BS * BS;
+        const int li = (int)(i - lo);
+        const int sz = lo < n_full ? BS : (int)(a.n - lo);
+        // inverse blocks are stored block after block, row-major: full blocks take BS*BS entries
+        const double *m = a.bj_inv + lo * BS + (int64_t)li * sz;
+        double mv[BS], rv[BS], qv[BS];
+#pragma unroll
+        for (int j = 0; j < BS; ++j) mv[j] = j < sz ? __ldcs(&m[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < BS; ++j) rv[j] = j < sz ? a.in3[lo + j] : 0.0;
+        if (upd) {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) qv[j] = j < sz ? a.in1[lo + j] : 0.0;
+        }
+        double r = 0.0, z = 0.0;
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+            if (j < sz) {
+                double rj = rv[j];
+                if (upd) rj = __dsub_rn(rj, __dmul_rn(t, qv[j]));
+                if (j == li) r = rj;
+                z = __dadd_rn(z, __dmul_rn(mv[j], rj));
+            }
+        }
+        if (upd) a.out0[i] = __dadd_rn(a.out0[i], __dmul_rn(t, a.in0[i]));
+        a.out1[i] = r;
+        a.out2[i] = z;
+        red[1] = __dadd_rn(red[1], fabs(r));
+        red[0] = __dadd_rn(red[0], __dmul_rn(r, z));
+    }
+    const int last = grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
     if (a.cond && last == 2 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
 }
 
@@ -566,7 +666,7 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
     }
     }
     {
-        VecK a = base_args(ctx, pk == 2 ? EPI_NONE : EPI_CG_RHO_CHECK, true, pk == 2 ? 0 : 2);
+        VecK a = base_args(ctx, EPI_CG_RHO_CHECK, true, 2);
         a.in0 = p;
         a.in1 = q;
         a.in2 = ctx->d_inv_diag;
@@ -590,9 +690,19 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
         if (pk == 0) LAUNCH_XR(0);
         else if (pk == 1) LAUNCH_XR(1);
         else {
-            LAUNCH_XR(2);
-            OGL_TRY(precond_apply(ctx, r, z, r, 0, true, EPI_CG_RHO_CHECK,
-                                  ctx->n_ranks == 1 || use_p2p(ctx), 2));
+            a.bj_row_block = ctx->d_row_block;
+            a.bj_block_ptrs = ctx->d_block_ptrs;
+            a.bj_block_offs = ctx->d_block_offs;
+            a.bj_inv = ctx->d_inv_blocks;
+#define LAUNCH_BJ(KERNEL) \
+    OGL_CUDA(ctx, launch_pdl(KERNEL, vec_grid(ctx), kT, 0, ctx->stream, ctx->use_pdl != 0, a))
+            const int bs = ctx->bj_uniform ? (int)ctx->max_block_size : 0;
+            if (bs == 2) LAUNCH_BJ(k_cg_xr_bj_uniform<2>);
+            else if (bs == 4) LAUNCH_BJ(k_cg_xr_bj_uniform<4>);
+            else if (bs == 8) LAUNCH_BJ(k_cg_xr_bj_uniform<8>);
+            else LAUNCH_BJ(k_cg_xr_bj);
+#undef LAUNCH_BJ
+            ctx->launches++;
         }
     }
     return finish_reduction(ctx, 2, EPI_CG_RHO_CHECK, true);
@@ -707,16 +817,17 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
     cudaStream_t st = ctx->stream;
     const bool graph_ok = ctx->use_graph && (ctx->n_ranks == 1 || use_p2p(ctx)) &&
                           ctx->profile_stride == 0;
-    // CG with an in-kernel criterion (no block-Jacobi apply kernel): the chunk becomes the body
+    // CG (its x/r-update kernels carry the criterion): the chunk becomes the body
     // of a WHILE node; k_cg_xr clears the condition when the criterion fires, so a solve is one
     // graph launch with no early-exit launches behind the last iteration and no host polling
-    const bool loop = graph_ok && ctx->device_loop && solver == OGL_SOLVER_CG && pk_of(ctx) != 2;
+    const bool loop = graph_ok && ctx->device_loop && solver == OGL_SOLVER_CG;
     int chunk = (int)(loop ? ctx->loop_iters : ctx->chunk_iters);
     if (chunk < 1) chunk = 1;
     chunk += chunk & 1;
     const int64_t sig0 = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^ (ctx->use_pdl << 60) ^
                          ((int64_t)chunk << 32) ^ (int64_t)ctx->n ^ (ctx->spmv_variant << 56);
-    const int64_t sig = sig0 ^ ((int64_t)(loop ? 1 : 0) << 62);
+    const int64_t sig = sig0 ^ ((int64_t)(loop ? 1 : 0) << 62) ^ ((int64_t)(ctx->bj_uniform ? 1 : 0) << 61) ^
+                        ((int64_t)ctx->max_block_size << 24);
     if (graph_ok && (!ctx->graph_exec || ctx->graph_sig != sig)) {
         if (ctx->graph_exec) {
             cudaGraphExecDestroy(ctx->graph_exec);
