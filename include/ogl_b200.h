@@ -219,7 +219,11 @@ int ogl_commbench(ogl_ctx *ctx, int mode, int32_t reps, double *us);
 /* ---- Matrix-Market export ---------------------------------------
  * replaces export_mtx / export_vec (common/common.C:31-58,
  * CsrMatrixWrapper.H:273-290, Vector.H:173-176): coordinate layout,
- * setprecision(15).  which: 0 local, 1 non-local, 2 rhs b. */
+ * setprecision(15).  which: 0 local, 1 non-local, 2 rhs b, 3 the partition
+ * side-car `<field>_partition.json` ({rank, n_ranks, n_local, target_ids,
+ * target_sizes}: OGL's communication pattern, HostMatrix.C:251-306), which the
+ * reference does not write and without which a decomposed dump cannot be read
+ * back (ogl_b200/mtxio.py:import_decomposed). */
 int ogl_export_mtx(ogl_ctx *ctx, int which, const char *path);
 
 #ifdef __cplusplus

@@ -761,10 +761,20 @@ int ogl_export_mtx(ogl_ctx *ctx, int which, const char *path)
 {
     CHECK_CTX(ctx);
     if (!path) return fail(ctx, OGL_ERR_INVALID, "null path");
-    if (which < 0 || which > 2) return fail(ctx, OGL_ERR_INVALID, "which in {0,1,2}");
+    if (which < 0 || which > 3) return fail(ctx, OGL_ERR_INVALID, "which in {0,1,2,3}");
     std::ofstream os(path);
     if (!os) return fail(ctx, OGL_ERR_INVALID, std::string("cannot open ") + path);
     os << std::setprecision(15);   // common.C:48
+    if (which == 3) {
+        // partition side-car (JSON): the communication pattern the matrices do not carry
+        os << "{\"rank\": " << ctx->rank << ", \"n_ranks\": " << ctx->n_ranks << ", \"n_local\": " << ctx->n
+           << ", \"target_ids\": [";
+        for (size_t t = 0; t < ctx->target_ids.size(); ++t) os << (t ? ", " : "") << ctx->target_ids[t];
+        os << "], \"target_sizes\": [";
+        for (size_t t = 0; t < ctx->target_sizes.size(); ++t) os << (t ? ", " : "") << ctx->target_sizes[t];
+        os << "]}\n";
+        return OGL_OK;
+    }
     if (which == 2) {
         if (!ctx->have_b) return fail(ctx, OGL_ERR_INVALID, "no rhs");
         std::vector<double> b(ctx->n);

@@ -17,8 +17,12 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .cases import LduSystem
+import json
+
+from .cases import Interface, LduSystem
 from .host import FatalError
+
+SIDECAR = "_partition.json"
 
 
 def read_mtx(path: str):
@@ -136,3 +140,83 @@ def import_system(folder: str, field: str, psi: Optional[np.ndarray] = None) -> 
     return LduSystem(n=n, lower_addr=lower_addr, upper_addr=upper_addr, diag=diag, upper=upper, lower=lower,
                      interfaces=[], source=source, psi=np.zeros(n) if psi is None else np.asarray(psi, float).copy(),
                      global_ids=np.arange(n, dtype=np.int64))
+
+
+# ---- decomposed dumps ---------------------------------------------------------------------
+# The reference writes one set of files per processor directory (common.C:31-58: the path is
+# `<case>/processorN/<time>/`); the matrices alone do not say which neighbour a halo column belongs
+# to.  This library's export therefore adds a small side-car next to them,
+# `<field>_partition.json` = {rank, n_ranks, n_local, target_ids, target_sizes} -- OGL's
+# communication pattern (HostMatrix.C:251-306) --, and `import_decomposed` rebuilds every rank's
+# processor interfaces from it: halo column k of `_A_non_local.mtx` is the k-th processor face
+# (HostMatrix.C:438-466), its row the face cell, its value minus the boundary coefficient
+# (:199-204), and the columns are blocked by ascending neighbour rank.
+
+def write_partition_sidecar(folder: str, field: str, rank: int, n_ranks: int, n_local: int,
+                            target_ids, target_sizes) -> None:
+    with open(os.path.join(folder, field + SIDECAR), "w") as f:
+        json.dump({"rank": int(rank), "n_ranks": int(n_ranks), "n_local": int(n_local),
+                   "target_ids": [int(t) for t in target_ids],
+                   "target_sizes": [int(t) for t in target_sizes]}, f)
+
+
+def import_rank(folder: str, field: str) -> LduSystem:
+    """One processor directory of a decomposed dump -> that rank's LduSystem (interfaces included)."""
+    side = os.path.join(folder, field + SIDECAR)
+    if not os.path.exists(side):
+        raise FatalError(f"{side} is missing: a decomposed dump needs the partition side-car this "
+                         "library's export writes (the matrices do not carry the neighbour lists)")
+    part = json.load(open(side))
+    kind, n, n_cols, rows, cols, vals = read_mtx(os.path.join(folder, field + "_A_local.mtx"))
+    if kind != "coordinate" or n != n_cols or n != part["n_local"]:
+        raise FatalError("local matrix must be a square coordinate matrix of the side-car's size")
+    lower_addr, upper_addr, diag, upper, lower = ldu_from_coo(n, rows, cols, vals)
+    nk = read_mtx(os.path.join(folder, field + "_A_non_local.mtx"))
+    if nk[0] != "coordinate" or nk[1] != n:
+        raise FatalError("non-local matrix must be an n x n_halo coordinate matrix")
+    n_halo, nl_rows, nl_cols, nl_vals = nk[2], nk[3], nk[4], nk[5]
+    sizes = [int(t) for t in part["target_sizes"]]
+    if sum(sizes) != n_halo or len(nl_vals) != n_halo or len(sizes) != len(part["target_ids"]):
+        raise FatalError("side-car and non-local matrix disagree on the halo size")
+    if n_halo and not np.array_equal(np.sort(nl_cols), np.arange(n_halo)):
+        raise FatalError("every halo column must appear exactly once (one entry per processor face)")
+    by_col = np.argsort(nl_cols, kind="stable")       # running interface index order
+    face_cells, bou = nl_rows[by_col], -nl_vals[by_col]
+    interfaces, off = [], 0
+    for nbr, size in zip(part["target_ids"], sizes):
+        interfaces.append(Interface("processor", face_cells[off:off + size].astype(np.int32),
+                                    bou[off:off + size].copy(), nbr_rank=int(nbr)))
+        off += size
+    rhs = os.path.join(folder, field + "_rhs_b_.mtx")
+    source = read_mtx(rhs)[3][:, 0].copy() if os.path.exists(rhs) else np.zeros(n)
+    if source.size != n:
+        raise FatalError("right-hand side must be an n x 1 array")
+    return LduSystem(n=n, lower_addr=lower_addr, upper_addr=upper_addr, diag=diag, upper=upper, lower=lower,
+                     interfaces=interfaces, source=source, psi=np.zeros(n),
+                     global_ids=np.arange(n, dtype=np.int64), rank=int(part["rank"]),
+                     n_ranks=int(part["n_ranks"]))
+
+
+def import_decomposed(case_folder: str, time_name: str, field: str):
+    """`<case>/processor0..R-1/<time>/<field>_*` -> [LduSystem per rank] with consistent
+    global ids (rank offsets by exclusive scan of the local sizes, gkoGlobalIndex.C:172-201)."""
+    systems, r = [], 0
+    while os.path.isdir(os.path.join(case_folder, f"processor{r}", time_name)):
+        systems.append(import_rank(os.path.join(case_folder, f"processor{r}", time_name), field))
+        r += 1
+    if not systems:
+        raise FatalError(f"no processor*/{time_name} directories under {case_folder}")
+    if any(s.n_ranks != len(systems) or s.rank != i for i, s in enumerate(systems)):
+        raise FatalError("processor directories and side-cars disagree on the decomposition")
+    # the neighbour relation must be symmetric, block sizes included
+    for s in systems:
+        for itf in s.interfaces:
+            back = [j for j in systems[itf.nbr_rank].interfaces if j.nbr_rank == s.rank]
+            if sum(j.face_cells.size for j in back) != sum(
+                    j.face_cells.size for j in s.interfaces if j.nbr_rank == itf.nbr_rank):
+                raise FatalError(f"ranks {s.rank} and {itf.nbr_rank} disagree on their shared faces")
+    off = 0
+    for s in systems:
+        s.global_ids = off + np.arange(s.n, dtype=np.int64)
+        off += s.n
+    return systems

@@ -211,6 +211,9 @@ class GKOlduBaseSolver:
         self.ctx.export_mtx(0, os.path.join(folder, f + "_A_local.mtx"))
         self.ctx.export_mtx(1, os.path.join(folder, f + "_A_non_local.mtx"))
         self.ctx.export_mtx(2, os.path.join(folder, f + "_rhs_b_.mtx"))
+        # side-car with the communication pattern, so that a decomposed dump can be read back
+        # (mtxio.import_decomposed); the reference's files do not carry it
+        self.ctx.export_mtx(3, os.path.join(folder, f + "_partition.json"))
 
 
 class GKOCG(GKOlduBaseSolver):

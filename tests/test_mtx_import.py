@@ -91,3 +91,43 @@ def test_export_import_solve_again(oracle, tmp_path):
     perf2 = sol2.solve(psi2, t.source)
     assert abs(perf2.n_iterations - perf.n_iterations) <= 2
     assert np.linalg.norm(psi2 - psi) / np.linalg.norm(psi) <= 1e-8
+
+
+@pytest.mark.parametrize("procs", [(2, 1, 1), (2, 2, 1), (2, 2, 2)])
+def test_decomposed_dump_round_trip(oracle, tmp_path, procs):
+    """Per-processor dumps + the partition side-car -> the ranks' systems with their processor
+    interfaces: same assembled matrices, same communication pattern, same solve."""
+    from ogl_b200 import host
+    systems = cases.pressure_3d(8, procs)
+    asms = [oracle.assemble(s) for s in systems]
+    for s, a in zip(systems, asms):
+        folder = tmp_path / f"processor{s.rank}" / "0.005"
+        os.makedirs(folder)
+        mtxio.write_mtx_coordinate(folder / "p_A_local.mtx", a.n, a.n, a.rows, a.cols, a.vals)
+        mtxio.write_mtx_coordinate(folder / "p_A_non_local.mtx", a.n, a.nl_rows.size, a.nl_rows, a.nl_cols, a.nl_vals)
+        mtxio.write_mtx_array(folder / "p_rhs_b_.mtx", s.source)
+        tid, tsz, _ = host.create_communication_pattern(s)
+        mtxio.write_partition_sidecar(str(folder), "p", s.rank, len(systems), s.n, tid, tsz)
+    back = mtxio.import_decomposed(str(tmp_path), "0.005", "p")
+    assert len(back) == len(systems)
+    basms = [oracle.assemble(t) for t in back]
+    for a, b in zip(asms, basms):
+        assert np.array_equal(a.rows, b.rows) and np.array_equal(a.cols, b.cols)
+        assert np.allclose(a.vals, b.vals, rtol=1e-14, atol=0)
+        assert np.array_equal(a.target_ids, b.target_ids) and np.array_equal(a.target_sizes, b.target_sizes)
+        assert np.array_equal(a.send_idxs, b.send_idxs)
+        assert np.array_equal(a.nl_rows, b.nl_rows) and np.allclose(a.nl_vals, b.nl_vals, rtol=1e-14, atol=0)
+    o1 = oracle.solve(asms, "GKOCG", "BJ", tolerance=1e-9)
+    o2 = oracle.solve(basms, "GKOCG", "BJ", tolerance=1e-9)
+    assert abs(o1.n_iterations - o2.n_iterations) <= 1
+    for x1, x2 in zip(o1.x, o2.x):
+        assert np.allclose(x1, x2, rtol=0, atol=1e-9 * np.abs(x1).max())
+
+
+def test_decomposed_dump_without_sidecar_is_rejected(tmp_path):
+    folder = tmp_path / "processor0" / "1"
+    os.makedirs(folder)
+    mtxio.write_mtx_coordinate(folder / "p_A_local.mtx", 2, 2, [0, 1], [0, 1], [1, 1])
+    mtxio.write_mtx_coordinate(folder / "p_A_non_local.mtx", 2, 1, [0], [0], [3])
+    with pytest.raises(FatalError, match="side-car"):
+        mtxio.import_decomposed(str(tmp_path), "1", "p")
