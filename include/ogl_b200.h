@@ -146,7 +146,10 @@ int ogl_vector_fill(ogl_ctx *ctx, int which, double value);
  * (Preconditioner/Preconditioner.H:47-64, :91-105, :342-344): Jacobi on the
  * LOCAL block only.  max_block_size 1 = inverse diagonal; 2..32 = block
  * detection + Gauss-Jordan inverses (Ginkgo jacobi::find_blocks/generate). */
-enum { OGL_PRECOND_NONE = 0, OGL_PRECOND_BJ = 1 };
+/* ISAI: Ginkgo preconditioner::Isai<isai_type::spd> (Preconditioner/Preconditioner.H:225-242; needs an
+ * SPD local matrix, i.e. `scaling -1` for OpenFOAM's pressure equation, README.md:101), GISAI:
+ * Isai<isai_type::general> (:243-260); sparsityPower 1, rows up to 8 entries */
+enum { OGL_PRECOND_NONE = 0, OGL_PRECOND_BJ = 1, OGL_PRECOND_ISAI = 2, OGL_PRECOND_GISAI = 3 };
 int ogl_precond_setup(ogl_ctx *ctx, int kind, int32_t max_block_size,
                       int skip_sorting);
 /* parity hooks: block pointers and inverted blocks (row-major, concatenated) */

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libogl_b200.so")
 OGL_OK, OGL_ERR_INVALID, OGL_ERR_CUDA, OGL_ERR_NCCL, OGL_ERR_UNSUPPORTED = range(5)
 OGL_NCCL_ID_BYTES = 128
 OGL_VEC_B, OGL_VEC_X = 0, 1
-OGL_PRECOND_NONE, OGL_PRECOND_BJ = 0, 1
+OGL_PRECOND_NONE, OGL_PRECOND_BJ, OGL_PRECOND_ISAI, OGL_PRECOND_GISAI = 0, 1, 2, 3
 OGL_SOLVER_CG, OGL_SOLVER_BICGSTAB, OGL_SOLVER_GMRES = 0, 1, 2
 
 i32p = C.POINTER(C.c_int32)

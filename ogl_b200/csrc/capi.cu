@@ -138,7 +138,8 @@ static void destroy(Context *c)
                     c->d_history,    c->d_g_row_ptrs, c->d_g_cols,     c->d_g_map,
                     c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar,
                     c->ell.cols,     c->ell.vals,     c->ell.code,     c->ell.ptab,
-                    c->gell.cols,    c->gell.vals,    c->gell.code,    c->gell.ptab};
+                    c->gell.cols,    c->gell.vals,    c->gell.code,    c->gell.ptab,
+                    c->d_isai_w,     c->d_isai_wt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (double *w : c->work)

@@ -214,6 +214,9 @@ struct Context {
     int64_t *d_block_offs = nullptr;
     double *d_inv_blocks = nullptr;
     int64_t inv_blocks_len = 0;
+    // ISAI / GISAI: approximate-inverse values over the CSR pattern of the local matrix (w), and
+    // for the spd variant the transpose (wt); z = W r  or  z = W^T (W r)
+    double *d_isai_w = nullptr, *d_isai_wt = nullptr;
 
     // reduction scratch
     double *d_partials = nullptr;          // kMaxPartialBlocks * kMaxReduce
@@ -321,6 +324,8 @@ struct SpmvArgs {
     bool halo_stored = false;           // boundary values already stored by the previous kernel
     bool ghost_x = false;               // x has n + n_halo entries, the ghost part already filled:
                                         // ghosted CSR, no flag handshake (CG ghost-p mode)
+    const double *vals_override = nullptr;   // other values over the LOCAL CSR pattern (ISAI apply)
+    int ar_count = 0;                   // vals_override on several ranks: red[] slots all-reduced in the launch
 };
 int spmv_local(Context *ctx, const SpmvArgs &a);
 int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,

@@ -200,7 +200,7 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     const label n = ctx->n;
     const int64_t launches0 = ctx->launches;
     cudaStream_t st = ctx->stream;
-    const int pk = ctx->precond_kind == OGL_PRECOND_NONE ? 0 : (ctx->max_block_size == 1 ? 1 : 2);
+    const int pk = ctx->precond_kind == OGL_PRECOND_NONE ? 0 : ((ctx->precond_kind == OGL_PRECOND_BJ && ctx->max_block_size == 1) ? 1 : 2);
 
     // workspace
     const int64_t need = (int64_t)(m + 1) * (n > 0 ? n : 1);

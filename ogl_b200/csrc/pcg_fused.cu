@@ -467,7 +467,7 @@ bool pcg_fused_ok(const Context *ctx)
     // auto: measured faster than three kernels per iteration at 32 k rows (12.9 vs 13.9 us),
     // slower at 1 M (42 vs 38 us: a grid barrier over 740 CTAs costs more than a kernel boundary)
     if (ctx->fused_pcg == 2 && ctx->n > 262144) return false;
-    if (ctx->precond_kind != OGL_PRECOND_NONE && ctx->max_block_size != 1) return false;
+    if (ctx->precond_kind != OGL_PRECOND_NONE && (ctx->precond_kind != OGL_PRECOND_BJ || ctx->max_block_size != 1)) return false;
     if (ctx->spmv_variant != 0 && ctx->spmv_variant != 6) return false;
     if (spmv_variant_in_use(ctx) != 6) return false;
     if (ctx->n < 2) return false;

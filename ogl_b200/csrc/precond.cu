@@ -116,6 +116,101 @@ __global__ void k_row_block(label n_blocks, const label *__restrict__ block_ptrs
     for (label i = block_ptrs[b]; i < block_ptrs[b + 1]; ++i) row_block[i] = b;
 }
 
+// ---- ISAI / GISAI (sparsity power 1) ------------------------------------------------------------
+// One thread per row: gather the row's column set J (spd: columns <= row), the dense A(J,J) (or its
+// transpose), solve with Gaussian elimination + partial pivoting (k <= 8) and scatter the row of the
+// approximate inverse over the CSR pattern (spd: also the transposed position).  Same steps as
+// oracle/krylov.cpp:isai_generate.
+constexpr int kIsaiMax = 8;
+
+template <bool SPD>
+__global__ void __launch_bounds__(128) k_isai_generate(label n, const label *__restrict__ rp,
+                                                       const label *__restrict__ cols,
+                                                       const double *__restrict__ vals, double *__restrict__ W,
+                                                       double *__restrict__ WT, int *bad)
+{
+    const label i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    label J[kIsaiMax], pos[kIsaiMax];
+    int k = 0, p = -1;
+    if (rp[i + 1] - rp[i] > kIsaiMax) {
+        *bad = 1;
+        return;
+    }
+    for (label e = rp[i]; e < rp[i + 1]; ++e) {
+        const label c = cols[e];
+        if (SPD && c > i) continue;
+        if (c == i) p = k;
+        J[k] = c;
+        pos[k] = e;
+        ++k;
+    }
+    if (p < 0) {
+        *bad = 2;
+        return;
+    }
+    double M[kIsaiMax * kIsaiMax], y[kIsaiMax];
+    for (int a = 0; a < k * kIsaiMax; ++a) M[a] = 0.0;
+    for (int a = 0; a < k; ++a) {
+        y[a] = a == p ? 1.0 : 0.0;
+        const label j = J[a];
+        for (label e = rp[j]; e < rp[j + 1]; ++e) {
+            const label c = cols[e];
+            const double v = vals[e];
+            for (int b = 0; b < k; ++b)
+                if (c == J[b]) {
+                    if (SPD) M[a * kIsaiMax + b] = v;   // A(J,J)
+                    else M[b * kIsaiMax + a] = v;       // A(J,J)^T
+                }
+        }
+    }
+    for (int c = 0; c < k; ++c) {
+        int piv = c;
+        double best = fabs(M[c * kIsaiMax + c]);
+        for (int r = c + 1; r < k; ++r) {
+            const double v = fabs(M[r * kIsaiMax + c]);
+            if (v > best) {
+                best = v;
+                piv = r;
+            }
+        }
+        if (piv != c) {
+            for (int cc = 0; cc < k; ++cc) {
+                const double t = M[c * kIsaiMax + cc];
+                M[c * kIsaiMax + cc] = M[piv * kIsaiMax + cc];
+                M[piv * kIsaiMax + cc] = t;
+            }
+            const double t = y[c];
+            y[c] = y[piv];
+            y[piv] = t;
+        }
+        const double d = M[c * kIsaiMax + c];
+        for (int r = c + 1; r < k; ++r) {
+            const double f = M[r * kIsaiMax + c] / d;
+            for (int cc = c; cc < k; ++cc)
+                M[r * kIsaiMax + cc] = __dsub_rn(M[r * kIsaiMax + cc], __dmul_rn(f, M[c * kIsaiMax + cc]));
+            y[r] = __dsub_rn(y[r], __dmul_rn(f, y[c]));
+        }
+    }
+    for (int r = k - 1; r >= 0; --r) {
+        double s = y[r];
+        for (int cc = r + 1; cc < k; ++cc) s = __dsub_rn(s, __dmul_rn(M[r * kIsaiMax + cc], y[cc]));
+        y[r] = s / M[r * kIsaiMax + r];
+    }
+    if (SPD) {
+        const double scale = 1.0 / sqrt(y[p]);
+        for (int a = 0; a < k; ++a) {
+            const double w = __dmul_rn(y[a], scale);
+            W[pos[a]] = w;
+            const label j = J[a];
+            for (label e = rp[j]; e < rp[j + 1]; ++e)
+                if (cols[e] == i) WT[e] = w;
+        }
+    } else {
+        for (int a = 0; a < k; ++a) W[pos[a]] = y[a];
+    }
+}
+
 struct ApplyK {
     label n;
     const double *r;
@@ -164,9 +259,45 @@ int precond_setup(Context *ctx, int kind, label mbs)
 {
     if (!ctx->have_pattern || !ctx->have_values)
         return fail(ctx, OGL_ERR_INVALID, "ogl_precond_setup before the matrix is assembled");
-    if (kind != OGL_PRECOND_NONE && kind != OGL_PRECOND_BJ)
+    if (kind != OGL_PRECOND_NONE && kind != OGL_PRECOND_BJ && kind != OGL_PRECOND_ISAI && kind != OGL_PRECOND_GISAI)
         return fail(ctx, OGL_ERR_UNSUPPORTED,
-                    "preconditioner not supported; valid choices: none, BJ");
+                    "preconditioner not supported; valid choices: none, BJ, ISAI, GISAI");
+    if (kind == OGL_PRECOND_ISAI || kind == OGL_PRECOND_GISAI) {
+        if (ctx->max_row_len > kIsaiMax)
+            return fail(ctx, OGL_ERR_UNSUPPORTED, "ISAI: rows longer than 8 entries are not supported");
+        if (kind == OGL_PRECOND_ISAI && !ctx->symmetric)
+            return fail(ctx, OGL_ERR_INVALID, "ISAI (spd) needs a symmetric matrix; use GISAI");
+        const bool spd = kind == OGL_PRECOND_ISAI;
+        if (!ctx->d_isai_w) OGL_TRY(dev_alloc(ctx, &ctx->d_isai_w, (size_t)ctx->nnz));
+        if (spd && !ctx->d_isai_wt) OGL_TRY(dev_alloc(ctx, &ctx->d_isai_wt, (size_t)ctx->nnz));
+        int *d_bad = nullptr;
+        OGL_TRY(dev_alloc(ctx, &d_bad, 1));
+        cudaStream_t s2 = ctx->stream;
+        cudaMemsetAsync(d_bad, 0, sizeof(int), s2);
+        cudaMemsetAsync(ctx->d_isai_w, 0, sizeof(double) * ctx->nnz, s2);
+        if (spd) cudaMemsetAsync(ctx->d_isai_wt, 0, sizeof(double) * ctx->nnz, s2);
+        const int grid = (ctx->n + 127) / 128;
+        if (ctx->n > 0) {
+            if (spd)
+                k_isai_generate<true><<<grid, 128, 0, s2>>>(ctx->n, ctx->d_row_ptrs, ctx->d_cols, ctx->d_vals,
+                                                            ctx->d_isai_w, ctx->d_isai_wt, d_bad);
+            else
+                k_isai_generate<false><<<grid, 128, 0, s2>>>(ctx->n, ctx->d_row_ptrs, ctx->d_cols, ctx->d_vals,
+                                                             ctx->d_isai_w, ctx->d_isai_wt, d_bad);
+            ctx->launches++;
+        }
+        int bad = 0;
+        cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s2);
+        cudaError_t e = cudaStreamSynchronize(s2);
+        cudaFree(d_bad);
+        if (e != cudaSuccess) return fail(ctx, OGL_ERR_CUDA, std::string("ISAI generation: ") + cudaGetErrorString(e));
+        if (bad) return fail(ctx, OGL_ERR_INVALID, "ISAI: a row without diagonal entry");
+        ctx->precond_kind = kind;
+        ctx->max_block_size = 1;
+        ctx->have_precond = true;
+        ctx->precond_setups++;
+        return OGL_OK;
+    }
     if (mbs < 1) mbs = 1;
     if (mbs > 32) return fail(ctx, OGL_ERR_INVALID, "maxBlockSize must be in [1, 32]");
     ctx->precond_kind = kind;
@@ -271,6 +402,36 @@ int precond_apply(Context *ctx, const double *r, double *z, const double *dot_wi
             OGL_CUDA(ctx, cudaMemcpyAsync(z, r, sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice,
                                           ctx->stream));
         return OGL_OK;
+    }
+    if (ctx->precond_kind == OGL_PRECOND_ISAI || ctx->precond_kind == OGL_PRECOND_GISAI) {
+        // Schwarz: the LOCAL approximate inverse, as sparse mat-vecs over the pattern of A
+        const bool spd = ctx->precond_kind == OGL_PRECOND_ISAI;
+        const double *in = r;
+        if (spd) {
+            double *t;
+            OGL_TRY(get_work(ctx, 11, &t));
+            SpmvArgs s1;
+            s1.x = r;
+            s1.y = t;
+            s1.vals_override = ctx->d_isai_w;
+            s1.guard_done = guard_done;
+            OGL_TRY(spmv_local(ctx, s1));
+            in = t;
+        }
+        SpmvArgs s2;
+        s2.x = in;
+        s2.y = z;
+        s2.vals_override = spd ? ctx->d_isai_wt : ctx->d_isai_w;
+        s2.guard_done = guard_done;
+        if (dot_with) {
+            if (red_base != 0) return fail(ctx, OGL_ERR_INVALID, "ISAI apply reduces into red[0] only");
+            s2.dot_with = dot_with;
+            s2.nred = 1;
+            s2.epi = epi;
+            s2.inline_epi = inline_epi;
+            s2.ar_count = ar_count;
+        }
+        return spmv_local(ctx, s2);
     }
     ApplyK a;
     a.n = ctx->n;

@@ -533,6 +533,8 @@ int vec_scale(Context *ctx, double *v, double s)
 static int pk_of(const Context *ctx)
 {
     if (ctx->precond_kind == OGL_PRECOND_NONE) return 0;
+    if (ctx->precond_kind == OGL_PRECOND_ISAI || ctx->precond_kind == OGL_PRECOND_GISAI)
+        return 3;   // applied by its own launches (precond_apply)
     return ctx->max_block_size == 1 ? 1 : 2;
 }
 
@@ -574,7 +576,7 @@ int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, dou
         s.beta = 1.0;
         OGL_TRY(dist_spmv(ctx, s));
     }
-    const bool defer = (pk == 2 && mode == 0);   // block Jacobi finishes <r,z> afterwards
+    const bool defer = (pk >= 2 && mode == 0);   // block Jacobi / ISAI finish <r,z> afterwards
     VecK a = base_args(ctx, defer ? EPI_NONE : epi, false, defer ? 0 : 3);
     a.in0 = r;
     a.in1 = ctx->d_b;
@@ -607,7 +609,7 @@ int solve_prologue(Context *ctx, int mode, double *r, double *z, double *rr, dou
 // single-GPU kernel over the ghosted CSR.
 static bool ghost_p_mode(const Context *ctx)
 {
-    return ctx->ghost_p != 0 && ctx->n_ranks > 1 && fused_halo_ok(ctx) && pk_of(ctx) != 2;
+    return ctx->ghost_p != 0 && ctx->n_ranks > 1 && fused_halo_ok(ctx) && pk_of(ctx) < 2;
 }
 
 static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z, const double *p_old,
@@ -666,7 +668,7 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
     }
     }
     {
-        VecK a = base_args(ctx, EPI_CG_RHO_CHECK, true, 2);
+        VecK a = base_args(ctx, pk == 3 ? EPI_NONE : EPI_CG_RHO_CHECK, true, pk == 3 ? 0 : 2);
         a.in0 = p;
         a.in1 = q;
         a.in2 = ctx->d_inv_diag;
@@ -689,7 +691,12 @@ static int cg_iteration(Context *ctx, const double *r_old, double *r, double *z,
     } while (0)
         if (pk == 0) LAUNCH_XR(0);
         else if (pk == 1) LAUNCH_XR(1);
-        else {
+        else if (pk == 3) {
+            // ISAI: x, r', |r'|_1 here; z = M^-1 r', <r',z> and the criterion in the apply launches
+            LAUNCH_XR(2);
+            OGL_TRY(precond_apply(ctx, r, z, r, 0, true, EPI_CG_RHO_CHECK,
+                                  ctx->n_ranks == 1 || use_p2p(ctx), 2));
+        } else {
             a.bj_row_block = ctx->d_row_block;
             a.bj_block_ptrs = ctx->d_block_ptrs;
             a.bj_block_offs = ctx->d_block_offs;
@@ -721,7 +728,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         a.out1 = y;
         if (pk == 1) LAUNCH(k_bicg_step1<1>, a);
         else LAUNCH(k_bicg_step1<0>, a);
-        if (pk == 2) OGL_TRY(precond_apply(ctx, p, y, nullptr, 0, true, EPI_NONE, false, 0));
+        if (pk >= 2) OGL_TRY(precond_apply(ctx, p, y, nullptr, 0, true, EPI_NONE, false, 0));
     }
     const double *yy = pk == 0 ? p : y;
     {
@@ -744,7 +751,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         if (pk == 1) LAUNCH(k_bicg_step2<1>, a);
         else LAUNCH(k_bicg_step2<0>, a);
         OGL_TRY(finish_reduction(ctx, 2, EPI_BICG_CHECK_S, true));
-        if (pk == 2) OGL_TRY(precond_apply(ctx, s, z, nullptr, 0, true, EPI_NONE, false, 0));
+        if (pk >= 2) OGL_TRY(precond_apply(ctx, s, z, nullptr, 0, true, EPI_NONE, false, 0));
     }
     const double *zz = pk == 0 ? s : z;
     {
@@ -820,7 +827,7 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
     // CG (its x/r-update kernels carry the criterion): the chunk becomes the body
     // of a WHILE node; k_cg_xr clears the condition when the criterion fires, so a solve is one
     // graph launch with no early-exit launches behind the last iteration and no host polling
-    const bool loop = graph_ok && ctx->device_loop && solver == OGL_SOLVER_CG;
+    const bool loop = graph_ok && ctx->device_loop && solver == OGL_SOLVER_CG && pk_of(ctx) != 3;
     int chunk = (int)(loop ? ctx->loop_iters : ctx->chunk_iters);
     if (chunk < 1) chunk = 1;
     chunk += chunk & 1;

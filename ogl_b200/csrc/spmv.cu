@@ -954,6 +954,14 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
     int variant = pick_variant(ctx);
     if (variant == 7 && sa.fused_halo) variant = 6;   // the flag-handshake kernel exists for CSR only
+    if (sa.vals_override) {
+        // another operator over the same local pattern (ISAI): CSR kernels, local block only
+        if (sa.fused_halo || sa.ghost_x) return fail(ctx, OGL_ERR_INVALID, "vals_override is local-only");
+        k.vals = sa.vals_override;
+        if (variant == 7 || variant == 4) variant = 6;
+        if (variant == 6 && (size_t)ctx->max_block_nnz * sizeof(double) > (size_t)kStreamSmemMax) variant = 2;
+        k.ea = make_epi_args(ctx, sa.ar_count), k.ea.trace_tag = 20;
+    }
     // a rank without halo rows (n_halo == 0) runs the halo kernel on its local matrix
     const bool ghosted = (sa.fused_halo || sa.ghost_x) && ctx->have_ghosted;
     cudaStream_t st = ctx->stream;

@@ -25,6 +25,12 @@ from .host import FatalError, HostMatrixWrapper, ObjectRegistry
 from .parallel import Pstream
 
 
+# `preconditioner` keyword (Preconditioner.H:91-105 BJ, :225-242 ISAI, :243-260 GISAI); the other
+# families (ILU, IC, Multigrid) are rejected
+PRECOND_KINDS = {"none": L.OGL_PRECOND_NONE, "BJ": L.OGL_PRECOND_BJ, "ISAI": L.OGL_PRECOND_ISAI,
+                 "GISAI": L.OGL_PRECOND_GISAI}
+
+
 @dataclass
 class SolverPerformance:
     solver_name: str
@@ -147,9 +153,11 @@ class GKOlduBaseSolver:
             raise FatalError("keyword preconditioner is undefined")
         self.precond_controls = pre if isinstance(pre, dict) else {}
         self.precond_name = pre["preconditioner"] if isinstance(pre, dict) else str(pre)
-        if self.precond_name not in ("none", "BJ"):
+        if self.precond_name not in PRECOND_KINDS:
             raise FatalError(f"OGL does not support the preconditioner: {self.precond_name}\n"
-                             "Valid Choices: none, BJ")
+                             "Valid Choices: none, BJ, ISAI, GISAI")
+        if self.precond_name in ("ISAI", "GISAI") and int(self.precond_controls.get("sparsityPower", 1)) != 1:
+            raise FatalError("ISAI / GISAI: only sparsityPower 1 is implemented")
         self.host_matrix = HostMatrixWrapper(db, matrix, controls, field_name, self.ctx, self.pstream)
 
     # lduLduBase.H:189-308
@@ -172,7 +180,7 @@ class GKOlduBaseSolver:
         else:
             set_gko_solver_property(f, db, "preconditionerCaching",
                                     int(self.precond_controls.get("caching", 0)))
-            ctx.precond_setup(L.OGL_PRECOND_BJ if self.precond_name == "BJ" else L.OGL_PRECOND_NONE,
+            ctx.precond_setup(PRECOND_KINDS[self.precond_name],
                               int(self.precond_controls.get("maxBlockSize", 1)),
                               bool(self.precond_controls.get("skipSorting", True)))
             db["Cached_preconditioner_" + f] = True

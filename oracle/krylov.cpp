@@ -275,9 +275,102 @@ void invert_block(orc_label b, orc_scalar *m)
         for (orc_label k = 0; k < b; ++k) m[i * b + perm[k]] = tmp[i * b + k];
 }
 
+// ---- incomplete sparse approximate inverse (ISAI) ---------------------------------------------
+// [upstream Ginkgo core/preconditioner/isai.cpp + reference/preconditioner/isai_kernels.cpp;
+// Anzt, Huckle, Braeckle, Dongarra, "Incomplete Sparse Approximate Inverses for Parallel
+// Preconditioning", 2018], sparsity power 1, on the LOCAL block (Schwarz).
+//   general (GISAI): M with the pattern of A, row i: M(i,J) A(J,J) = I(i,J), J = columns of row i
+//                    -> one small dense solve A(J,J)^T m = e_pos(i) per row;  z = M r
+//   spd (ISAI):      W with the pattern of tril(A), row i: A(J,J) y = e_last, J = columns <= i,
+//                    w = y / sqrt(y_last)  (factorised sparse approximate inverse of the Cholesky
+//                    factor);  z = W^T (W r)
+// Dense solves: Gaussian elimination with partial pivoting.
+constexpr int kIsaiMax = 8;
+
+// solve M y = rhs in place (k x k row-major, k <= kIsaiMax); the solution overwrites rhs
+void isai_dense_solve(int k, orc_scalar *M, orc_scalar *rhs)
+{
+    for (int c = 0; c < k; ++c) {
+        int piv = c;
+        orc_scalar best = std::fabs(M[c * kIsaiMax + c]);
+        for (int r = c + 1; r < k; ++r) {
+            const orc_scalar v = std::fabs(M[r * kIsaiMax + c]);
+            if (v > best) {
+                best = v;
+                piv = r;
+            }
+        }
+        if (piv != c) {
+            for (int cc = 0; cc < k; ++cc) std::swap(M[c * kIsaiMax + cc], M[piv * kIsaiMax + cc]);
+            std::swap(rhs[c], rhs[piv]);
+        }
+        const orc_scalar d = M[c * kIsaiMax + c];
+        for (int r = c + 1; r < k; ++r) {
+            const orc_scalar f = M[r * kIsaiMax + c] / d;
+            for (int cc = c; cc < k; ++cc) M[r * kIsaiMax + cc] -= f * M[c * kIsaiMax + cc];
+            rhs[r] -= f * rhs[c];
+        }
+    }
+    for (int r = k - 1; r >= 0; --r) {
+        orc_scalar s = rhs[r];
+        for (int cc = r + 1; cc < k; ++cc) s -= M[r * kIsaiMax + cc] * rhs[cc];
+        rhs[r] = s / M[r * kIsaiMax + r];
+    }
+}
+
+// W (and, spd, its transpose WT) as value arrays over the CSR pattern of A; false: unsupported row
+bool isai_generate(orc_label n, const orc_label *rp, const orc_label *cols, const orc_scalar *vals, bool spd,
+                   orc_scalar *W, orc_scalar *WT)
+{
+    for (orc_label e = 0; e < rp[n]; ++e) W[e] = 0.0;
+    if (spd)
+        for (orc_label e = 0; e < rp[n]; ++e) WT[e] = 0.0;
+    for (orc_label i = 0; i < n; ++i) {
+        orc_label J[kIsaiMax], pos[kIsaiMax];
+        int k = 0, p = -1;
+        if (rp[i + 1] - rp[i] > kIsaiMax) return false;
+        for (orc_label e = rp[i]; e < rp[i + 1]; ++e) {
+            const orc_label c = cols[e];
+            if (c >= n || (spd && c > i)) continue;
+            if (c == i) p = k;
+            J[k] = c;
+            pos[k] = e;
+            ++k;
+        }
+        if (p < 0) return false;
+        orc_scalar M[kIsaiMax * kIsaiMax], y[kIsaiMax];
+        for (int a = 0; a < k * kIsaiMax; ++a) M[a] = 0.0;
+        for (int a = 0; a < k; ++a) {
+            y[a] = a == p ? 1.0 : 0.0;
+            const orc_label j = J[a];
+            for (orc_label e = rp[j]; e < rp[j + 1]; ++e)
+                for (int b = 0; b < k; ++b)
+                    if (cols[e] == J[b]) {
+                        if (spd) M[a * kIsaiMax + b] = vals[e];   // A(J,J)
+                        else M[b * kIsaiMax + a] = vals[e];       // A(J,J)^T
+                    }
+        }
+        isai_dense_solve(k, M, y);
+        if (spd) {
+            const orc_scalar scale = 1.0 / std::sqrt(y[p]);
+            for (int a = 0; a < k; ++a) {
+                const orc_scalar w = y[a] * scale;
+                W[pos[a]] = w;
+                const orc_label j = J[a];
+                for (orc_label e = rp[j]; e < rp[j + 1]; ++e)
+                    if (cols[e] == i) WT[e] = w;
+            }
+        } else {
+            for (int a = 0; a < k; ++a) W[pos[a]] = y[a];
+        }
+    }
+    return true;
+}
+
 struct Jacobi {
     int kind = ORC_PRECOND_NONE;
     orc_label mbs = 1;
+    dvec isai_w, isai_wt;                        // ISAI / GISAI values over the pattern of A
     dvec inv_diag;                               // mbs == 1
     std::vector<std::vector<orc_label>> bptr;    // mbs > 1
     std::vector<std::vector<orc_label>> boff;
@@ -289,6 +382,19 @@ Jacobi make_jacobi(const Sys &s, int kind, orc_label mbs)
     Jacobi J;
     J.kind = kind;
     J.mbs = mbs < 1 ? 1 : mbs;
+    if (kind == ORC_PRECOND_ISAI || kind == ORC_PRECOND_GISAI) {
+        J.isai_w.resize(s.R);
+        J.isai_wt.resize(s.R);
+        for (int r = 0; r < s.R; ++r) {
+            const auto &k = s.rk[r];
+            J.isai_w[r].assign(static_cast<size_t>(k.nnz), 0.0);
+            J.isai_wt[r].assign(static_cast<size_t>(k.nnz), 0.0);
+            if (!isai_generate(k.n, s.row_ptrs[r].data(), k.cols, k.vals, kind == ORC_PRECOND_ISAI,
+                               J.isai_w[r].data(), J.isai_wt[r].data()))
+                J.kind = -1;   // reported by orc_solve
+        }
+        return J;
+    }
     if (kind != ORC_PRECOND_BJ) return J;
     if (J.mbs == 1) {
         // jacobi::invert_diagonal on the LOCAL block (Schwarz, Preconditioner.H:53-62)
@@ -326,7 +432,25 @@ void precond_apply(const Sys &s, const Jacobi &J, const dvec &r, dvec &z)
 {
     for (int q = 0; q < s.R; ++q) {
         const orc_label n = s.rk[q].n;
-        if (J.kind != ORC_PRECOND_BJ) {
+        if (J.kind == ORC_PRECOND_ISAI || J.kind == ORC_PRECOND_GISAI) {
+            // sequential CSR row sums over the LOCAL pattern with the ISAI values
+            const orc_label *rp = s.row_ptrs[q].data(), *cols = s.rk[q].cols;
+            auto apply = [&](const orc_scalar *v, const orc_scalar *in, orc_scalar *out) {
+#pragma omp parallel for schedule(static) num_threads(s.threads) if (s.threads > 1)
+                for (orc_label i = 0; i < n; ++i) {
+                    orc_scalar acc = 0.0;
+                    for (orc_label e = rp[i]; e < rp[i + 1]; ++e) acc += v[e] * in[cols[e]];
+                    out[i] = acc;
+                }
+            };
+            if (J.kind == ORC_PRECOND_GISAI) {
+                apply(J.isai_w[q].data(), r[q].data(), z[q].data());
+            } else {
+                vec t(static_cast<size_t>(n));
+                apply(J.isai_w[q].data(), r[q].data(), t.data());
+                apply(J.isai_wt[q].data(), t.data(), z[q].data());
+            }
+        } else if (J.kind != ORC_PRECOND_BJ) {
             std::memcpy(z[q].data(), r[q].data(), sizeof(orc_scalar) * n);
         } else if (J.mbs == 1) {
             // jacobi::scalar_apply: x = b * inv_diag
@@ -658,6 +782,7 @@ int orc_solve(int n_ranks, const orc_rank_system *ranks,
         b[r].assign(ranks[r].b, ranks[r].b + ranks[r].n);
     }
     Jacobi J = make_jacobi(s, params->precond, params->max_block_size);
+    if (J.kind < 0) return 5;  // ISAI: a row longer than the dense solver handles / no diagonal
     Criterion crit{s, *params, x, b, 0, 1.0, 0.0, 0.0, history, history_cap, 0};
     const auto t0 = std::chrono::steady_clock::now();
     switch (params->solver) {
@@ -693,6 +818,12 @@ orc_label orc_bj_find_blocks(orc_label n, const orc_label *row_ptrs,
 {
     return find_blocks(n, row_ptrs, cols, max_block_size < 1 ? 1 : max_block_size,
                        block_ptrs);
+}
+
+int orc_isai_generate(orc_label n, const orc_label *row_ptrs, const orc_label *cols, const orc_scalar *vals,
+                      int spd, orc_scalar *w, orc_scalar *wt)
+{
+    return isai_generate(n, row_ptrs, cols, vals, spd != 0, w, wt) ? 0 : 1;
 }
 
 void orc_bj_invert_blocks(orc_label n, const orc_label *row_ptrs,

@@ -134,7 +134,9 @@ typedef struct orc_rank_system {
 } orc_rank_system;
 
 enum { ORC_CG = 0, ORC_BICGSTAB = 1, ORC_GMRES = 2 };
-enum { ORC_PRECOND_NONE = 0, ORC_PRECOND_BJ = 1 };
+/* ISAI: Ginkgo preconditioner::Isai<isai_type::spd> (Preconditioner.H:225-242), GISAI: <general>
+ * (:243-260); sparsityPower 1 */
+enum { ORC_PRECOND_NONE = 0, ORC_PRECOND_BJ = 1, ORC_PRECOND_ISAI = 2, ORC_PRECOND_GISAI = 3 };
 
 typedef struct orc_solve_params {
     int solver;               /* ORC_CG ...                                  */
@@ -177,6 +179,9 @@ int orc_solve(int n_ranks, const orc_rank_system *ranks,
 orc_label orc_bj_find_blocks(orc_label n, const orc_label *row_ptrs,
                              const orc_label *cols, orc_label max_block_size,
                              orc_label *block_ptrs /* [n+1] */);
+/* ISAI values over the CSR pattern (w; spd: also wt = transpose), 0 on success */
+int orc_isai_generate(orc_label n, const orc_label *row_ptrs, const orc_label *cols,
+                      const orc_scalar *vals, int spd, orc_scalar *w, orc_scalar *wt);
 void orc_bj_invert_blocks(orc_label n, const orc_label *row_ptrs,
                           const orc_label *cols, const orc_scalar *vals,
                           orc_label n_blocks, const orc_label *block_ptrs,

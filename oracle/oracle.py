@@ -75,7 +75,7 @@ class SolveResult(C.Structure):
 
 
 SOLVERS = {"GKOCG": 0, "GKOBiCGStab": 1, "GKOGMRES": 2}
-PRECONDS = {"none": 0, "BJ": 1}
+PRECONDS = {"none": 0, "BJ": 1, "ISAI": 2, "GISAI": 3}
 
 
 def lib():
@@ -343,6 +343,18 @@ def dist_spmv(asms: Sequence[Assembled], xs: Sequence[np.ndarray]) -> List[np.nd
     yp = (f64p * len(asms))(*[_fp(y) for y in ys])
     lib().orc_dist_spmv(C.c_int(len(asms)), arr, xp, yp)
     return ys
+
+
+def isai_values(n, row_ptrs, cols, vals, spd: bool):
+    """ISAI / GISAI values over the CSR pattern: (W, WT) (WT only meaningful for spd)."""
+    rp, c, v = _i32(row_ptrs), _i32(cols), _f64(vals)
+    w, wt = np.zeros(v.size), np.zeros(v.size)
+    fn = lib().orc_isai_generate
+    fn.restype = C.c_int
+    rc = fn(C.c_int32(n), _ip(rp), _ip(c), _fp(v), C.c_int(1 if spd else 0), _fp(w), _fp(wt))
+    if rc != 0:
+        raise RuntimeError("ISAI: row too long for the dense solver or missing diagonal")
+    return w, wt
 
 
 def bj_blocks(n, row_ptrs, cols, vals, max_block_size):

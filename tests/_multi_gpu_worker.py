@@ -18,6 +18,9 @@ CASES = {
     "pressure_cg": (lambda p: cases.pressure_3d(16, p), "GKOCG", "BJ", 1, 1e-9),
     "pressure_cg_bj4": (lambda p: cases.pressure_3d(12, p), "GKOCG", "BJ", 4, 1e-9),
     "momentum_bicgstab": (lambda p: cases.momentum_3d(14, p), "GKOBiCGStab", "BJ", 1, 1e-10),
+    # Schwarz-wrapped approximate inverses of the local blocks (no communication in the apply)
+    "pressure_cg_isai": (lambda p: cases.pressure_3d(12, p, sign=-1.0), "GKOCG", "ISAI", 1, 1e-9),
+    "momentum_bicgstab_gisai": (lambda p: cases.momentum_3d(10, p), "GKOBiCGStab", "GISAI", 1, 1e-10),
     "channel_gmres": (lambda p: cases.channel((16, 8, 8), p), "GKOGMRES", "BJ", 1, 1e-8),
     # all-Neumann + one reference cell: nearly singular, so solve tighter than the L2 bar
     # 2-D case: fold the z split into x ([2,2,2] -> [4,2,1] like test/integration.yaml:53-55)

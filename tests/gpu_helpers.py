@@ -24,7 +24,8 @@ def upload_system(ctx: Context, s, scaling=1.0, partition=True):
 
 
 def gpu_solve(ctx: Context, solver, precond, mbs=1, **kw):
-    ctx.precond_setup(L.OGL_PRECOND_BJ if precond == "BJ" else L.OGL_PRECOND_NONE, mbs)
+    ctx.precond_setup({"none": L.OGL_PRECOND_NONE, "BJ": L.OGL_PRECOND_BJ, "ISAI": L.OGL_PRECOND_ISAI,
+                       "GISAI": L.OGL_PRECOND_GISAI}[precond], mbs)
     max_iter = kw.pop("max_iter", 1000)
     if solver == "GKOBiCGStab":
         max_iter *= 2   # StoppingCriterion.H:188, done by the host layer

@@ -504,3 +504,40 @@ def test_adaptive_criterion_is_live_over_a_time_loop(oracle):
     sol = lduMatrix_solver_New("p", s, dict(controls, export=True), db)
     sol.solve(np.zeros(s.n), s.source)
     assert (sol.last_min_iter, sol.last_frequency) == (0, 1)
+
+
+# ---- ISAI / GISAI (the first of the "other preconditioners") ----
+
+def test_cg_isai_spd(ctx, oracle):
+    """preconditioner ISAI (Isai<spd>: z = W^T W r with W ~ inv(chol(A))) on the SPD twin of the
+    pressure matrix (README.md:101: OpenFOAM's pressure matrix needs `scaling -1` for IC / ISAI)."""
+    s = cases.pressure_3d(24, sign=-1.0)[0]
+    r, o, x = check_against_oracle(ctx, oracle, s, "GKOCG", "ISAI", tolerance=1e-9)
+    rj, _ = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-9)     # same system, x already solved: re-upload
+    upload_system(ctx, s, partition=False)
+    rj, _ = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-9)
+    assert r.n_iterations < 0.7 * rj.n_iterations               # it is a better preconditioner
+
+
+@pytest.mark.parametrize("solver", ["GKOBiCGStab", "GKOGMRES"])
+def test_gisai_momentum(ctx, oracle, solver):
+    s = cases.momentum_3d(20)[0]
+    kw = {"krylov_dim": 30} if solver == "GKOGMRES" else {}
+    check_against_oracle(ctx, oracle, s, solver, "GISAI", tolerance=1e-9, **kw)
+
+
+def test_cg_gisai_on_symmetric_matrix_and_plugin_keyword(oracle):
+    s = cases.pressure_3d(16, sign=-1.0)[0]
+    o = oracle.solve([oracle.assemble(s)], "GKOCG", "GISAI", tolerance=1e-9)
+    controls = {"solver": "GKOCG", "executor": "cuda", "tolerance": 1e-9, "relTol": 0.0, "adaptMinIter": False,
+                "preconditioner": {"preconditioner": "GISAI", "sparsityPower": 1}}
+    sol = lduMatrix_solver_New("p", s, controls, ObjectRegistry())
+    psi = s.psi.copy()
+    perf = sol.solve(psi, s.source)
+    assert perf.solver_name == "GISAIcudaGKOCG"
+    assert abs(perf.n_iterations - o.n_iterations) <= ITER_TOL and rel_l2(psi, o.x[0]) <= L2_TOL
+    with pytest.raises(FatalError):
+        lduMatrix_solver_New("p", s, dict(controls, preconditioner={"preconditioner": "ISAI", "sparsityPower": 2}),
+                             ObjectRegistry())
+    with pytest.raises(FatalError):
+        lduMatrix_solver_New("p", s, dict(controls, preconditioner="Multigrid"), ObjectRegistry())

@@ -179,3 +179,33 @@ def test_two_restatements_agree_bicgstab(oracle, n):
     assert len(o.history) == k
     assert np.allclose(o.history, f.history, rtol=1e-5, atol=0)
     assert np.linalg.norm(o.x[0] - f.x[0]) <= 1e-10 * np.linalg.norm(f.x[0])
+
+
+def test_isai_properties_and_effect(oracle):
+    """ISAI restatement: GISAI satisfies (W A)|pattern = I, the spd variant the FSAI conditions
+    (W A has no strictly-lower pattern entries, diag(W A W^T) = 1); both cut the iteration count."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    for s, spd, solver in ((cases.pressure_3d(9, sign=-1.0)[0], True, "GKOCG"),
+                           (cases.momentum_3d(8)[0], False, "GKOBiCGStab")):
+        a = oracle.assemble(s)
+        rp = np.zeros(s.n + 1, np.int32)
+        np.cumsum(np.bincount(a.rows, minlength=s.n), out=rp[1:])
+        A = sp.csr_matrix((a.vals, a.cols, rp), shape=(s.n, s.n))
+        w, wt = oracle.isai_values(s.n, rp, a.cols, a.vals, spd)
+        W = sp.csr_matrix((w, a.cols, rp), shape=(s.n, s.n))
+        if spd:
+            WT = sp.csr_matrix((wt, a.cols, rp), shape=(s.n, s.n))
+            assert abs(WT - W.T).max() < 1e-15
+            strict = sp.tril(A, k=-1).tocsr()
+            strict.data[:] = 1
+            assert abs((W @ A).multiply(strict)).max() < 1e-12 * abs(A).max()
+            assert abs((W @ A @ W.T).diagonal() - 1).max() < 1e-12
+        else:
+            pat = A.copy()
+            pat.data[:] = 1
+            assert abs((W @ A).multiply(pat) - sp.identity(s.n)).max() < 1e-12
+        o_bj = oracle.solve([a], solver, "BJ", tolerance=1e-9)
+        o_is = oracle.solve([a], solver, "ISAI" if spd else "GISAI", tolerance=1e-9)
+        assert o_is.n_iterations < 0.8 * o_bj.n_iterations
+        assert np.linalg.norm(o_is.x[0] - o_bj.x[0]) <= 1e-6 * np.linalg.norm(o_bj.x[0])
