@@ -352,6 +352,8 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->fuse_p = value != 0;
     } else if (k == "ell_auto") {
         ctx->ell_auto = value != 0;
+    } else if (k == "gmres_persist") {
+        ctx->gmres_persist = value != 0;
     } else if (k == "ell_chunk") {
         if (value < 1 || value > 4096) return fail(ctx, OGL_ERR_INVALID, "ell_chunk in [1,4096]");
         ctx->ell_chunk = value;
@@ -425,6 +427,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "ell_auto") *value = ctx->ell_auto;
     else if (k == "ell_coded") *value = ctx->ell_coded;
     else if (k == "ell_chunk") *value = ctx->ell_chunk;
+    else if (k == "gmres_persist") *value = ctx->gmres_persist;
     else if (k == "ell_minb") *value = ctx->ell_minb;
     else if (k == "ell_minb_cgp") *value = ctx->ell_minb_cgp;
     else if (k == "ell_coded_active") *value = (ctx->ell.coded ? 1 : 0) | (ctx->gell.coded ? 2 : 0);

@@ -243,6 +243,7 @@ struct Context {
     bool graph_is_loop = false;
     unsigned long long cond_handle = 0;   // cudaGraphConditionalHandle while the loop body is captured
 
+    int64_t gmres_persist = 1;   // GMRES: MGS sweep of an Arnoldi step as one persistent cooperative kernel (<= ~0.6 M rows)
     int64_t launches = 0;
     int64_t precond_setups = 0;   // ogl_precond_setup calls (tests of the `caching` keyword)
 

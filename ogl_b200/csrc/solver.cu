@@ -397,20 +397,54 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_xr_bj_uniform(cons
     if (a.cond && last == 2 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
 }
 
+// The BiCGStab update kernels move 128 bits per thread and trip (two rows; an odd last row is
+// handled by one thread): as scalar 8-byte loops they ran at 3.7-4.9 TB/s (ncu, round 2), far from
+// what k_cg_xr reaches on the same kind of stream.
+#define GRID_STRIDE2(i, n2) \
+    _Pragma("unroll 2") for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n2); \
+                             i += (int64_t)gridDim.x * blockDim.x)
+
 // bicgstab::step_1 + y = M^-1 p     in0 = r, in1 = v, in2 = inv_diag ; out0 = p, out1 = y
+template <int PK>
+__device__ __forceinline__ void bicg_step1_elem(bool p_is_r, double t, double omega, double r, double v,
+                                                double d, double &p, double &y)
+{
+    if (p_is_r) p = r;
+    else p = __dadd_rn(r, __dmul_rn(t, __dsub_rn(p, __dmul_rn(omega, v))));
+    if (PK == 1) y = __dmul_rn(p, d);
+}
+
 template <int PK>
 __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step1(const VecK a)
 {
     if (a.guard_done && a.state->done) return;
     const bool p_is_r = a.state->flag_p_is_z != 0;
     const double t = a.state->coef_p, omega = a.state->omega;
-    GRID_STRIDE(i, a.n) {
-        const double r = a.in0[i];
-        double p = r;
-        if (!p_is_r)
-            p = __dadd_rn(r, __dmul_rn(t, __dsub_rn(a.out0[i], __dmul_rn(omega, a.in1[i]))));
+    const double2 *__restrict__ r2 = reinterpret_cast<const double2 *>(a.in0);
+    const double2 *__restrict__ v2 = reinterpret_cast<const double2 *>(a.in1);
+    const double2 *__restrict__ d2 = reinterpret_cast<const double2 *>(a.in2);
+    double2 *__restrict__ p2 = reinterpret_cast<double2 *>(a.out0);
+    double2 *__restrict__ y2 = reinterpret_cast<double2 *>(a.out1);
+    const int64_t n2 = a.n >> 1;
+    GRID_STRIDE2(i, n2) {
+        const double2 r = r2[i];
+        double2 p = make_double2(0.0, 0.0), v = p, d = p, y = p;
+        if (!p_is_r) {
+            p = p2[i];
+            v = v2[i];
+        }
+        if (PK == 1) d = d2[i];
+        bicg_step1_elem<PK>(p_is_r, t, omega, r.x, v.x, d.x, p.x, y.x);
+        bicg_step1_elem<PK>(p_is_r, t, omega, r.y, v.y, d.y, p.y, y.y);
+        p2[i] = p;
+        if (PK == 1) y2[i] = y;
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = a.n - 1;
+        double p = a.out0[i], y = 0.0;
+        bicg_step1_elem<PK>(p_is_r, t, omega, a.in0[i], a.in1[i], PK == 1 ? a.in2[i] : 0.0, p, y);
         a.out0[i] = p;
-        if (PK == 1) a.out1[i] = __dmul_rn(p, a.in2[i]);
+        if (PK == 1) a.out1[i] = y;
     }
 }
 
@@ -422,7 +456,28 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step2(const VecK
     const bool upd = a.state->beta != 0.0;
     const double alpha = a.state->alpha;
     double red[2] = {0.0, 0.0};
-    GRID_STRIDE(i, a.n) {
+    const double2 *__restrict__ r2 = reinterpret_cast<const double2 *>(a.in0);
+    const double2 *__restrict__ v2 = reinterpret_cast<const double2 *>(a.in1);
+    const double2 *__restrict__ d2 = reinterpret_cast<const double2 *>(a.in2);
+    double2 *__restrict__ s2 = reinterpret_cast<double2 *>(a.out0);
+    double2 *__restrict__ z2 = reinterpret_cast<double2 *>(a.out1);
+    const int64_t n2 = a.n >> 1;
+    GRID_STRIDE2(i, n2) {
+        double2 s = r2[i];
+        if (upd) {
+            const double2 v = v2[i];
+            s.x = __dsub_rn(s.x, __dmul_rn(alpha, v.x));
+            s.y = __dsub_rn(s.y, __dmul_rn(alpha, v.y));
+        }
+        s2[i] = s;
+        red[1] = __dadd_rn(__dadd_rn(red[1], fabs(s.x)), fabs(s.y));
+        if (PK == 1) {
+            const double2 d = d2[i];
+            z2[i] = make_double2(__dmul_rn(s.x, d.x), __dmul_rn(s.y, d.y));
+        }
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = a.n - 1;
         double s = a.in0[i];
         if (upd) s = __dsub_rn(s, __dmul_rn(alpha, a.in1[i]));
         a.out0[i] = s;
@@ -439,9 +494,29 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step3(const VecK
     if (a.guard_done && a.state->done) return;
     const double alpha = a.state->alpha, omega = a.state->omega;
     double red[2] = {0.0, 0.0};
-    GRID_STRIDE(i, a.n) {
-        a.out0[i] = __dadd_rn(a.out0[i], __dadd_rn(__dmul_rn(alpha, a.in2[i]),
-                                                   __dmul_rn(omega, a.in3[i])));
+    const double2 *__restrict__ s2 = reinterpret_cast<const double2 *>(a.in0);
+    const double2 *__restrict__ t2 = reinterpret_cast<const double2 *>(a.in1);
+    const double2 *__restrict__ y2 = reinterpret_cast<const double2 *>(a.in2);
+    const double2 *__restrict__ z2 = reinterpret_cast<const double2 *>(a.in3);
+    const double2 *__restrict__ rr2 = reinterpret_cast<const double2 *>(a.in4);
+    double2 *__restrict__ x2 = reinterpret_cast<double2 *>(a.out0);
+    double2 *__restrict__ r2 = reinterpret_cast<double2 *>(a.out1);
+    const int64_t n2 = a.n >> 1;
+    GRID_STRIDE2(i, n2) {
+        const double2 s = s2[i], t = t2[i], y = y2[i], z = z2[i], rr = rr2[i];
+        double2 x = x2[i], r;
+        x.x = __dadd_rn(x.x, __dadd_rn(__dmul_rn(alpha, y.x), __dmul_rn(omega, z.x)));
+        x.y = __dadd_rn(x.y, __dadd_rn(__dmul_rn(alpha, y.y), __dmul_rn(omega, z.y)));
+        r.x = __dsub_rn(s.x, __dmul_rn(omega, t.x));
+        r.y = __dsub_rn(s.y, __dmul_rn(omega, t.y));
+        x2[i] = x;
+        r2[i] = r;
+        red[0] = __dadd_rn(__dadd_rn(red[0], __dmul_rn(rr.x, r.x)), __dmul_rn(rr.y, r.y));
+        red[1] = __dadd_rn(__dadd_rn(red[1], fabs(r.x)), fabs(r.y));
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = a.n - 1;
+        a.out0[i] = __dadd_rn(a.out0[i], __dadd_rn(__dmul_rn(alpha, a.in2[i]), __dmul_rn(omega, a.in3[i])));
         const double r = __dsub_rn(a.in0[i], __dmul_rn(omega, a.in1[i]));
         a.out1[i] = r;
         red[0] = __dadd_rn(red[0], __dmul_rn(a.in4[i], r));
