@@ -445,6 +445,8 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "fused_halo") *value = ctx->fused_halo;
     else if (k == "p2p_active") *value = use_p2p(ctx) ? 1 : 0;
     else if (k == "max_row_len") *value = ctx->max_row_len;
+    else if (k.rfind("row_len_hist_", 0) == 0 && k.size() == 14 && k[13] >= '0' && k[13] <= '7')
+        *value = (int64_t)ctx->row_len_hist[k[13] - '0'];
     else if (k == "max_block_nnz") *value = ctx->max_block_nnz;
     else if (k == "launches") *value = ctx->launches;
     else if (k == "precond_setups") *value = ctx->precond_setups;

@@ -118,6 +118,7 @@ struct Context {
     int64_t nnz = 0;
     label *d_rows = nullptr, *d_cols = nullptr, *d_map = nullptr, *d_row_ptrs = nullptr;
     label max_row_len = 0;
+    unsigned long long row_len_hist[16] = {};   // spmv.cu:k_row_len_hist: rows / entries per power-of-two length bucket
     // ELL copies (spmv_variant 7 / `matrixFormat Ell`, ell.cu): `ell` of the local matrix, `gell` of
     // the ghosted one (several ranks, CG ghost-p mode)
     struct EllMatrix {

@@ -37,6 +37,7 @@ namespace {
 
 constexpr label kPadDelta = INT_MIN;   // table entry of a padding slot
 constexpr int kPatSlots = 1024;        // open-addressing hash table of tuples
+constexpr int kPatProbes = 64;         // longest probe sequence (at most 127 tuples are ever coded)
 constexpr int kPatMaxW = 8;            // widest row the tuple table holds
 constexpr int kEscape = 127;           // low 7 bits of a code: row not in the table
 constexpr int kGhostBit = 128;         // the row has ghost entries (columns >= n) behind its local ones
@@ -105,8 +106,11 @@ __global__ void k_pat_insert(label n, const label *__restrict__ ell_cols, int wi
     unsigned long long h;
     bool ghost;
     row_tuple(n, row, ell_cols, width, pitch, d, h, ghost);
+    // an unstructured pattern has (almost) as many tuples as rows: once the table has overflowed
+    // nobody probes any more -- those rows escape, and the format is dropped if they are many
+    if (*reinterpret_cast<volatile int *>(overflow)) return;
     unsigned int slot = (unsigned int)(h % kPatSlots);
-    for (int probe = 0; probe < kPatSlots; ++probe, slot = (slot + 1) % kPatSlots) {
+    for (int probe = 0; probe < kPatProbes; ++probe, slot = (slot + 1) % kPatSlots) {
         unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&keys[slot]);
         if (cur == 0) cur = atomicCAS(&keys[slot], 0ull, h);
         if (cur == 0) {   // mine
@@ -154,7 +158,7 @@ __global__ void k_pat_assign(label n, const label *__restrict__ ell_cols, int wi
         bool ghost;
         row_tuple(n, row, ell_cols, width, pitch, d, h, ghost);
         unsigned int slot = (unsigned int)(h % kPatSlots);
-        for (int probe = 0; probe < kPatSlots; ++probe, slot = (slot + 1) % kPatSlots) {
+        for (int probe = 0; probe < kPatProbes; ++probe, slot = (slot + 1) % kPatSlots) {
             const unsigned long long cur = keys[slot];
             if (cur == 0) break;
             if (cur == h) {

@@ -484,14 +484,20 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step2(const VecK
         red[1] = __dadd_rn(red[1], fabs(s));
         if (PK == 1) a.out1[i] = __dmul_rn(s, a.in2[i]);
     }
-    grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+    const int last = grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+    if (a.cond && last == 2 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);   // stopped at the s check
 }
 
 // bicgstab::step_3 + <rr,r> + |r|_1
 //   in0 = s, in1 = t, in2 = y, in3 = z, in4 = rr ; out0 = x, out1 = r
 __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step3(const VecK a)
 {
-    if (a.guard_done && a.state->done) return;
+    if (a.guard_done && a.state->done) {
+        // the last kernel of a loop body: the criterion fired earlier (before the loop, at the s
+        // check of this iteration, or in the first half of the body)
+        if (a.cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
+        return;
+    }
     const double alpha = a.state->alpha, omega = a.state->omega;
     double red[2] = {0.0, 0.0};
     const double2 *__restrict__ s2 = reinterpret_cast<const double2 *>(a.in0);
@@ -522,7 +528,8 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_bicg_step3(const VecK
         red[0] = __dadd_rn(red[0], __dmul_rn(a.in4[i], r));
         red[1] = __dadd_rn(red[1], fabs(r));
     }
-    grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+    const int last = grid_reduce<2>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+    if (a.cond && last == 2 && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0);
 }
 
 // bicgstab::finalize  x += alpha y when the solver stopped at the first check
@@ -823,6 +830,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         a.in2 = ctx->d_inv_diag;
         a.out0 = s;
         a.out1 = z;
+        a.cond = ctx->cond_handle;
         if (pk == 1) LAUNCH(k_bicg_step2<1>, a);
         else LAUNCH(k_bicg_step2<0>, a);
         OGL_TRY(finish_reduction(ctx, 2, EPI_BICG_CHECK_S, true));
@@ -848,6 +856,7 @@ static int bicg_iteration(Context *ctx, double *r, double *rr, double *p, double
         a.in4 = rr;
         a.out0 = ctx->d_x;
         a.out1 = r;
+        a.cond = ctx->cond_handle;
         LAUNCH(k_bicg_step3, a);
     }
     return finish_reduction(ctx, 2, EPI_BICG_RHO_CHECK, true);
@@ -902,8 +911,13 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
     // CG (its x/r-update kernels carry the criterion): the chunk becomes the body
     // of a WHILE node; k_cg_xr clears the condition when the criterion fires, so a solve is one
     // graph launch with no early-exit launches behind the last iteration and no host polling
-    const bool loop = graph_ok && ctx->device_loop && solver == OGL_SOLVER_CG && pk_of(ctx) != 3;
+    // (preconditioners with their own apply launches keep the host-polled chunks: their criterion
+    // call sits in the apply kernels)
+    const bool loop = graph_ok && ctx->device_loop &&
+                      ((solver == OGL_SOLVER_CG && pk_of(ctx) != 3) || (solver == OGL_SOLVER_BICGSTAB && pk_of(ctx) < 2));
     int chunk = (int)(loop ? ctx->loop_iters : ctx->chunk_iters);
+    // a BiCGStab iteration is two SpMVs + three updates: short bodies waste fewer early-exit launches
+    if (loop && solver == OGL_SOLVER_BICGSTAB && chunk > 4) chunk = 4;
     if (chunk < 1) chunk = 1;
     chunk += chunk & 1;
     const int64_t sig0 = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^ (ctx->use_pdl << 60) ^
@@ -1093,7 +1107,8 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     res->resnorm_us = hs.crit_ns > 0 ? (double)hs.crit_ns * 1e-3 : 0.0;
     if (ctx->loop_body_iters > 0) {
         // device-side loop: whole bodies ran, up to and including the one the criterion fired in
-        const int64_t calls = hs.iter > 0 ? hs.iter - 1 : 0;   // minus the prologue's criterion call
+        int64_t calls = hs.iter > 0 ? hs.iter - 1 : 0;   // minus the prologue's criterion call
+        if (p->solver == OGL_SOLVER_BICGSTAB) calls = (calls + 1) / 2;   // two criterion calls per iteration
         int64_t bodies = (calls + ctx->loop_body_iters - 1) / ctx->loop_body_iters;
         if (bodies < 1) bodies = 1;
         ctx->launches += bodies * ctx->graph_kernels;

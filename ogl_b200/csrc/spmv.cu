@@ -787,6 +787,25 @@ __global__ void k_block_nnz_max(label n, const label *__restrict__ row_ptrs, int
     }
 }
 
+// row-length histogram in powers of two: bucket b counts the rows (hist[b]) and their entries
+// (hist[8 + b]) with length in (2^(b-1), 2^b] for b = 1..6, b = 0: empty rows and length 1,
+// b = 7: longer than 64
+__global__ void k_row_len_hist(label n, const label *__restrict__ row_ptrs, unsigned long long *hist)
+{
+    __shared__ unsigned long long sh[16];
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0ull;
+    __syncthreads();
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int len = row_ptrs[r + 1] - row_ptrs[r];
+        int b = 0;
+        while (b < 7 && (1 << b) < len) ++b;
+        atomicAdd(&sh[b], 1ull);
+        atomicAdd(&sh[8 + b], (unsigned long long)len);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
 template <typename K, typename A>
 void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const A &args)
 {
@@ -828,11 +847,20 @@ int spmv_setup(Context *ctx)
         k_block_nnz_max<<<(int)((nwt + 255) / 256), 256, 0, ctx->stream>>>(
             ctx->n, ctx->d_row_ptrs, kWarpRows, d_max + 1);
     }
+    unsigned long long *d_hist = nullptr;
+    if (cudaMalloc(&d_hist, 16 * sizeof(unsigned long long)) == cudaSuccess) {
+        cudaMemsetAsync(d_hist, 0, 16 * sizeof(unsigned long long), ctx->stream);
+        if (ctx->n > 0)
+            k_row_len_hist<<<kNumSM * 4, 256, 0, ctx->stream>>>(ctx->n, ctx->d_row_ptrs, d_hist);
+        cudaMemcpyAsync(ctx->row_len_hist, d_hist, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                        ctx->stream);
+    }
     int mx2[2] = {0, 0};
     int &mx = mx2[0];
     cudaMemcpyAsync(mx2, d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_max);
+    cudaFree(d_hist);
     if (e != cudaSuccess)
         return fail(ctx, OGL_ERR_CUDA, std::string("spmv_setup: ") + cudaGetErrorString(e));
     ctx->max_block_nnz = mx;
@@ -914,8 +942,15 @@ static int pick_variant(const Context *ctx)
     if (ctx->ell_auto && ctx->n > 262144 && ctx->max_row_len <= 16 &&
         (double)ctx->max_row_len * ctx->n <= 1.25 * (double)ctx->nnz)
         return 7;
-    // row-length histogram summary: short regular rows -> stream; long rows -> warp per row
-    if (smem <= (size_t)kStreamSmemMax && mean_len <= 48.0) return 6;   // pipelined stream
+    // row-length histogram (spmv_setup): the share of the entries that sit in long rows decides.
+    // Short rows (finite-volume meshes: 5..30 entries) -> the pipelined stream kernel, whose tiles
+    // park every product in shared memory; a matrix whose entries are mostly in rows longer than 32
+    // -> one warp per row; in between, or when a tile would not fit in shared memory -> thread per row.
+    const double nnz = ctx->nnz > 0 ? (double)ctx->nnz : 1.0;
+    const double share_long = (double)(ctx->row_len_hist[8 + 6] + ctx->row_len_hist[8 + 7]) / nnz;   // rows > 32
+    const double share_huge = (double)ctx->row_len_hist[8 + 7] / nnz;                                 // rows > 64
+    if (share_long > 0.5) return 3;
+    if (smem <= (size_t)kStreamSmemMax && share_huge < 0.05 && mean_len <= 48.0) return 6;   // pipelined stream
     return mean_len >= 16.0 ? 3 : 2;
 }
 

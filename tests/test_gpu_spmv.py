@@ -155,3 +155,21 @@ def test_ell_codes_fall_back_on_an_unstructured_pattern(ctx, oracle):
         assert (ctx.get_option("ell_coded_active") & 1) == (1 if coded == 2 else 0)
     ctx.set_option("spmv_variant", 0)
     ctx.set_option("ell_coded", 1)
+
+
+def test_row_length_histogram_drives_the_kernel_choice(ctx):
+    """spmv_setup builds a power-of-two row-length histogram on the device; the automatic kernel
+    choice reads it: stencil rows -> ELL / pipelined stream, an arrow matrix -> warp per row."""
+    s = cases.pressure_3d(12)[0]
+    upload_system(ctx, s, partition=False)
+    ctx.set_option("spmv_variant", 0)
+    hist = [ctx.get_option(f"row_len_hist_{b}") for b in range(8)]
+    assert sum(hist) == s.n and hist[2] == 8 and hist[3] == s.n - 8   # corners: 4 entries, the rest 5..7
+    assert ctx.get_option("spmv_variant_in_use") in (6, 7)
+    n = 4000                                            # arrow: row 0 holds a third of the entries
+    lower = np.zeros(n - 1, np.int32)
+    upper = np.arange(1, n, dtype=np.int32)
+    ctx.pattern_from_ldu(n, lower, upper, True)
+    hist = [ctx.get_option(f"row_len_hist_{b}") for b in range(8)]
+    assert hist[7] == 1 and hist[1] == n - 1
+    assert ctx.get_option("spmv_variant_in_use") in (2, 3)
