@@ -541,3 +541,40 @@ def test_cg_gisai_on_symmetric_matrix_and_plugin_keyword(oracle):
                              ObjectRegistry())
     with pytest.raises(FatalError):
         lduMatrix_solver_New("p", s, dict(controls, preconditioner="Multigrid"), ObjectRegistry())
+
+
+@pytest.mark.parametrize("n,extra,force_ell", [(30000, 60000, False), (300000, 400000, False), (30000, 4000, True)])
+def test_unstructured_mesh_automatic_kernel_choice(ctx, oracle, n, extra, force_ell):
+    """A random (unstructured) lduAddressing: thousands of distinct row patterns, row lengths from 2 up.
+    Whatever the automatic selection picks (CSR stream here; ELL with mostly-escaped codes when forced),
+    SpMV is bit-exact and the solve matches the oracle."""
+    from conftest import random_ldu_mesh
+    rng = np.random.default_rng(n)
+    lower, upper = random_ldu_mesh(rng, n, extra)
+    up = -rng.uniform(0.5, 1.0, lower.size)
+    diag = np.full(n, 0.05)
+    np.add.at(diag, lower, -up)
+    np.add.at(diag, upper, -up)
+    x_star = rng.uniform(-1, 1, n)
+    b = diag * x_star
+    np.add.at(b, lower, up * x_star[upper])
+    np.add.at(b, upper, up * x_star[lower])
+    s = cases.LduSystem(n=n, lower_addr=lower, upper_addr=upper, diag=diag, upper=up, lower=None, interfaces=[],
+                        source=b, psi=np.zeros(n), global_ids=np.arange(n, dtype=np.int64), x_star=x_star)
+    upload_system(ctx, s, partition=False)
+    max_len = ctx.get_option("max_row_len")
+    if force_ell:
+        if max_len > 64:
+            pytest.skip("random mesh drew a row too long for ELL")
+        ctx.set_option("spmv_variant", 7)
+        ctx.set_option("ell_coded", 2)
+    a = oracle.assemble(s)
+    xv = rng.normal(size=n)
+    assert np.array_equal(ctx.spmv(xv), oracle.dist_spmv([a], [xv])[0])
+    variant = ctx.get_option("spmv_variant_in_use")
+    assert variant == (7 if force_ell else 6), (variant, max_len)
+    r, x = gpu_solve(ctx, "GKOCG", "BJ", tolerance=1e-9)
+    o = oracle.solve([a], "GKOCG", "BJ", tolerance=1e-9)
+    assert abs(r.n_iterations - o.n_iterations) <= ITER_TOL and rel_l2(x, o.x[0]) <= L2_TOL
+    ctx.set_option("spmv_variant", 0)
+    ctx.set_option("ell_coded", 1)
