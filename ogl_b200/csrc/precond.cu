@@ -119,8 +119,7 @@ __global__ void k_row_block(label n_blocks, const label *__restrict__ block_ptrs
 // ---- ISAI / GISAI (sparsity power 1) ------------------------------------------------------------
 // One thread per row: gather the row's column set J (spd: columns <= row), the dense A(J,J) (or its
 // transpose), solve with Gaussian elimination + partial pivoting (k <= 8) and scatter the row of the
-// approximate inverse over the CSR pattern (spd: also the transposed position).  Same steps as
-// oracle/krylov.cpp:isai_generate.
+// approximate inverse over the CSR pattern (spd: also the transposed position).
 constexpr int kIsaiMax = 8;
 
 template <bool SPD>
