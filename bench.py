@@ -521,6 +521,7 @@ def run_gpu(args):
     spmv_ms, spmv_plain_ms, spmv_b2b_ms = (float(v) for v in t.tolist())
     variant = ctx.get_option("spmv_variant_in_use")
     coded = ctx.get_option("ell_coded_active")
+    ctx_ell_tma = coded and (ctx.get_option("ell_tma") == 1 or (ctx.get_option("ell_tma") == 2 and n > (1 << 21)))
 
     if ps.rank != 0:
         ctx.close()
@@ -541,7 +542,10 @@ def run_gpu(args):
         pitch = (n + 31) // 32 * 32
         # ELL copy: 8 B per slot (+ 4 B columns unless pattern-coded: then 1 B code per row), x, y
         actual = width * pitch * 8 + (n if coded else 4 * width * pitch) + 16 * n + 8 * n_halo
-        kernel = ("k_spmv_ell<false,1,7,coded,4>: FP64 ELL SpMV + fused <p,q>, %s%s" % (
+        tma = ctx_ell_tma
+        kernel = ("%s: FP64 ELL SpMV + fused <p,q>, %s%s" % (
+            "k_spmv_ell_tma<1,7> (values and row codes staged by TMA bulk copies through an mbarrier ring)" if tma
+            else "k_spmv_ell<false,1,7,coded,4>",
             "1-byte row-pattern codes instead of column indices" if coded else "4-byte columns",
             "; ghosted matrix, all-reduce of <p,q> inside the launch" if n_gpus > 1 else ""))
     else:

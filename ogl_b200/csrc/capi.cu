@@ -357,6 +357,9 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     } else if (k == "ell_chunk") {
         if (value < 1 || value > 4096) return fail(ctx, OGL_ERR_INVALID, "ell_chunk in [1,4096]");
         ctx->ell_chunk = value;
+    } else if (k == "ell_tma") {
+        if (value < 0 || value > 2) return fail(ctx, OGL_ERR_INVALID, "ell_tma in {0,1,2}");
+        ctx->ell_tma = value;
     } else if (k == "ell_minb") {
         if (value < 3 || value > 4) return fail(ctx, OGL_ERR_INVALID, "ell_minb in {3,4}");
         ctx->ell_minb = value;
@@ -428,6 +431,7 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "ell_coded") *value = ctx->ell_coded;
     else if (k == "ell_chunk") *value = ctx->ell_chunk;
     else if (k == "gmres_persist") *value = ctx->gmres_persist;
+    else if (k == "ell_tma") *value = ctx->ell_tma;
     else if (k == "ell_minb") *value = ctx->ell_minb;
     else if (k == "ell_minb_cgp") *value = ctx->ell_minb_cgp;
     else if (k == "ell_coded_active") *value = (ctx->ell.coded ? 1 : 0) | (ctx->gell.coded ? 2 : 0);

@@ -139,6 +139,8 @@ struct Context {
     label max_row_len_g = 0;     // longest row of the ghosted CSR
     int64_t ell_coded = 1;       // 0 off, 1 auto (when <= 25% of the rows escape), 2 whenever a table exists
     int64_t ell_chunk = 1;       // consecutive 256-row tiles per CTA visit (ell.cu:TileWalk)
+    int64_t ell_tma = 2;         // coded ELL SpMV fed by TMA bulk copies through a shared-memory ring (ell.cu:k_spmv_ell_tma):
+                                 // 0 off, 1 on, 2 auto = above 2 M rows (measured: 88 vs 93 us at 8 M rows, 30.5 vs 30.2 at 1 M)
     int64_t ell_minb = 4;        // resident CTAs per SM the coded ELL SpMV is compiled for (3: 85 registers, 4: 64)
     int64_t ell_minb_cgp = 3;    // ... and the fused CG kernel (2, 3 or 4)
     int64_t fuse_p = 0;          // CG: p-update fused into the ELL SpMV (ell.cu:k_spmv_ell_cgp); measured slower than

@@ -379,6 +379,115 @@ k_spmv_ell(const SpmvK a, const EllK m, const int chunk)
                                            a.inline_epi != 0, a.ea);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed variant of the pattern-coded kernel (option ell_tma).  The value stream never touches the
+// load/store units: one producer lane per CTA walks the CTA's tiles ahead of the consumers and
+// issues W + 1 bulk copies per 256-row tile (cp.async.bulk = the TMA engine: W slot slices of
+// 2 KB and the 256 row codes) into a ring of shared-memory stages guarded by mbarriers; the 8
+// consumer warps wait on a stage, read code and values from shared memory (conflict-free: thread t
+// owns element t of every slice), gather x, add the row left to right, and hand the stage back.
+// Bytes in flight per SM are set by the ring (3 CTAs x stages x 14.6 KB), not by how many loads a
+// warp can have outstanding.  Same arithmetic and order as k_spmv_ell: bit-identical results.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmaEllThreads = kEllThreads + 32;   // 8 consumer warps + 1 producer warp
+constexpr int kTmaEllCtasPerSM = 4;      // <= 56 registers; the ring depth decides how many fit (option ell_minb caps the grid)
+constexpr int kTmaEllMaxStages = 4;
+
+template <int NRED, int W>
+__global__ void __launch_bounds__(kTmaEllThreads, kTmaEllCtasPerSM)
+k_spmv_ell_tma(const SpmvK a, const EllK m, const int stages)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kStageBytes = W * kEllThreads * 8 + kEllThreads;   // W value slices + the codes
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * kStageBytes);
+    uint64_t *empty = full + kTmaEllMaxStages;
+    label *tab = reinterpret_cast<label *>(empty + kTmaEllMaxStages);
+    if (a.guard_done && a.state->done) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int st = 0; st < stages; ++st) {
+            tma::mbar_init(&full[st], 1);
+            tma::mbar_init(&empty[st], kEllThreads / 32);
+        }
+        tma::fence_barrier_init();
+        tma::fence_proxy_async();
+    }
+    for (int i = tid; i < m.n_patterns * W; i += kTmaEllThreads) tab[i] = m.ptab[i];
+    __syncthreads();
+    double red[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) red[j] = 0.0;
+    const int64_t n_tiles = ((int64_t)a.n + kEllThreads - 1) / kEllThreads;
+    if (warp == kEllThreads / 32) {
+        // ===== producer: one lane feeds the ring =====
+        if (lane == 0) {
+            const uint64_t pol = tma::policy_evict_first();
+            int it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const int st = it % stages;
+                const uint32_t round = (uint32_t)(it / stages);
+                if (round > 0) tma::mbar_wait(&empty[st], (round - 1) & 1);
+                const int64_t r0 = t * kEllThreads;
+                const int64_t left = m.pitch - r0;                       // pitch is a multiple of 32 rows
+                const uint32_t rows = (uint32_t)(left < kEllThreads ? left : kEllThreads);
+                unsigned char *base = smem_raw + (size_t)st * kStageBytes;
+                tma::mbar_expect_tx(&full[st], rows * 8u * W + rows);
+#pragma unroll
+                for (int u = 0; u < W; ++u)
+                    tma::bulk_load(base + (size_t)u * kEllThreads * 8, m.vals + u * m.pitch + r0, rows * 8u, &full[st], pol);
+                tma::bulk_load(base + (size_t)W * kEllThreads * 8, m.code + r0, rows, &full[st], pol);
+            }
+        }
+        __syncwarp();   // reconverge the producer warp before the block-wide reduction
+    } else {
+        // ===== consumers: thread t owns row t of every tile =====
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int st = it % stages;
+            const uint32_t round = (uint32_t)(it / stages);
+            const int64_t row = t * kEllThreads + tid;
+            // the fused dot's operand does not depend on the stage: in flight during the wait
+            double dw = 0.0;
+            if (NRED >= 1 && row < a.n) asm volatile("ld.global.f64 %0, [%1];" : "=d"(dw) : "l"(a.dot_with + row));
+            tma::mbar_wait(&full[st], round & 1);
+            const unsigned char *base = smem_raw + (size_t)st * kStageBytes;
+            const double *vs = reinterpret_cast<const double *>(base);
+            if (row < a.n) {
+                const unsigned int cd = base[(size_t)W * kEllThreads * 8 + tid];
+                label c[W];
+                double v[W], xv[W];
+                const unsigned int live = coded_columns<W>(c, (label)row, cd, tab);
+#pragma unroll
+                for (int u = 0; u < W; ++u) xv[u] = __ldg(&a.x[c[u]]);
+#pragma unroll
+                for (int u = 0; u < W; ++u) v[u] = vs[u * kEllThreads + tid];
+                double sum = 0.0;
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const double s2 = __dadd_rn(sum, __dmul_rn(v[u], xv[u]));
+                    sum = (live >> u) & 1u ? s2 : sum;
+                }
+                if (coded_tail(cd)) {
+#pragma unroll 1
+                    for (int u = __popc(live); u < W; ++u) {
+                        const label ce = m.cols[u * m.pitch + row];
+                        if (ce < 0) break;
+                        sum = __dadd_rn(sum, __dmul_rn(vs[u * kEllThreads + tid], a.x[ce]));
+                    }
+                }
+                a.y[row] = sum;
+                if (NRED >= 1) red[0] = __dadd_rn(red[0], __dmul_rn(dw, sum));
+                if (NRED >= 2) red[1] = __dadd_rn(red[1], __dmul_rn(sum, sum));
+            }
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty[st]);
+        }
+    }
+    if (NRED > 0)
+        grid_reduce<(NRED > 0 ? NRED : 1)>(red, a.partials, a.ticket, a.state, 0, a.epi,
+                                           a.inline_epi != 0, a.ea);
+}
+
 // CG step_1 fused into the SpMV:  x = z (or r), y_in = p (previous), y = q, p_new = the other p
 // buffer.  GHOST (several ranks, peer-memory path): columns >= n are ghost operands -- z from the
 // stamped words in slot 2 of this rank's window (pushed by the neighbours' k_cg_xr, stamped with
@@ -651,6 +760,32 @@ int spmv_ell(Context *ctx, SpmvK &k, const SpmvArgs &sa, bool ghosted)
     const bool pc = e.coded && (e.width == 7 || e.width == 5);
     const int chunk = (int)ctx->ell_chunk;
     const int minb = (int)ctx->ell_minb;
+    const bool tma_on = ctx->ell_tma == 1 || (ctx->ell_tma == 2 && ctx->n > (1 << 21));
+    if (tma_on && pc && e.width == 7 && !sa.advanced) {
+        // TMA-fed ring (k_spmv_ell_tma)
+        int stages = (int)ctx->tma_stages;
+        if (stages < 2) stages = 2;
+        if (stages > kTmaEllMaxStages) stages = kTmaEllMaxStages;
+        const size_t smem = (size_t)stages * (7 * kEllThreads * 8 + kEllThreads) +
+                            2 * kTmaEllMaxStages * sizeof(uint64_t) + 128 * 7 * sizeof(label);
+        int per_sm = (int)((227 * 1024) / (smem + 1024));      // resident CTAs for this ring depth
+        if (per_sm > kTmaEllCtasPerSM) per_sm = kTmaEllCtasPerSM;
+        if (per_sm > minb) per_sm = minb;
+        if (per_sm < 1) per_sm = 1;
+        const int grid_t = ell_grid(ctx, per_sm);
+#define TMA_GO(R)                                                                                              \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(k_spmv_ell_tma<R, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        k_spmv_ell_tma<R, 7><<<grid_t, kTmaEllThreads, smem, st>>>(k, m, stages);                              \
+    } while (0)
+        if (nred == 0) TMA_GO(0);
+        else if (nred == 1) TMA_GO(1);
+        else TMA_GO(2);
+#undef TMA_GO
+        ctx->launches++;
+        OGL_CUDA(ctx, cudaGetLastError());
+        return OGL_OK;
+    }
     const int grid = ell_grid(ctx, pc ? minb : kEllCtasPerSM);
 #define ELL_GO(A, R, W, P, B) k_spmv_ell<A, R, W, P, B><<<grid, kEllThreads, 0, st>>>(k, m, chunk)
 #define ELL_WP(A, R, W)                                       \

@@ -142,7 +142,7 @@ class GKOlduBaseSolver:
         # one set_option per key with its final value: an unchanged value keeps the cached chunk graph
         opts = {"spmv_variant": 7 if fmt == "Ell" else 0}
         for opt in ("spmv_variant", "chunk_iters", "use_graph", "comm_mode", "fused_halo", "ghost_p",
-                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb", "ell_auto", "fuse_p", "ell_coded"):
+                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb", "ell_auto", "fuse_p", "ell_coded", "ell_tma", "gmres_persist"):
             if opt in controls:
                 opts[opt] = int(controls[opt])
         for opt, val in opts.items():

@@ -65,7 +65,8 @@ def main():
                     "fused_halo": 0 if mode == 2 else 1, "ghost_p": 0 if mode == 3 else 1,
                     "preconditioner": {"preconditioner": precond, "maxBlockSize": mbs}}
         if mode >= 4:
-            controls.update({"spmv_variant": 7, "ell_coded": 2, "fused_pcg": 0, "fuse_p": 1 if mode == 4 else 0})
+            controls.update({"spmv_variant": 7, "ell_coded": 2, "fused_pcg": 0, "fuse_p": 1 if mode == 4 else 0,
+                             "ell_tma": 1 if mode == 5 else 0})   # 5: the TMA-fed kernel over the ghosted matrix
         name = f"{name}@{mode}"
         sol = lduMatrix_solver_New(name, s, controls, db, ps)
         psi = s.psi.copy()

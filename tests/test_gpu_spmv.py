@@ -173,3 +173,22 @@ def test_row_length_histogram_drives_the_kernel_choice(ctx):
     hist = [ctx.get_option(f"row_len_hist_{b}") for b in range(8)]
     assert hist[7] == 1 and hist[1] == n - 1
     assert ctx.get_option("spmv_variant_in_use") in (2, 3)
+
+
+def test_tma_fed_coded_ell_is_bit_identical(ctx, oracle):
+    """ell_tma: the value stream goes through cp.async.bulk + mbarrier stages instead of per-thread
+    loads; same row sums."""
+    s = cases.pressure_3d(33)[0]            # 35937 rows: a ragged last tile
+    x = np.random.default_rng(8).normal(size=s.n)
+    upload_system(ctx, s, partition=False)
+    ctx.set_option("spmv_variant", 7)
+    ref = oracle.dist_spmv([oracle.assemble(s)], [x])[0]
+    for stages in (2, 3, 4):
+        ctx.set_option("ell_tma", 1)
+        ctx.set_option("tma_stages", stages)
+        assert np.array_equal(ctx.spmv(x), ref)
+    ms = ctx.spmv_bench(5, fused_dot=True)
+    assert ms > 0
+    ctx.set_option("ell_tma", 2)
+    ctx.set_option("tma_stages", 3)
+    ctx.set_option("spmv_variant", 0)
