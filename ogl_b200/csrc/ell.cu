@@ -488,6 +488,121 @@ k_spmv_ell_tma(const SpmvK a, const EllK m, const int stages)
                                            a.inline_epi != 0, a.ea);
 }
 
+// The fused CG kernel (k_spmv_ell_cgp below) on the same TMA ring: values and codes arrive through
+// shared memory, the load/store units only see the two gathers (z, p) and the three row-local
+// accesses.  x = z (or r), y_in = p (previous), y = q, p_new = the other p buffer.
+template <int W, bool GHOST>
+__global__ void __launch_bounds__(kTmaEllThreads, kTmaEllCtasPerSM)
+k_spmv_ell_cgp_tma(const SpmvK a, const EllK m, double *__restrict__ p_new, const int stages)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kStageBytes = W * kEllThreads * 8 + kEllThreads;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * kStageBytes);
+    uint64_t *empty = full + kTmaEllMaxStages;
+    label *tab = reinterpret_cast<label *>(empty + kTmaEllMaxStages);
+    if (a.guard_done && a.state->done) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int st = 0; st < stages; ++st) {
+            tma::mbar_init(&full[st], 1);
+            tma::mbar_init(&empty[st], kEllThreads / 32);
+        }
+        tma::fence_barrier_init();
+        tma::fence_proxy_async();
+    }
+    for (int i = tid; i < m.n_patterns * W; i += kTmaEllThreads) tab[i] = m.ptab[i];
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) trace_event(a.ea, 0);
+    const bool p_is_z = a.state->flag_p_is_z != 0;
+    const double t = a.state->coef_p;
+    const unsigned long long *zg = nullptr;
+    unsigned long long stamp = 0;
+    long long t0 = 0;
+    if (GHOST) {
+        const CommDev *cm = a.ea.comm;
+        zg = reinterpret_cast<const unsigned long long *>(cm->my_recv + 2 * (size_t)cm->my_recv_stride);
+        stamp = stamp_of(ld_ar_seq(cm));
+        t0 = clock64();
+    }
+    double red[1] = {0.0};
+    const int64_t n_tiles = ((int64_t)a.n + kEllThreads - 1) / kEllThreads;
+    if (warp == kEllThreads / 32) {
+        if (lane == 0) {
+            const uint64_t pol = tma::policy_evict_first();
+            int it = 0;
+            for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++it) {
+                const int st = it % stages;
+                const uint32_t round = (uint32_t)(it / stages);
+                if (round > 0) tma::mbar_wait(&empty[st], (round - 1) & 1);
+                const int64_t r0 = tl * kEllThreads;
+                const int64_t left = m.pitch - r0;
+                const uint32_t rows = (uint32_t)(left < kEllThreads ? left : kEllThreads);
+                unsigned char *base = smem_raw + (size_t)st * kStageBytes;
+                tma::mbar_expect_tx(&full[st], rows * 8u * W + rows);
+#pragma unroll
+                for (int u = 0; u < W; ++u)
+                    tma::bulk_load(base + (size_t)u * kEllThreads * 8, m.vals + u * m.pitch + r0, rows * 8u, &full[st], pol);
+                tma::bulk_load(base + (size_t)W * kEllThreads * 8, m.code + r0, rows, &full[st], pol);
+            }
+        }
+        __syncwarp();
+    } else {
+        int it = 0;
+        for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++it) {
+            const int st = it % stages;
+            const uint32_t round = (uint32_t)(it / stages);
+            const int64_t row = tl * kEllThreads + tid;
+            tma::mbar_wait(&full[st], round & 1);
+            const unsigned char *base = smem_raw + (size_t)st * kStageBytes;
+            const double *vs = reinterpret_cast<const double *>(base);
+            if (row < a.n) {
+                const unsigned int cd = base[(size_t)W * kEllThreads * 8 + tid];
+                label c[W];
+                double zc[W], pc[W];
+                const unsigned int live = coded_columns<W>(c, (label)row, cd, tab);
+#pragma unroll
+                for (int u = 0; u < W; ++u) zc[u] = __ldg(&a.x[c[u]]);
+                if (!p_is_z) {
+#pragma unroll
+                    for (int u = 0; u < W; ++u) pc[u] = a.y_in[c[u]];
+                }
+                double sum = 0.0, mine = 0.0;
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const double pv = p_is_z ? zc[u] : __dadd_rn(zc[u], __dmul_rn(t, pc[u]));
+                    const bool on = (live >> u) & 1u;
+                    if (on && c[u] == (label)row) mine = pv;
+                    const double s2 = __dadd_rn(sum, __dmul_rn(vs[u * kEllThreads + tid], pv));
+                    sum = on ? s2 : sum;
+                }
+                if (coded_tail(cd)) {
+#pragma unroll 1
+                    for (int u = __popc(live); u < W; ++u) {
+                        const label ce = m.cols[u * m.pitch + row];
+                        if (ce < 0) break;
+                        double zv = 0.0;
+                        if (GHOST && ce >= a.n) {
+                            if (!pull_stamped(zg + 2 * (size_t)(ce - a.n), stamp, t0, zv)) a.state->comm_error = 1;
+                        } else {
+                            zv = a.x[ce];
+                        }
+                        const double pv = p_is_z ? zv : __dadd_rn(zv, __dmul_rn(t, a.y_in[ce]));
+                        if (ce == (label)row) mine = pv;
+                        if (GHOST && ce >= a.n) p_new[ce] = pv;
+                        sum = __dadd_rn(sum, __dmul_rn(vs[u * kEllThreads + tid], pv));
+                    }
+                }
+                p_new[row] = mine;
+                a.y[row] = sum;
+                red[0] = __dadd_rn(red[0], __dmul_rn(mine, sum));
+            }
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty[st]);
+        }
+    }
+    grid_reduce<1>(red, a.partials, a.ticket, a.state, 0, a.epi, a.inline_epi != 0, a.ea);
+}
+
 // CG step_1 fused into the SpMV:  x = z (or r), y_in = p (previous), y = q, p_new = the other p
 // buffer.  GHOST (several ranks, peer-memory path): columns >= n are ghost operands -- z from the
 // stamped words in slot 2 of this rank's window (pushed by the neighbours' k_cg_xr, stamped with
@@ -852,6 +967,29 @@ int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_n
     k.ea = make_epi_args(ctx, ghost ? 1 : 0);
     k.ea.trace_tag = 20;
     const EllK m = ell_args(e);
+    const bool tma_on = ctx->ell_tma == 1 || (ctx->ell_tma == 2 && ctx->n > (1 << 21));
+    if (tma_on && e.coded && e.width == 7) {
+        int stages = (int)ctx->tma_stages;
+        if (stages < 2) stages = 2;
+        if (stages > kTmaEllMaxStages) stages = kTmaEllMaxStages;
+        const size_t smem = (size_t)stages * (7 * kEllThreads * 8 + kEllThreads) +
+                            2 * kTmaEllMaxStages * sizeof(uint64_t) + 128 * 7 * sizeof(label);
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > kTmaEllCtasPerSM) per_sm = kTmaEllCtasPerSM;
+        if (per_sm > (int)ctx->ell_minb) per_sm = (int)ctx->ell_minb;
+        if (per_sm < 1) per_sm = 1;
+        const int grid_t = ell_grid(ctx, per_sm);
+        if (ghost) {
+            cudaFuncSetAttribute(k_spmv_ell_cgp_tma<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_spmv_ell_cgp_tma<7, true><<<grid_t, kTmaEllThreads, smem, ctx->stream>>>(k, m, p_new, stages);
+        } else {
+            cudaFuncSetAttribute(k_spmv_ell_cgp_tma<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_spmv_ell_cgp_tma<7, false><<<grid_t, kTmaEllThreads, smem, ctx->stream>>>(k, m, p_new, stages);
+        }
+        ctx->launches++;
+        OGL_CUDA(ctx, cudaGetLastError());
+        return OGL_OK;
+    }
     const int minb = (int)ctx->ell_minb_cgp;
     const int grid = ell_grid(ctx, minb);
     const int chunk = (int)ctx->ell_chunk;
