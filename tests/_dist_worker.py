@@ -92,7 +92,27 @@ def main():
         r -= alpha * q
         rho_prev = rho
 
+    # the two host collectives of the NCCL-free bootstrap / the adaptive criterion (Pstream helpers)
+    blobs = ps.all_gather_bytes(bytes([rank]) * (3 + rank))
+    cost = ps.broadcast_scalar(100.0 + rank)       # rank 0's figure everywhere
+    ps.barrier()
+    # and the decomposed Matrix-Market bridge: every rank dumps its block, rank 0 reads them all back
+    from ogl_b200 import mtxio
+    folder = os.path.join(os.path.dirname(out_path), f"processor{rank}", "1")
+    os.makedirs(folder, exist_ok=True)
+    mtxio.write_mtx_coordinate(os.path.join(folder, "p_A_local.mtx"), a.n, a.n, a.rows, a.cols, a.vals)
+    mtxio.write_mtx_coordinate(os.path.join(folder, "p_A_non_local.mtx"), a.n, a.nl_rows.size, a.nl_rows, a.nl_cols,
+                               a.nl_vals)
+    mtxio.write_mtx_array(os.path.join(folder, "p_rhs_b_.mtx"), s.source)
+    mtxio.write_partition_sidecar(folder, "p", rank, world, s.n, tid, tsz)
+    ps.barrier()
+    reread = -1
+    if rank == 0:
+        back = mtxio.import_decomposed(os.path.dirname(out_path), "1", "p")
+        reread = int(sum(len(t.interfaces) for t in back))
+
     json.dump({"rank": rank, "world": world, "nccl_id": list(ps.nccl_id) if ps.nccl_id else None,
+               "blobs": [list(b) for b in blobs], "cost": cost, "reread_interfaces": reread,
                "y": y.tolist(), "halo_gids": recv.tolist(), "iters": it, "res": res,
                "x": xk.tolist(), "fcs": fcs.tolist()},
               open(f"{out_path}.{rank}", "w"))

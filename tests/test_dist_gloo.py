@@ -42,6 +42,14 @@ def test_two_ranks_over_gloo(oracle, tmp_path, case):
     # both ranks hold the same 128-byte NCCL id
     assert res[0]["nccl_id"] is not None and len(res[0]["nccl_id"]) == 128
     assert res[0]["nccl_id"] == res[1]["nccl_id"] and any(res[0]["nccl_id"])
+    # host collectives used by the NCCL-free window bootstrap and by the adaptive criterion
+    for r in range(2):
+        assert res[r]["blobs"] == [[0, 0, 0], [1, 1, 1, 1]] and res[r]["cost"] == 100.0
+    # per-processor Matrix-Market dumps written by the ranks and read back on rank 0
+    # (one interface per neighbour rank comes back: patches to the same neighbour are concatenated, and
+    # rank-local cyclic couplings are ordinary entries of A_local after the dump)
+    n_nbr_pairs = sum(len({i.nbr_rank for i in s.interfaces if i.kind == "processor"}) for s in systems)
+    assert res[0]["reread_interfaces"] == n_nbr_pairs
     # distributed SpMV == oracle's rank-by-rank emulation
     xg = np.random.default_rng(5).normal(size=sum(s.n for s in systems))
     ys = oracle.dist_spmv(asms, [xg[s.global_ids] for s in systems])
