@@ -104,7 +104,7 @@ __device__ __forceinline__ bool criterion_check_untimed(SolveState *s, double no
 constexpr int kMaxPeers = 8;       // ranks per NVSwitch domain
 constexpr int kMaxTargets = 32;    // neighbour ranks of one rank
 constexpr int kSlot = 2 * kMaxReduce;   // 8-byte words per source rank: (low half | seq), (high half | seq) per value
-constexpr long long kSpinCycles = 6000000000LL;   // ~3 s: fail loudly instead of hanging
+constexpr long long kSpinCycles = 40000000000LL;   // ~20 s (ranks time-slicing ONE device wait that long for each other): fail loudly instead of hanging
 
 struct CommDev {
     int rank, n_ranks, n_targets, pad;
