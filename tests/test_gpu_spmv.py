@@ -175,10 +175,11 @@ def test_row_length_histogram_drives_the_kernel_choice(ctx):
     assert ctx.get_option("spmv_variant_in_use") in (2, 3)
 
 
-def test_tma_fed_coded_ell_is_bit_identical(ctx, oracle):
+@pytest.mark.parametrize("cells", [4, 5, 7, 33])
+def test_tma_fed_coded_ell_is_bit_identical(ctx, oracle, cells):
     """ell_tma: the value stream goes through cp.async.bulk + mbarrier stages instead of per-thread
-    loads; same row sums."""
-    s = cases.pressure_3d(33)[0]            # 35937 rows: a ragged last tile
+    loads; same row sums.  64 / 125 / 343 rows: less than one or two tiles; 35937: a ragged last tile."""
+    s = cases.pressure_3d(cells)[0]
     x = np.random.default_rng(8).normal(size=s.n)
     upload_system(ctx, s, partition=False)
     ctx.set_option("spmv_variant", 7)
