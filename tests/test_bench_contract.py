@@ -33,3 +33,27 @@ def test_reference_arm_line():
 def test_reference_arm_other_ranks_stay_silent():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     assert run("--gpus", "2", env=env) == []
+
+
+def test_both_arms_build_the_same_config_dict():
+    """The driver compares the two arms' `config`: it comes from one function fed with the rank-0
+    block of the same decomposition, and names the workload BASELINE.json is quoted on."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for n_gpus in (1, 2, 8):
+        s = bench.build_rank_system(6, n_gpus, 0)
+        c = bench.common_config(6, n_gpus, s)
+        assert c["rows_per_gpu"] == 216 and c["cells_global"] == 216 * n_gpus
+        assert c["decomposition"] == list(bench.procs_for(n_gpus))
+        assert c["halo_per_gpu"] == {1: 0, 2: 36, 8: 108}[n_gpus]
+        assert set(c) == {"workload", "rows_per_gpu", "nnz_per_gpu", "halo_per_gpu", "cells_global",
+                          "decomposition", "value_definition", "l2"}
+    assert "BASELINE configs[4]" in bench.workload_text(200, 8) and "64 M cells" in bench.workload_text(200, 8)
+    # SURVEY 8(d): algorithmic bytes at 200^3
+    n, nnz = 8_000_000, 55_760_000
+    assert bench.alg_bytes_spmv(n, nnz) == 12 * nnz + 4 * (n + 1) + 16 * n == 829_120_004
+    assert bench.alg_bytes_pcg(n, nnz) == 1_469_120_004
+    assert bench.alg_bytes_bicgstab(n, nnz) == 2 * (12 * nnz + 4 * (n + 1)) + 200 * n
+    # the oracle's pinned iteration counts exist for every default workload of the scaling run
+    for k in ("pressure_200_x1", "pressure_200_x2", "pressure_200_x4", "pressure_200_x8", "pressure_100_x1"):
+        assert bench.expected(k)["iterations"] > 100
