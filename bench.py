@@ -521,7 +521,8 @@ def run_gpu(args):
     spmv_ms, spmv_plain_ms, spmv_b2b_ms = (float(v) for v in t.tolist())
     variant = ctx.get_option("spmv_variant_in_use")
     coded = ctx.get_option("ell_coded_active")
-    ctx_ell_tma = coded and (ctx.get_option("ell_tma") == 1 or (ctx.get_option("ell_tma") == 2 and n > (1 << 21)))
+    ctx_ell_tma = coded and (ctx.get_option("ell_tma") == 1 or (ctx.get_option("ell_tma") == 2 and (
+        n > (1 << 21) or (n_gpus > 1 and n > (1 << 18)))))
 
     if ps.rank != 0:
         ctx.close()
