@@ -137,22 +137,7 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
     if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(a.ea, 0);
     const bool p_is_z = a.state->flag_p_is_z != 0;
     const double t = a.state->coef_p;
-    if (a.pack == 2) {
-        // ghost-p mode: the neighbours pushed their boundary z into slot 2 of my window
-        // (k_cg_xr / push_boundary) as self-validating words stamped with the number of the
-        // all-reduce that gave rho; the ghost entries of p get the same update as the
-        // neighbours' own cells -- same operands, same operations, same bits.
-        const CommDev *c = a.ea.comm;
-        const unsigned long long *zg =
-            reinterpret_cast<const unsigned long long *>(c->my_recv + 2 * (size_t)c->my_recv_stride);
-        const unsigned long long stamp = stamp_of(ld_ar_seq(c));
-        const long long t0 = clock64();
-        GRID_STRIDE(k, a.n_send) {
-            double z = 0.0;
-            if (!pull_stamped(zg + 2 * k, stamp, t0, z)) a.state->comm_error = 1;
-            a.out0[a.n + k] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.in1[a.n + k]));
-        }
-    } else if (a.pack) {
+    if (a.pack == 1) {
         CommDev *c = a.ea.comm;
         const unsigned long long seq = c->halo_seq + 1;
         const int parity = (int)(seq & 1ull);
@@ -195,6 +180,24 @@ __global__ void __launch_bounds__(kT, kBlas1BlocksPerSM) k_cg_p(const VecK a)
         const int64_t i = a.n - 1;
         const double z = a.in0[i];
         a.out0[i] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.in1[i]));
+    }
+    // (behind the main loop: nobody needs the ghost entries before the next launch, and the words were
+    // pushed a whole kernel ago -- in front of the loop the extra round trip delayed every thread)
+    if (a.pack == 2) {
+        // ghost-p mode: the neighbours pushed their boundary z into slot 2 of my window
+        // (k_cg_xr / push_boundary) as self-validating words stamped with the number of the
+        // all-reduce that gave rho; the ghost entries of p get the same update as the
+        // neighbours' own cells -- same operands, same operations, same bits.
+        const CommDev *c = a.ea.comm;
+        const unsigned long long *zg =
+            reinterpret_cast<const unsigned long long *>(c->my_recv + 2 * (size_t)c->my_recv_stride);
+        const unsigned long long stamp = stamp_of(ld_ar_seq(c));
+        const long long t0 = clock64();
+        GRID_STRIDE(k, a.n_send) {
+            double z = 0.0;
+            if (!pull_stamped(zg + 2 * k, stamp, t0, z)) a.state->comm_error = 1;
+            a.out0[a.n + k] = p_is_z ? z : __dadd_rn(z, __dmul_rn(t, a.in1[a.n + k]));
+        }
     }
 }
 
