@@ -57,3 +57,30 @@ def test_both_arms_build_the_same_config_dict():
     # the oracle's pinned iteration counts exist for every default workload of the scaling run
     for k in ("pressure_200_x1", "pressure_200_x2", "pressure_200_x4", "pressure_200_x8", "pressure_100_x1"):
         assert bench.expected(k)["iterations"] > 100
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_at_a_small_size():
+    """The GPU arm end to end on a small system (72^3 per GPU: the kernels of the default run): one JSON
+    line with the contract's keys, a passing in-line check, e2e bytes counted, launches counted."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--cells", "72", "--steps", "2",
+                        "--warmup", "3", "--no-extra"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = lines[0]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks",
+                "check"):
+        assert key in d, key
+    assert d["metric"] == "PCG iterations/sec" and d["dtype"] == "f64" and d["n_gpus"] == 1
+    assert d["check"]["ok"] is True and d["check"]["true_residual"] < 1e-6
+    assert d["gpu_launches"] > 0 and d["value"] > 0 and 0 < d["e2e"]["value"] < d["value"]
+    n, f = 72 ** 3, 3 * 72 * 72 * 71
+    assert d["e2e"]["h2d_bytes_per_step"] == 8 * f + 24 * n and d["e2e"]["d2h_bytes_per_step"] == 8 * n
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert "k_spmv_ell" in r["kernel"] and d["cpu_baseline"]["kind"] == "port"
