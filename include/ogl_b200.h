@@ -51,7 +51,8 @@ enum {
  *
  * nccl_id: OGL_NCCL_ID_BYTES bytes produced by ogl_nccl_unique_id() on rank 0
  * and distributed by the caller (MPI_Bcast in OpenFOAM, torch.distributed
- * here); may be NULL when n_ranks == 1.
+ * here); may be NULL when n_ranks == 1, and also when n_ranks > 1 if the caller
+ * bootstraps the peer-memory windows itself (ogl_partition_export / _connect).
  * stream: a cudaStream_t to order all work on, or NULL for a private stream. */
 int ogl_nccl_unique_id(void *out_id);
 int ogl_device_count(int *count);
@@ -59,8 +60,15 @@ int ogl_ctx_create(int device_id, int rank, int n_ranks, const void *nccl_id,
                    void *stream, ogl_ctx **out);
 int ogl_ctx_destroy(ogl_ctx *ctx);
 const char *ogl_last_error(const ogl_ctx *ctx);
-/* tuning knobs for experiments ("spmv_variant", "chunk_iters", "use_graph",
- * "profile_stride", ...); unknown keys fail with OGL_ERR_INVALID */
+/* tuning knobs for experiments; unknown keys fail with OGL_ERR_INVALID, setting a key to its
+ * current value keeps the cached iteration graph.  Kernel choice: "spmv_variant" (0 auto from the
+ * row-length histogram, 1 stream, 2 thread/row, 3 warp/row, 4 TMA CSR, 5 warp tile, 6 pipelined
+ * stream, 7 ELL), "ell_auto", "ell_coded" (pattern-coded ELL columns: 0 off, 1 auto, 2 force),
+ * "ell_tma" (TMA-fed coded ELL: 0 off, 1 on, 2 auto by size), "tma_stages", "ell_minb", "ell_chunk",
+ * "fuse_p" (CG p-update inside the ELL SpMV), "fused_pcg" (persistent CG loop kernel: 0/1/2 auto),
+ * "gmres_persist".  Loop control: "use_graph", "device_loop", "loop_iters", "chunk_iters",
+ * "use_pdl".  Several ranks: "comm_mode" (0 auto, 1 NCCL, 2 peer memory), "fused_halo", "ghost_p".
+ * Measurement: "profile_stride", "trace", "blas1_blocks", "stream_ctas", "l2_keep_mb". */
 int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value);
 int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value);
 
