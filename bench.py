@@ -302,7 +302,7 @@ def pin_system(s):
 
 
 def extra_solve(name, s, solver_kw, precond, tol, exp_key, alg_bytes_fn, peak, max_iter=1000, krylov_dim=100,
-                reps=3):
+                reps=3, scaling=1.0):
     """One of the other BASELINE configs as a device-resident solve on one GPU (plugin surface for
     the setup, resident loop for the timing), with its own check."""
     import torch
@@ -314,11 +314,13 @@ def extra_solve(name, s, solver_kw, precond, tol, exp_key, alg_bytes_fn, peak, m
     controls = {"solver": solver_kw, "executor": "cuda", "tolerance": tol, "relTol": 0.0, "adaptMinIter": False,
                 "updateInitGuess": True, "krylovDim": krylov_dim, "maxIter": max_iter,
                 "preconditioner": precond}
+    if scaling != 1.0:
+        controls["scaling"] = scaling      # e.g. -1: the SPD twin of OpenFOAM's pressure matrix (README.md:101)
     sol = lduMatrix_solver_New("f", s, controls, db)
     psi = np.zeros(s.n)
     perf = sol.solve(psi, s.source)        # builds everything; also the checked solve
     ctx = sol.ctx
-    true_res = float(np.abs(ctx.spmv(psi) - s.source).sum() / sol.last_result.norm_factor)
+    true_res = float(np.abs(ctx.spmv(psi) - scaling * s.source).sum() / sol.last_result.norm_factor)
     best = None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     for _ in range(reps):
@@ -596,6 +598,12 @@ def run_gpu(args):
                 f"{args.n}^3 pressure GKOCG+BJ(maxBlockSize 4): same system as the bench line", s, "GKOCG",
                 {"preconditioner": "BJ", "maxBlockSize": 4}, TOL, None, alg_bytes_pcg, peak)
             extra["pressure_cg_bj4"]["us_per_iteration_scalar_jacobi"] = 1e6 / it_per_s
+            # incomplete Cholesky (exact IC(0), exact triangular sweeps in dependency order) on the SPD twin
+            # of the same system: fewer iterations, each paying two sweeps of 3N-2 dependency levels
+            extra["pressure_cg_ic"] = extra_solve(
+                f"{args.n}^3 pressure GKOCG+IC, scaling -1: same system as the bench line", s, "GKOCG", "IC", TOL,
+                f"pressure_{args.n}_x1_ic", None, peak, scaling=-1.0, reps=2)
+            extra["pressure_cg_ic"]["solve_ms_scalar_jacobi"] = ms_res / args.steps
             mom = cases.momentum_3d(200)[0]
             extra["configs2_momentum_200_bicgstab"] = extra_solve(
                 "200^3 momentum GKOBiCGStab+BJ, tolerance 1e-5 (BASELINE configs[2])", mom, "GKOBiCGStab", "BJ",
@@ -607,6 +615,9 @@ def run_gpu(args):
                     "sample": f"{foam_done} PBiCGStab iterations (oracle/foam_pcg.cpp), {foam_sec:.1f} s"}
             except Exception as e:
                 extra["configs2_momentum_200_bicgstab"]["cpu_openfoam_native_pbicgstab"] = {"error": repr(e)[:200]}
+            extra["momentum_200_bicgstab_ilu"] = extra_solve(
+                "200^3 momentum GKOBiCGStab+ILU, tolerance 1e-5 (exact ILU(0), exact triangular sweeps)", mom,
+                "GKOBiCGStab", "ILU", 1e-5, "momentum_200_x1_ilu", None, peak, max_iter=1000, reps=2)
             del mom
             ch = cases.channel((128, 64, 64), (1, 1, 1))[0]
             rec = extra_solve("channel 128x64x64, cyclic in x and z, GKOGMRES(100)+BJ (BASELINE configs[3], "

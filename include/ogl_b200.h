@@ -66,7 +66,8 @@ const char *ogl_last_error(const ogl_ctx *ctx);
  * stream, 7 ELL), "ell_auto", "ell_coded" (pattern-coded ELL columns: 0 off, 1 auto, 2 force),
  * "ell_tma" (TMA-fed coded ELL: 0 off, 1 on, 2 auto by size), "tma_stages", "ell_minb", "ell_chunk",
  * "fuse_p" (CG p-update inside the ELL SpMV), "fused_pcg" (persistent CG loop kernel: 0/1/2 auto),
- * "gmres_persist".  Loop control: "use_graph", "device_loop", "loop_iters", "chunk_iters",
+ * "gmres_persist", "tri_variant" (ILU / IC sweeps: 0 one launch per dependency level, 1 one
+ * dependency-driven launch per sweep; read-only "tri_levels_lower" / "tri_levels_upper").  Loop control: "use_graph", "device_loop", "loop_iters", "chunk_iters",
  * "use_pdl".  Several ranks: "comm_mode" (0 auto, 1 NCCL, 2 peer memory), "fused_halo", "ghost_p".
  * Measurement: "profile_stride", "trace", "blas1_blocks", "stream_ctas", "l2_keep_mb". */
 int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value);
@@ -157,9 +158,23 @@ int ogl_vector_fill(ogl_ctx *ctx, int which, double value);
 /* ISAI: Ginkgo preconditioner::Isai<isai_type::spd> (Preconditioner/Preconditioner.H:225-242; needs an
  * SPD local matrix, i.e. `scaling -1` for OpenFOAM's pressure equation, README.md:101), GISAI:
  * Isai<isai_type::general> (:243-260); sparsityPower 1, rows up to 8 entries */
-enum { OGL_PRECOND_NONE = 0, OGL_PRECOND_BJ = 1, OGL_PRECOND_ISAI = 2, OGL_PRECOND_GISAI = 3 };
+/* ILU: Ginkgo factorization::Ilu (exact ILU(0)) + preconditioner::Ilu<LowerTrs, UpperTrs>
+ * (Preconditioner/Preconditioner.H:106-124); IC: factorization::Ic + preconditioner::Ic (:177-196,
+ * needs an SPD local matrix like ISAI); IRILU: the ILU(0) factors with each triangular solve replaced
+ * by 5 Richardson sweeps preconditioned with scalar Jacobi (:143-176).  All on the LOCAL block
+ * (wrap_schwarz, :66-82).  The factorisation and the exact sweeps run level by level over the
+ * dependency graph of the pattern, analysed once per mesh on the device.  ILUT / ICT (ParILUT / ParICT,
+ * threshold-based and non-deterministic in the reference) are not built. */
+enum { OGL_PRECOND_NONE = 0, OGL_PRECOND_BJ = 1, OGL_PRECOND_ISAI = 2, OGL_PRECOND_GISAI = 3,
+       OGL_PRECOND_ILU = 4, OGL_PRECOND_IC = 5, OGL_PRECOND_IRILU = 6 };
 int ogl_precond_setup(ogl_ctx *ctx, int kind, int32_t max_block_size,
                       int skip_sorting);
+/* parity hook: the incomplete factors over the local CSR pattern ([nnz]; strictly lower part = L,
+ * upper part incl. the diagonal = U; IC: lower part incl. the diagonal = L, upper part = L^T) */
+int ogl_precond_factors_download(ogl_ctx *ctx, double *factors);
+/* z = M^-1 r through the current preconditioner on host vectors of the local size (parity hook for
+ * the triangular sweeps; any preconditioner kind) */
+int ogl_precond_apply(ogl_ctx *ctx, const double *r_host, double *z_host);
 /* parity hooks: block pointers and inverted blocks (row-major, concatenated) */
 int ogl_precond_download(ogl_ctx *ctx, int32_t *n_blocks, int32_t *block_ptrs,
                          double *inv_blocks);

@@ -181,6 +181,19 @@ class Context:
         self._check(self.lib.ogl_precond_download(self.h, C.byref(nb), _ptr(bp), _ptr(inv)))
         return bp, inv
 
+    def precond_factors_download(self):
+        """ILU / IC / IRILU factors over the local CSR pattern (parity hook)."""
+        out = np.empty(self.nnz)
+        self._check(self.lib.ogl_precond_factors_download(self.h, _ptr(out)))
+        return out
+
+    def precond_apply(self, r):
+        """z = M^-1 r on host vectors of the local size (parity hook)."""
+        r = np.ascontiguousarray(r, np.float64)
+        z = np.empty_like(r)
+        self._check(self.lib.ogl_precond_apply(self.h, _ptr(r), _ptr(z)))
+        return z
+
     def solve(self, solver, tolerance=1e-6, rel_tol=0.0, min_iter=0, max_iter=1000, frequency=1,
               krylov_dim=100, export_res=False) -> L.SolveResult:
         p = L.SolveParams(solver, tolerance, rel_tol, min_iter, max_iter, frequency, krylov_dim,

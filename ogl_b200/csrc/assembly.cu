@@ -377,6 +377,7 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     ctx->max_row_len = max_len;
     ctx->have_pattern = true;
     ell_invalidate(ctx, /*structure=*/true);
+    ctx->tri.structure_ready = false;   // ILU / IC dependency levels belong to the old pattern (trifactor.cu)
     ctx->have_values = false;
     // `regenerate true` rebuilds the pattern of the same mesh every solve; the reference's
     // PersistentVector b / x survive that (lduLduBase.H:217-237), so do these

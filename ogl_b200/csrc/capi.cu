@@ -142,6 +142,7 @@ static void destroy(Context *c)
                     c->d_isai_w,     c->d_isai_wt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    tri_release(c);
     for (double *w : c->work)
         if (w) cudaFree(w);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -354,6 +355,15 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
         ctx->ell_auto = value != 0;
     } else if (k == "gmres_persist") {
         ctx->gmres_persist = value != 0;
+    } else if (k == "tri_variant") {
+        if (value < 0 || value > 1) return fail(ctx, OGL_ERR_INVALID, "tri_variant in {0,1}");
+        ctx->tri_variant = value;
+    } else if (k == "tri_sleep_ns") {
+        if (value < 0 || value > 100000) return fail(ctx, OGL_ERR_INVALID, "tri_sleep_ns in [0,100000]");
+        ctx->tri_sleep_ns = value;
+    } else if (k == "tri_ctas") {
+        if (value < 0 || value > 32) return fail(ctx, OGL_ERR_INVALID, "tri_ctas in [0,32]");
+        ctx->tri_ctas = value;
     } else if (k == "ell_chunk") {
         if (value < 1 || value > 4096) return fail(ctx, OGL_ERR_INVALID, "ell_chunk in [1,4096]");
         ctx->ell_chunk = value;
@@ -431,6 +441,11 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "ell_coded") *value = ctx->ell_coded;
     else if (k == "ell_chunk") *value = ctx->ell_chunk;
     else if (k == "gmres_persist") *value = ctx->gmres_persist;
+    else if (k == "tri_variant") *value = ctx->tri_variant;
+    else if (k == "tri_sleep_ns") *value = ctx->tri_sleep_ns;
+    else if (k == "tri_ctas") *value = ctx->tri_ctas;
+    else if (k == "tri_levels_lower") *value = ctx->tri.structure_ready ? (int64_t)ctx->tri.lvl_l.size() - 1 : 0;
+    else if (k == "tri_levels_upper") *value = ctx->tri.structure_ready ? (int64_t)ctx->tri.lvl_u.size() - 1 : 0;
     else if (k == "ell_tma") *value = ctx->ell_tma;
     else if (k == "ell_minb") *value = ctx->ell_minb;
     else if (k == "ell_minb_cgp") *value = ctx->ell_minb_cgp;
@@ -611,6 +626,34 @@ int ogl_precond_download(ogl_ctx *ctx, int32_t *n_blocks, int32_t *block_ptrs, d
     if (inv_blocks)
         OGL_TRY(download(ctx, inv_blocks, ctx->d_inv_blocks, sizeof(double) * ctx->inv_blocks_len));
     return OGL_OK;
+}
+
+int ogl_precond_factors_download(ogl_ctx *ctx, double *factors)
+{
+    CHECK_CTX(ctx);
+    if (!factors) return fail(ctx, OGL_ERR_INVALID, "null argument");
+    if (!ctx->have_precond || !is_tri_precond(ctx->precond_kind) || !ctx->tri.vals)
+        return fail(ctx, OGL_ERR_INVALID, "no ILU / IC / IRILU preconditioner");
+    return download(ctx, factors, ctx->tri.vals, sizeof(double) * ctx->nnz);
+}
+
+int ogl_precond_apply(ogl_ctx *ctx, const double *r_host, double *z_host)
+{
+    CHECK_CTX(ctx);
+    if (!r_host || !z_host) return fail(ctx, OGL_ERR_INVALID, "null argument");
+    if (!ctx->have_pattern || !ctx->have_precond)
+        return fail(ctx, OGL_ERR_INVALID, "ogl_precond_apply before ogl_precond_setup");
+    if (is_tri_precond(ctx->precond_kind)) OGL_TRY(tri_ensure_structure(ctx));
+    double *r, *z;
+    OGL_TRY(get_work(ctx, 0, &r));
+    OGL_TRY(get_work(ctx, 1, &z));
+    OGL_TRY(upload(ctx, r, r_host, sizeof(double) * ctx->n));
+    OGL_CUDA(ctx, cudaMemsetAsync(&ctx->d_state->comm_error, 0, sizeof(int), ctx->stream));
+    OGL_TRY(precond_apply(ctx, r, z, nullptr, 0, false, 0, false, 0));
+    int err = 0;
+    OGL_TRY(download(ctx, &err, &ctx->d_state->comm_error, sizeof(int)));
+    if (err) return fail(ctx, OGL_ERR_CUDA, "ILU/IC triangular sweep timed out waiting for a row it depends on");
+    return download(ctx, z_host, z, sizeof(double) * ctx->n);
 }
 
 int ogl_solve(ogl_ctx *ctx, const ogl_solve_params *params, ogl_solve_result *result)

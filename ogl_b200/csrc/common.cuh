@@ -220,6 +220,25 @@ struct Context {
     // ISAI / GISAI: approximate-inverse values over the CSR pattern of the local matrix (w), and
     // for the spd variant the transpose (wt); z = W r  or  z = W^T (W r)
     double *d_isai_w = nullptr, *d_isai_wt = nullptr;
+    // ILU / IC / IRILU (trifactor.cu): incomplete factors over the CSR pattern of the local matrix
+    // (strictly lower part = L, upper part = U with the diagonal; IC: L with its diagonal, mirrored
+    // into the upper part), rows grouped into dependency levels for the two triangular sweeps
+    struct TriFactor {
+        bool structure_ready = false;   // diag_pos / perm_* / levels match the current pattern
+        int64_t nnz = 0;                // entries `vals` was sized for
+        label *diag_pos = nullptr;      // [n] position of (i,i) in the CSR
+        label *perm_l = nullptr, *perm_u = nullptr;   // [n] rows in level order (forward / backward sweep)
+        std::vector<label> lvl_l, lvl_u;              // level offsets into perm_* (host copy, one launch per level)
+        double *vals = nullptr;         // [nnz]
+        double *dval = nullptr;         // [n] the factor's diagonal (vals[diag_pos[i]]), contiguous
+        label dval_n = 0;
+        int max_lower = 0, max_upper = 0;   // longest strictly lower / upper part of a row
+        int sf_grid = 0, sf_per_sm = 1;     // co-resident grid of the dependency-driven sweeps
+    } tri;
+    int64_t tri_sleep_ns = 0;     // dependency-driven sweep: pause of a waiting warp between two rounds of polls
+    int64_t tri_ctas = 0;         // ... and its CTAs per SM (0 = as many as fit)
+    int64_t tri_variant = 1;   // triangular sweeps: 0 one launch per dependency level, 1 ONE launch per sweep whose
+                               // rows wait for the entries they depend on (trifactor.cu:k_trisolve_sf)
 
     // reduction scratch
     double *d_partials = nullptr;          // kMaxPartialBlocks * kMaxReduce
@@ -354,6 +373,15 @@ int dist_spmv(Context *ctx, const SpmvArgs &a);                   // halo + loca
 int precond_setup(Context *ctx, int kind, label mbs);
 int precond_apply(Context *ctx, const double *r, double *z, const double *dot_with,
                   int red_base, bool guard_done, int epi, bool inline_epi, int ar_count);
+// trifactor.cu -------------------------------------------------------------------
+inline bool is_tri_precond(int kind)
+{
+    return kind == OGL_PRECOND_ILU || kind == OGL_PRECOND_IC || kind == OGL_PRECOND_IRILU;
+}
+int tri_setup(Context *ctx, int kind);                 // (analysis once per pattern) + factorisation
+int tri_ensure_structure(Context *ctx);                // re-analyse after a pattern rebuild (cached factors)
+int tri_apply(Context *ctx, const double *r, double *z, bool guard_done);
+void tri_release(Context *ctx);
 bool use_p2p(const Context *ctx);
 void comm_teardown(Context *ctx);
 int comm_bench(Context *ctx, int mode, int reps, double *us);

@@ -561,6 +561,8 @@ int solve_gmres(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
     res->solve_us = ms * 1e3;
     res->resnorm_us = hs.crit_ns > 0 ? (double)hs.crit_ns * 1e-3 : 0.0;   // see solver.cu:solve
     res->kernel_launches = ctx->launches - launches0;
+    if (hs.comm_error == 2)
+        return fail(ctx, OGL_ERR_CUDA, "ILU/IC triangular sweep timed out waiting for a row it depends on");
     if (hs.comm_error)
         return fail(ctx, OGL_ERR_NCCL, "peer synchronisation timed out (a rank left the solve?)");
     if (!hs.done)

@@ -226,7 +226,8 @@ struct ApplyK {
     EpiArgs ea;
 };
 
-// z = M^-1 r, one thread per row.  KIND 1: scalar, 2: block.
+// z = M^-1 r, one thread per row.  KIND 1: scalar, 2: block, 0: z was written by the launches
+// before (ILU / IC sweeps) and only <dot_with, z> + the epilogue are left.
 template <int KIND, int NRED>
 __global__ void __launch_bounds__(256) k_jacobi_apply(const ApplyK a)
 {
@@ -235,7 +236,9 @@ __global__ void __launch_bounds__(256) k_jacobi_apply(const ApplyK a)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n; row += stride) {
         double z;
-        if (KIND == 1) {
+        if (KIND == 0) {
+            z = a.z[row];
+        } else if (KIND == 1) {
             z = __dmul_rn(a.r[row], a.inv_diag[row]);   // jacobi::scalar_apply
         } else {
             const label b = a.row_block[row];
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(256) k_jacobi_apply(const ApplyK a)
             z = 0.0;
             for (label j = 0; j < sz; ++j) z = __dadd_rn(z, __dmul_rn(m[j], a.r[lo + j]));
         }
-        a.z[row] = z;
+        if (KIND != 0) a.z[row] = z;
         if (NRED) red[0] += __dmul_rn(a.dot_with[row], z);
     }
     if (NRED)
@@ -258,9 +261,20 @@ int precond_setup(Context *ctx, int kind, label mbs)
 {
     if (!ctx->have_pattern || !ctx->have_values)
         return fail(ctx, OGL_ERR_INVALID, "ogl_precond_setup before the matrix is assembled");
-    if (kind != OGL_PRECOND_NONE && kind != OGL_PRECOND_BJ && kind != OGL_PRECOND_ISAI && kind != OGL_PRECOND_GISAI)
+    if (kind != OGL_PRECOND_NONE && kind != OGL_PRECOND_BJ && kind != OGL_PRECOND_ISAI && kind != OGL_PRECOND_GISAI &&
+        !is_tri_precond(kind))
         return fail(ctx, OGL_ERR_UNSUPPORTED,
-                    "preconditioner not supported; valid choices: none, BJ, ISAI, GISAI");
+                    "preconditioner not supported; valid choices: none, BJ, ISAI, GISAI, ILU, IC, IRILU");
+    if (is_tri_precond(kind)) {
+        if (kind == OGL_PRECOND_IC && !ctx->symmetric)
+            return fail(ctx, OGL_ERR_INVALID, "IC needs a symmetric matrix; use ILU");
+        OGL_TRY(tri_setup(ctx, kind));
+        ctx->precond_kind = kind;
+        ctx->max_block_size = 1;
+        ctx->have_precond = true;
+        ctx->precond_setups++;
+        return OGL_OK;
+    }
     if (kind == OGL_PRECOND_ISAI || kind == OGL_PRECOND_GISAI) {
         if (ctx->max_row_len > kIsaiMax)
             return fail(ctx, OGL_ERR_UNSUPPORTED, "ISAI: rows longer than 8 entries are not supported");
@@ -432,6 +446,13 @@ int precond_apply(Context *ctx, const double *r, double *z, const double *dot_wi
         }
         return spmv_local(ctx, s2);
     }
+    const bool tri = is_tri_precond(ctx->precond_kind);
+    if (tri) {
+        // Schwarz: the LOCAL factors; two triangular sweeps (or 5 + 5 Richardson sweeps), then the
+        // reduction the caller asked for as one more pass over z
+        OGL_TRY(tri_apply(ctx, r, z, guard_done));
+        if (!dot_with) return OGL_OK;
+    }
     ApplyK a;
     a.n = ctx->n;
     a.r = r;
@@ -453,7 +474,9 @@ int precond_apply(Context *ctx, const double *r, double *z, const double *dot_wi
     int grid = (ctx->n + 255) / 256;
     if (grid > ctx->blas1_blocks) grid = (int)ctx->blas1_blocks;
     const bool scalar = ctx->max_block_size == 1;
-    if (dot_with) {
+    if (tri) {
+        k_jacobi_apply<0, 1><<<grid, 256, 0, ctx->stream>>>(a);
+    } else if (dot_with) {
         if (scalar) k_jacobi_apply<1, 1><<<grid, 256, 0, ctx->stream>>>(a);
         else k_jacobi_apply<2, 1><<<grid, 256, 0, ctx->stream>>>(a);
     } else {

@@ -618,7 +618,8 @@ int vec_scale(Context *ctx, double *v, double s)
 static int pk_of(const Context *ctx)
 {
     if (ctx->precond_kind == OGL_PRECOND_NONE) return 0;
-    if (ctx->precond_kind == OGL_PRECOND_ISAI || ctx->precond_kind == OGL_PRECOND_GISAI)
+    if (ctx->precond_kind == OGL_PRECOND_ISAI || ctx->precond_kind == OGL_PRECOND_GISAI ||
+        is_tri_precond(ctx->precond_kind))
         return 3;   // applied by its own launches (precond_apply)
     return ctx->max_block_size == 1 ? 1 : 2;
 }
@@ -926,7 +927,8 @@ static int run_chunks(Context *ctx, int solver, int64_t max_criterion_calls, F e
     const int64_t sig0 = ((int64_t)solver << 48) ^ ((int64_t)pk_of(ctx) << 40) ^ (ctx->use_pdl << 60) ^
                          ((int64_t)chunk << 32) ^ (int64_t)ctx->n ^ (ctx->spmv_variant << 56);
     const int64_t sig = sig0 ^ ((int64_t)(loop ? 1 : 0) << 62) ^ ((int64_t)(ctx->bj_uniform ? 1 : 0) << 61) ^
-                        ((int64_t)ctx->max_block_size << 24);
+                        ((int64_t)ctx->max_block_size << 24) ^ ((int64_t)ctx->precond_kind << 52) ^
+                        ((int64_t)ctx->tri_variant << 30);
     if (graph_ok && (!ctx->graph_exec || ctx->graph_sig != sig)) {
         if (ctx->graph_exec) {
             cudaGraphExecDestroy(ctx->graph_exec);
@@ -1024,6 +1026,7 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
                     "context without NCCL id: ogl_partition_export / ogl_partition_connect must set up the "
                     "peer-memory windows before ogl_solve (comm_mode 1 is not available)");
     if (p->frequency < 1) return fail(ctx, OGL_ERR_INVALID, "frequency must be >= 1");
+    if (is_tri_precond(ctx->precond_kind)) OGL_TRY(tri_ensure_structure(ctx));   // + its work vectors, before any capture
     if (p->solver == OGL_SOLVER_GMRES) return solve_gmres(ctx, p, res);
     if (p->solver != OGL_SOLVER_CG && p->solver != OGL_SOLVER_BICGSTAB)
         return fail(ctx, OGL_ERR_UNSUPPORTED, "unknown solver kind");
@@ -1133,6 +1136,8 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
             res->spmv_samples = pairs;
         }
     }
+    if (hs.comm_error == 2)
+        return fail(ctx, OGL_ERR_CUDA, "ILU/IC triangular sweep timed out waiting for a row it depends on");
     if (hs.comm_error)
         return fail(ctx, OGL_ERR_NCCL, "peer synchronisation timed out (a rank left the solve?)");
     if (!hs.done)

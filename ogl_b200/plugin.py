@@ -25,10 +25,11 @@ from .host import FatalError, HostMatrixWrapper, ObjectRegistry
 from .parallel import Pstream
 
 
-# `preconditioner` keyword (Preconditioner.H:91-105 BJ, :225-242 ISAI, :243-260 GISAI); the other
-# families (ILU, IC, Multigrid) are rejected
+# `preconditioner` keyword (Preconditioner.H:91-105 BJ, :106-124 ILU, :143-176 IRILU, :177-196 IC,
+# :225-242 ISAI, :243-260 GISAI); ILUT / ICT (ParILUT / ParICT) and Multigrid are rejected
 PRECOND_KINDS = {"none": L.OGL_PRECOND_NONE, "BJ": L.OGL_PRECOND_BJ, "ISAI": L.OGL_PRECOND_ISAI,
-                 "GISAI": L.OGL_PRECOND_GISAI}
+                 "GISAI": L.OGL_PRECOND_GISAI, "ILU": L.OGL_PRECOND_ILU, "IC": L.OGL_PRECOND_IC,
+                 "IRILU": L.OGL_PRECOND_IRILU}
 
 
 @dataclass
@@ -142,7 +143,7 @@ class GKOlduBaseSolver:
         # one set_option per key with its final value: an unchanged value keeps the cached chunk graph
         opts = {"spmv_variant": 7 if fmt == "Ell" else 0}
         for opt in ("spmv_variant", "chunk_iters", "use_graph", "comm_mode", "fused_halo", "ghost_p",
-                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb", "ell_auto", "fuse_p", "ell_coded", "ell_tma", "gmres_persist"):
+                    "fused_pcg", "device_loop", "loop_iters", "l2_keep_mb", "ell_auto", "fuse_p", "ell_coded", "ell_tma", "gmres_persist", "tri_variant"):
             if opt in controls:
                 opts[opt] = int(controls[opt])
         for opt, val in opts.items():
@@ -155,7 +156,7 @@ class GKOlduBaseSolver:
         self.precond_name = pre["preconditioner"] if isinstance(pre, dict) else str(pre)
         if self.precond_name not in PRECOND_KINDS:
             raise FatalError(f"OGL does not support the preconditioner: {self.precond_name}\n"
-                             "Valid Choices: none, BJ, ISAI, GISAI")
+                             "Valid Choices: none, BJ, ILU, IRILU, IC, ISAI, GISAI")
         if self.precond_name in ("ISAI", "GISAI") and int(self.precond_controls.get("sparsityPower", 1)) != 1:
             raise FatalError("ISAI / GISAI: only sparsityPower 1 is implemented")
         self.host_matrix = HostMatrixWrapper(db, matrix, controls, field_name, self.ctx, self.pstream)

@@ -22,6 +22,7 @@
 // run with OpenMP (the analogue of Ginkgo's omp executor; used only as the CPU
 // baseline in bench.py).
 #include "oracle.h"
+#include "trifactor.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -371,6 +372,8 @@ struct Jacobi {
     int kind = ORC_PRECOND_NONE;
     orc_label mbs = 1;
     dvec isai_w, isai_wt;                        // ISAI / GISAI values over the pattern of A
+    dvec fact;                                   // ILU / IC / IRILU: factors over the pattern of A (trifactor.hpp)
+    std::vector<std::vector<orc_label>> dpos;    // ... and the position of every row's diagonal entry
     dvec inv_diag;                               // mbs == 1
     std::vector<std::vector<orc_label>> bptr;    // mbs > 1
     std::vector<std::vector<orc_label>> boff;
@@ -392,6 +395,26 @@ Jacobi make_jacobi(const Sys &s, int kind, orc_label mbs)
             if (!isai_generate(k.n, s.row_ptrs[r].data(), k.cols, k.vals, kind == ORC_PRECOND_ISAI,
                                J.isai_w[r].data(), J.isai_wt[r].data()))
                 J.kind = -1;   // reported by orc_solve
+        }
+        return J;
+    }
+    if (kind == ORC_PRECOND_ILU || kind == ORC_PRECOND_IC || kind == ORC_PRECOND_IRILU) {
+        // factorisation of the LOCAL block (Schwarz, Preconditioner.H:66-82, 113-123)
+        J.fact.resize(s.R);
+        J.dpos.resize(s.R);
+        for (int r = 0; r < s.R; ++r) {
+            const auto &k = s.rk[r];
+            const orc_label *rp = s.row_ptrs[r].data();
+            J.fact[r].assign(k.vals, k.vals + k.nnz);
+            if (!orc_tri::diag_positions(k.n, rp, k.cols, J.dpos[r])) {
+                J.kind = -1;
+                continue;
+            }
+            if (kind == ORC_PRECOND_IC) {
+                if (!orc_tri::ic0(k.n, rp, k.cols, J.dpos[r].data(), J.fact[r].data())) J.kind = -1;
+            } else {
+                orc_tri::ilu0(k.n, rp, k.cols, J.dpos[r].data(), J.fact[r].data());
+            }
         }
         return J;
     }
@@ -449,6 +472,22 @@ void precond_apply(const Sys &s, const Jacobi &J, const dvec &r, dvec &z)
                 vec t(static_cast<size_t>(n));
                 apply(J.isai_w[q].data(), r[q].data(), t.data());
                 apply(J.isai_wt[q].data(), t.data(), z[q].data());
+            }
+        } else if (J.kind == ORC_PRECOND_ILU || J.kind == ORC_PRECOND_IC || J.kind == ORC_PRECOND_IRILU) {
+            const orc_label *rp = s.row_ptrs[q].data(), *cols = s.rk[q].cols, *dp = J.dpos[q].data();
+            const orc_scalar *F = J.fact[q].data();
+            vec t(static_cast<size_t>(n));
+            if (J.kind == ORC_PRECOND_IRILU) {
+                // Ilu<Ir, Ir>::apply: the intermediate starts as a copy of b, x as a copy of the
+                // intermediate (both inner solvers use their initial guess); 5 sweeps each
+                vec scratch;
+                t = r[q];
+                orc_tri::ir_jacobi(n, rp, cols, dp, F, true, 5, r[q].data(), t.data(), scratch);
+                z[q] = t;
+                orc_tri::ir_jacobi(n, rp, cols, dp, F, false, 5, t.data(), z[q].data(), scratch);
+            } else {
+                orc_tri::lower_solve(n, rp, cols, dp, F, J.kind == ORC_PRECOND_ILU, r[q].data(), t.data());
+                orc_tri::upper_solve(n, rp, cols, dp, F, t.data(), z[q].data());
             }
         } else if (J.kind != ORC_PRECOND_BJ) {
             std::memcpy(z[q].data(), r[q].data(), sizeof(orc_scalar) * n);
@@ -824,6 +863,36 @@ int orc_isai_generate(orc_label n, const orc_label *row_ptrs, const orc_label *c
                       int spd, orc_scalar *w, orc_scalar *wt)
 {
     return isai_generate(n, row_ptrs, cols, vals, spd != 0, w, wt) ? 0 : 1;
+}
+
+int orc_trifactor(int kind, orc_label n, const orc_label *row_ptrs, const orc_label *cols,
+                  const orc_scalar *vals, orc_scalar *factors)
+{
+    std::vector<orc_label> dp;
+    if (!orc_tri::diag_positions(n, row_ptrs, cols, dp)) return 1;
+    std::memcpy(factors, vals, sizeof(orc_scalar) * static_cast<size_t>(row_ptrs[n]));
+    if (kind == ORC_PRECOND_IC) return orc_tri::ic0(n, row_ptrs, cols, dp.data(), factors) ? 0 : 2;
+    if (kind != ORC_PRECOND_ILU && kind != ORC_PRECOND_IRILU) return 3;
+    orc_tri::ilu0(n, row_ptrs, cols, dp.data(), factors);
+    return 0;
+}
+
+int orc_trifactor_apply(int kind, orc_label n, const orc_label *row_ptrs, const orc_label *cols,
+                        const orc_scalar *factors, const orc_scalar *r, orc_scalar *z)
+{
+    std::vector<orc_label> dp;
+    if (!orc_tri::diag_positions(n, row_ptrs, cols, dp)) return 1;
+    std::vector<orc_scalar> t(r, r + n), scratch;
+    if (kind == ORC_PRECOND_IRILU) {
+        orc_tri::ir_jacobi(n, row_ptrs, cols, dp.data(), factors, true, 5, r, t.data(), scratch);
+        std::memcpy(z, t.data(), sizeof(orc_scalar) * static_cast<size_t>(n));
+        orc_tri::ir_jacobi(n, row_ptrs, cols, dp.data(), factors, false, 5, t.data(), z, scratch);
+        return 0;
+    }
+    if (kind != ORC_PRECOND_ILU && kind != ORC_PRECOND_IC) return 3;
+    orc_tri::lower_solve(n, row_ptrs, cols, dp.data(), factors, kind == ORC_PRECOND_ILU, r, t.data());
+    orc_tri::upper_solve(n, row_ptrs, cols, dp.data(), factors, t.data(), z);
+    return 0;
 }
 
 void orc_bj_invert_blocks(orc_label n, const orc_label *row_ptrs,

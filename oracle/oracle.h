@@ -136,7 +136,10 @@ typedef struct orc_rank_system {
 enum { ORC_CG = 0, ORC_BICGSTAB = 1, ORC_GMRES = 2 };
 /* ISAI: Ginkgo preconditioner::Isai<isai_type::spd> (Preconditioner.H:225-242), GISAI: <general>
  * (:243-260); sparsityPower 1 */
-enum { ORC_PRECOND_NONE = 0, ORC_PRECOND_BJ = 1, ORC_PRECOND_ISAI = 2, ORC_PRECOND_GISAI = 3 };
+enum { ORC_PRECOND_NONE = 0, ORC_PRECOND_BJ = 1, ORC_PRECOND_ISAI = 2, ORC_PRECOND_GISAI = 3,
+       /* exact ILU(0) / IC(0) with exact triangular solves (Preconditioner.H:106-124, 177-196) and
+        * ILU(0) with 5 Jacobi-Richardson sweeps per factor (:143-176); trifactor.hpp */
+       ORC_PRECOND_ILU = 4, ORC_PRECOND_IC = 5, ORC_PRECOND_IRILU = 6 };
 
 typedef struct orc_solve_params {
     int solver;               /* ORC_CG ...                                  */
@@ -186,6 +189,15 @@ void orc_bj_invert_blocks(orc_label n, const orc_label *row_ptrs,
                           const orc_label *cols, const orc_scalar *vals,
                           orc_label n_blocks, const orc_label *block_ptrs,
                           orc_scalar *inv /* sum b^2 */);
+/* ILU(0) / IC(0) factors over the CSR pattern of A (strictly lower part = L, upper part = U incl.
+ * the diagonal; IC: lower part incl. the diagonal = L, upper part = its transpose); 0 on success,
+ * 1 row without diagonal or with a repeated column, 2 IC on a structurally unsymmetric pattern */
+int orc_trifactor(int kind, orc_label n, const orc_label *row_ptrs, const orc_label *cols,
+                  const orc_scalar *vals, orc_scalar *factors /* [nnz] */);
+/* z = M^-1 r with those factors: exact triangular solves (ILU, IC) or 5 + 5 Jacobi-Richardson
+ * sweeps (IRILU) */
+int orc_trifactor_apply(int kind, orc_label n, const orc_label *row_ptrs, const orc_label *cols,
+                        const orc_scalar *factors, const orc_scalar *r, orc_scalar *z);
 
 /* CPU baseline helpers (bench.py): repeat SpMV / run fixed PCG iterations with
  * `threads` OpenMP threads, return seconds. */

@@ -75,7 +75,7 @@ class SolveResult(C.Structure):
 
 
 SOLVERS = {"GKOCG": 0, "GKOBiCGStab": 1, "GKOGMRES": 2}
-PRECONDS = {"none": 0, "BJ": 1, "ISAI": 2, "GISAI": 3}
+PRECONDS = {"none": 0, "BJ": 1, "ISAI": 2, "GISAI": 3, "ILU": 4, "IC": 5, "IRILU": 6}
 
 
 def lib():
@@ -355,6 +355,31 @@ def isai_values(n, row_ptrs, cols, vals, spd: bool):
     if rc != 0:
         raise RuntimeError("ISAI: row too long for the dense solver or missing diagonal")
     return w, wt
+
+
+def trifactor(kind, n, row_ptrs, cols, vals):
+    """ILU(0) / IC(0) factors over the CSR pattern (kind: "ILU", "IC", "IRILU"), trifactor.hpp."""
+    rp, c, v = _i32(row_ptrs), _i32(cols), _f64(vals)
+    out = np.zeros(v.size)
+    fn = lib().orc_trifactor
+    fn.restype = C.c_int
+    rc = fn(C.c_int(PRECONDS[kind]), C.c_int32(n), _ip(rp), _ip(c), _fp(v), _fp(out))
+    if rc != 0:
+        raise RuntimeError(f"{kind}: factorisation failed (code {rc}: 1 missing diagonal / repeated column, "
+                           "2 unsymmetric pattern)")
+    return out
+
+
+def trifactor_apply(kind, n, row_ptrs, cols, factors, r):
+    """z = M^-1 r with the factors of `trifactor` (exact triangular solves; IRILU: 5 + 5 sweeps)."""
+    rp, c, f, r = _i32(row_ptrs), _i32(cols), _f64(factors), _f64(r)
+    z = np.zeros(n)
+    fn = lib().orc_trifactor_apply
+    fn.restype = C.c_int
+    rc = fn(C.c_int(PRECONDS[kind]), C.c_int32(n), _ip(rp), _ip(c), _fp(f), _fp(r), _fp(z))
+    if rc != 0:
+        raise RuntimeError(f"{kind}: apply failed (code {rc})")
+    return z
 
 
 def bj_blocks(n, row_ptrs, cols, vals, max_block_size):

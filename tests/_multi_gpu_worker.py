@@ -21,6 +21,9 @@ CASES = {
     # Schwarz-wrapped approximate inverses of the local blocks (no communication in the apply)
     "pressure_cg_isai": (lambda p: cases.pressure_3d(12, p, sign=-1.0), "GKOCG", "ISAI", 1, 1e-9),
     "momentum_bicgstab_gisai": (lambda p: cases.momentum_3d(10, p), "GKOBiCGStab", "GISAI", 1, 1e-10),
+    # ... and incomplete factorisations of the local blocks (exact triangular sweeps)
+    "pressure_cg_ic": (lambda p: cases.pressure_3d(12, p, sign=-1.0), "GKOCG", "IC", 1, 1e-9),
+    "momentum_bicgstab_ilu": (lambda p: cases.momentum_3d(10, p), "GKOBiCGStab", "ILU", 1, 1e-10),
     "channel_gmres": (lambda p: cases.channel((16, 8, 8), p), "GKOGMRES", "BJ", 1, 1e-8),
     # all-Neumann + one reference cell: nearly singular, so solve tighter than the L2 bar
     # 2-D case: fold the z split into x ([2,2,2] -> [4,2,1] like test/integration.yaml:53-55)

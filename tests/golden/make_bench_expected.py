@@ -28,9 +28,16 @@ def pressure(n, gpus):
     return oracle.solve(asms, "GKOCG", "BJ", tolerance=bench.TOL, rel_tol=0.0, max_iter=bench.MAX_ITER, threads=1)
 
 
-def momentum(n):
+def pressure_ic(n):
+    """The SPD twin of the pressure system (`scaling -1`, README.md:101) under GKOCG + IC."""
+    a = oracle.assemble(bench.build_rank_system(n, 1, 0))
+    a.vals, a.b = -a.vals, -a.b
+    return oracle.solve([a], "GKOCG", "IC", tolerance=bench.TOL, rel_tol=0.0, max_iter=bench.MAX_ITER, threads=1)
+
+
+def momentum(n, precond="BJ"):
     s = cases.momentum_3d(n)[0]
-    return oracle.solve([oracle.assemble(s)], "GKOBiCGStab", "BJ", tolerance=1e-5, rel_tol=0.0,
+    return oracle.solve([oracle.assemble(s)], "GKOBiCGStab", precond, tolerance=1e-5, rel_tol=0.0,
                         max_iter=2000, threads=1)
 
 
@@ -50,6 +57,8 @@ JOBS = {
     "pressure_100_x4": lambda: pressure(100, 4),
     "pressure_100_x8": lambda: pressure(100, 8),
     "momentum_200_x1": lambda: momentum(200),
+    "pressure_200_x1_ic": lambda: pressure_ic(200),
+    "momentum_200_x1_ilu": lambda: momentum(200, "ILU"),
     "channel_128x64x64_x1": lambda: channel((128, 64, 64), (1, 1, 1)),
 }
 

@@ -10,6 +10,11 @@ SOLVER_ID = {"GKOCG": L.OGL_SOLVER_CG, "GKOBiCGStab": L.OGL_SOLVER_BICGSTAB,
              "GKOGMRES": L.OGL_SOLVER_GMRES}
 
 
+PRECOND_ID = {"none": L.OGL_PRECOND_NONE, "BJ": L.OGL_PRECOND_BJ, "ISAI": L.OGL_PRECOND_ISAI,
+              "GISAI": L.OGL_PRECOND_GISAI, "ILU": L.OGL_PRECOND_ILU, "IC": L.OGL_PRECOND_IC,
+              "IRILU": L.OGL_PRECOND_IRILU}
+
+
 def upload_system(ctx: Context, s, scaling=1.0, partition=True):
     ir, ic = host.collect_local_interface_indices(s)
     ctx.pattern_from_ldu(s.n, s.lower_addr, s.upper_addr, s.symmetric, ir, ic)
@@ -24,8 +29,7 @@ def upload_system(ctx: Context, s, scaling=1.0, partition=True):
 
 
 def gpu_solve(ctx: Context, solver, precond, mbs=1, **kw):
-    ctx.precond_setup({"none": L.OGL_PRECOND_NONE, "BJ": L.OGL_PRECOND_BJ, "ISAI": L.OGL_PRECOND_ISAI,
-                       "GISAI": L.OGL_PRECOND_GISAI}[precond], mbs)
+    ctx.precond_setup(PRECOND_ID[precond], mbs)
     max_iter = kw.pop("max_iter", 1000)
     if solver == "GKOBiCGStab":
         max_iter *= 2   # StoppingCriterion.H:188, done by the host layer

@@ -21,6 +21,9 @@ BASE = {"executor": "cuda", "relTol": 0.0, "adaptMinIter": False}
     (lambda: cases.channel((16, 8, 8), (1, 1, 1))[0], "GKOGMRES", "BJ", 1e-8),
     (lambda: cases.pressure_3d(16, sign=-1.0)[0], "GKOCG", {"preconditioner": "ISAI", "sparsityPower": 1}, 1e-9),
     (lambda: cases.momentum_3d(14)[0], "GKOBiCGStab", "GISAI", 1e-10),
+    (lambda: cases.pressure_3d(16, sign=-1.0)[0], "GKOCG", "IC", 1e-9),
+    (lambda: cases.momentum_3d(14)[0], "GKOBiCGStab", "ILU", 1e-10),
+    (lambda: cases.momentum_3d(14)[0], "GKOGMRES", "IRILU", 1e-10),
 ])
 def test_plugin_solve_matches_oracle(oracle, builder, solver, precond, tol):
     s = builder()

@@ -209,3 +209,88 @@ def test_isai_properties_and_effect(oracle):
         o_is = oracle.solve([a], solver, "ISAI" if spd else "GISAI", tolerance=1e-9)
         assert o_is.n_iterations < 0.8 * o_bj.n_iterations
         assert np.linalg.norm(o_is.x[0] - o_bj.x[0]) <= 1e-6 * np.linalg.norm(o_bj.x[0])
+
+
+def _csr_of(oracle, s):
+    import scipy.sparse as sp
+    a = oracle.assemble(s)
+    rp = np.zeros(s.n + 1, np.int32)
+    np.cumsum(np.bincount(a.rows, minlength=s.n), out=rp[1:])
+    return a, rp, sp.csr_matrix((a.vals, a.cols, rp), shape=(s.n, s.n))
+
+
+def test_ilu0_ic0_defining_properties(oracle):
+    """Incomplete factors (oracle/trifactor.hpp): (L U)|pattern = A for ILU(0), (L L^T)|pattern = A
+    for IC(0) -- the properties that define them uniquely -- and the exact triangular solves invert
+    L U / L L^T."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    for s, kind in ((cases.momentum_3d(7)[0], "ILU"), (cases.pressure_3d(8, sign=-1.0)[0], "IC"),
+                    (cases.pressure_3d(8, sign=-1.0)[0], "ILU")):
+        a, rp, A = _csr_of(oracle, s)
+        f = oracle.trifactor(kind, s.n, rp, a.cols, a.vals)
+        Fm = sp.csr_matrix((f, a.cols, rp), shape=(s.n, s.n))
+        pat = A.copy()
+        pat.data[:] = 1
+        if kind == "ILU":
+            Lf = sp.tril(Fm, k=-1) + sp.identity(s.n)
+            Uf = sp.triu(Fm)
+        else:
+            Lf = sp.tril(Fm)
+            Uf = sp.triu(Fm)
+            assert abs(Uf - Lf.T).max() == 0.0      # the upper part mirrors L
+        prod = (Lf @ Uf).multiply(pat)
+        assert abs(prod - A).max() < 1e-12 * abs(A).max()
+        r = np.random.default_rng(3).standard_normal(s.n)
+        z = oracle.trifactor_apply(kind, s.n, rp, a.cols, f, r)
+        assert np.linalg.norm((Lf @ Uf) @ z - r) < 1e-10 * np.linalg.norm(r)
+
+
+def test_irilu_apply_is_truncated_neumann(oracle):
+    """IRILU: 5 Jacobi-Richardson sweeps per factor from the right-hand side as initial guess, checked
+    against the same iteration written with scipy matrices."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    s = cases.momentum_3d(6)[0]
+    a, rp, A = _csr_of(oracle, s)
+    f = oracle.trifactor("IRILU", s.n, rp, a.cols, a.vals)
+    assert np.array_equal(f, oracle.trifactor("ILU", s.n, rp, a.cols, a.vals))
+    Fm = sp.csr_matrix((f, a.cols, rp), shape=(s.n, s.n))
+    Lf = (sp.tril(Fm, k=-1) + sp.identity(s.n)).tocsr()
+    Uf = sp.triu(Fm).tocsr()
+    r = np.random.default_rng(4).standard_normal(s.n)
+    t = r.copy()
+    for _ in range(5):
+        t = t + (r - Lf @ t)
+    z = t.copy()
+    for _ in range(5):
+        z = z + (t - Uf @ z) / Uf.diagonal()
+    zo = oracle.trifactor_apply("IRILU", s.n, rp, a.cols, f, r)
+    assert np.linalg.norm(zo - z) < 1e-13 * np.linalg.norm(z)
+
+
+@pytest.mark.parametrize("solver,precond,case", [
+    ("GKOCG", "IC", "pressure"), ("GKOCG", "ILU", "pressure"), ("GKOBiCGStab", "ILU", "momentum"),
+    ("GKOGMRES", "ILU", "momentum"), ("GKOBiCGStab", "IRILU", "momentum"), ("GKOGMRES", "IRILU", "momentum")])
+def test_factorisation_preconditioners_cut_iterations(oracle, solver, precond, case):
+    from ogl_b200 import cases
+    systems = cases.pressure_3d(12, sign=-1.0) if case == "pressure" else cases.momentum_3d(10)
+    A, b = cases.assemble_global_csr(systems)
+    a = oracle.assemble(systems[0])
+    o_bj = oracle.solve([a], solver, "BJ", tolerance=1e-9, krylov_dim=30)
+    o = oracle.solve([a], solver, precond, tolerance=1e-9, krylov_dim=30)
+    assert o.n_iterations < o_bj.n_iterations
+    x_direct = spl.spsolve(A.tocsc(), b)
+    assert np.linalg.norm(o.x[0] - x_direct) / np.linalg.norm(x_direct) < 1e-6
+
+
+def test_factorisation_is_local_under_schwarz(oracle):
+    """wrap_schwarz (Preconditioner.H:66-82): each rank factorises its own diagonal block only."""
+    from ogl_b200 import cases
+    many = cases.pressure_3d(10, (2, 1, 1), sign=-1.0)
+    one = cases.pressure_3d(10, sign=-1.0)
+    r1 = oracle.solve([oracle.assemble(one[0])], "GKOCG", "IC", tolerance=1e-9)
+    rn = oracle.solve([oracle.assemble(s) for s in many], "GKOCG", "IC", tolerance=1e-9)
+    xg = gather_global(many, rn.x)
+    assert np.linalg.norm(xg - r1.x[0]) / np.linalg.norm(r1.x[0]) < 1e-6
+    assert rn.n_iterations >= r1.n_iterations      # block-local factors are the weaker preconditioner
