@@ -166,12 +166,24 @@ int ogl_vector_fill(ogl_ctx *ctx, int which, double value);
  * dependency graph of the pattern, analysed once per mesh on the device.  ILUT / ICT (ParILUT / ParICT,
  * threshold-based and non-deterministic in the reference) are not built. */
 enum { OGL_PRECOND_NONE = 0, OGL_PRECOND_BJ = 1, OGL_PRECOND_ISAI = 2, OGL_PRECOND_GISAI = 3,
-       OGL_PRECOND_ILU = 4, OGL_PRECOND_IC = 5, OGL_PRECOND_IRILU = 6 };
+       OGL_PRECOND_ILU = 4, OGL_PRECOND_IC = 5, OGL_PRECOND_IRILU = 6,
+       /* Multigrid (Preconditioner/Preconditioner.H:261-341): Ginkgo multigrid::Pgm (deterministic)
+        * aggregation, one V cycle per apply, Ir(2 sweeps, 0.9, scalar Jacobi) as pre- and
+        * post-smoother, `coarseSolverIters` CG iterations on the coarsest level; options
+        * "mg_max_levels" (maxLevels, 9), "mg_min_coarse_rows" (minCoarseRows, 10),
+        * "mg_coarse_iters" (coarseSolverIters, 4), set before ogl_precond_setup; cycle v only */
+       OGL_PRECOND_MULTIGRID = 7 };
 int ogl_precond_setup(ogl_ctx *ctx, int kind, int32_t max_block_size,
                       int skip_sorting);
 /* parity hook: the incomplete factors over the local CSR pattern ([nnz]; strictly lower part = L,
  * upper part incl. the diagonal = U; IC: lower part incl. the diagonal = L, upper part = L^T) */
 int ogl_precond_factors_download(ogl_ctx *ctx, double *factors);
+/* parity hooks for Multigrid: number of levels (the last one is the coarsest matrix), a level's
+ * sizes (n_coarse = 0 on the coarsest level) and its CSR matrix / aggregate of every row */
+int ogl_mg_levels(ogl_ctx *ctx, int32_t *n_levels);
+int ogl_mg_level_info(ogl_ctx *ctx, int32_t level, int32_t *n, int32_t *nnz, int32_t *n_coarse);
+int ogl_mg_level_download(ogl_ctx *ctx, int32_t level, int32_t *row_ptrs, int32_t *cols, double *vals,
+                          int32_t *agg);
 /* z = M^-1 r through the current preconditioner on host vectors of the local size (parity hook for
  * the triangular sweeps; any preconditioner kind) */
 int ogl_precond_apply(ogl_ctx *ctx, const double *r_host, double *z_host);

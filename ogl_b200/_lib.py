@@ -16,7 +16,7 @@ OGL_OK, OGL_ERR_INVALID, OGL_ERR_CUDA, OGL_ERR_NCCL, OGL_ERR_UNSUPPORTED = range
 OGL_NCCL_ID_BYTES = 128
 OGL_VEC_B, OGL_VEC_X = 0, 1
 OGL_PRECOND_NONE, OGL_PRECOND_BJ, OGL_PRECOND_ISAI, OGL_PRECOND_GISAI = 0, 1, 2, 3
-OGL_PRECOND_ILU, OGL_PRECOND_IC, OGL_PRECOND_IRILU = 4, 5, 6
+OGL_PRECOND_ILU, OGL_PRECOND_IC, OGL_PRECOND_IRILU, OGL_PRECOND_MULTIGRID = 4, 5, 6, 7
 OGL_SOLVER_CG, OGL_SOLVER_BICGSTAB, OGL_SOLVER_GMRES = 0, 1, 2
 
 i32p = C.POINTER(C.c_int32)
@@ -70,6 +70,9 @@ SYMBOLS = {
     "ogl_precond_download": (C.c_int, [ctx_p, i32p, C.c_void_p, C.c_void_p]),
     "ogl_precond_factors_download": (C.c_int, [ctx_p, C.c_void_p]),
     "ogl_precond_apply": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p]),
+    "ogl_mg_levels": (C.c_int, [ctx_p, i32p]),
+    "ogl_mg_level_info": (C.c_int, [ctx_p, C.c_int32, i32p, i32p, i32p]),
+    "ogl_mg_level_download": (C.c_int, [ctx_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ogl_solve": (C.c_int, [ctx_p, C.POINTER(SolveParams), C.POINTER(SolveResult)]),
     "ogl_residual_history": (C.c_int, [ctx_p, C.c_void_p, C.c_int32, i32p]),
     "ogl_spmv": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p]),

@@ -187,6 +187,23 @@ class Context:
         self._check(self.lib.ogl_precond_factors_download(self.h, _ptr(out)))
         return out
 
+    def mg_levels(self):
+        """The Multigrid hierarchy, level by level (parity hook): dicts with n, nnz, n_coarse, row_ptrs,
+        cols, vals, agg (None on the coarsest level)."""
+        nl = C.c_int32(0)
+        self._check(self.lib.ogl_mg_levels(self.h, C.byref(nl)))
+        out = []
+        for l in range(nl.value):
+            n, nnz, nc = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+            self._check(self.lib.ogl_mg_level_info(self.h, l, C.byref(n), C.byref(nnz), C.byref(nc)))
+            rp, cols = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32)
+            vals = np.empty(nnz.value)
+            agg = np.empty(n.value, np.int32) if nc.value > 0 else None
+            self._check(self.lib.ogl_mg_level_download(self.h, l, _ptr(rp), _ptr(cols), _ptr(vals),
+                                                       _ptr(agg) if agg is not None else None))
+            out.append(dict(n=n.value, nnz=nnz.value, n_coarse=nc.value, row_ptrs=rp, cols=cols, vals=vals, agg=agg))
+        return out
+
     def precond_apply(self, r):
         """z = M^-1 r on host vectors of the local size (parity hook)."""
         r = np.ascontiguousarray(r, np.float64)

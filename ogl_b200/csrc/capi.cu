@@ -143,6 +143,7 @@ static void destroy(Context *c)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tri_release(c);
+    mg_release(c);
     for (double *w : c->work)
         if (w) cudaFree(w);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -358,6 +359,15 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     } else if (k == "tri_variant") {
         if (value < 0 || value > 1) return fail(ctx, OGL_ERR_INVALID, "tri_variant in {0,1}");
         ctx->tri_variant = value;
+    } else if (k == "mg_max_levels") {
+        if (value < 1 || value > 64) return fail(ctx, OGL_ERR_INVALID, "mg_max_levels in [1,64]");
+        ctx->mg_max_levels = value;
+    } else if (k == "mg_min_coarse_rows") {
+        if (value < 1) return fail(ctx, OGL_ERR_INVALID, "mg_min_coarse_rows >= 1");
+        ctx->mg_min_coarse_rows = value;
+    } else if (k == "mg_coarse_iters") {
+        if (value < 1 || value > 10000) return fail(ctx, OGL_ERR_INVALID, "mg_coarse_iters in [1,10000]");
+        ctx->mg_coarse_iters = value;
     } else if (k == "tri_sleep_ns") {
         if (value < 0 || value > 100000) return fail(ctx, OGL_ERR_INVALID, "tri_sleep_ns in [0,100000]");
         ctx->tri_sleep_ns = value;
@@ -443,6 +453,9 @@ int ogl_get_option(ogl_ctx *ctx, const char *key, int64_t *value)
     else if (k == "gmres_persist") *value = ctx->gmres_persist;
     else if (k == "tri_variant") *value = ctx->tri_variant;
     else if (k == "tri_sleep_ns") *value = ctx->tri_sleep_ns;
+    else if (k == "mg_max_levels") *value = ctx->mg_max_levels;
+    else if (k == "mg_min_coarse_rows") *value = ctx->mg_min_coarse_rows;
+    else if (k == "mg_coarse_iters") *value = ctx->mg_coarse_iters;
     else if (k == "tri_ctas") *value = ctx->tri_ctas;
     else if (k == "tri_levels_lower") *value = ctx->tri.structure_ready ? (int64_t)ctx->tri.lvl_l.size() - 1 : 0;
     else if (k == "tri_levels_upper") *value = ctx->tri.structure_ready ? (int64_t)ctx->tri.lvl_u.size() - 1 : 0;
@@ -637,6 +650,30 @@ int ogl_precond_factors_download(ogl_ctx *ctx, double *factors)
     return download(ctx, factors, ctx->tri.vals, sizeof(double) * ctx->nnz);
 }
 
+int ogl_mg_levels(ogl_ctx *ctx, int32_t *n_levels)
+{
+    CHECK_CTX(ctx);
+    if (!n_levels) return fail(ctx, OGL_ERR_INVALID, "null argument");
+    if (!ctx->have_precond || ctx->precond_kind != OGL_PRECOND_MULTIGRID || !ctx->mg.ready)
+        return fail(ctx, OGL_ERR_INVALID, "no Multigrid preconditioner");
+    *n_levels = (int32_t)ctx->mg.levels.size();
+    return OGL_OK;
+}
+
+int ogl_mg_level_info(ogl_ctx *ctx, int32_t level, int32_t *n, int32_t *nnz, int32_t *n_coarse)
+{
+    CHECK_CTX(ctx);
+    if (!n || !nnz || !n_coarse) return fail(ctx, OGL_ERR_INVALID, "null argument");
+    return mg_level_info(ctx, level, n, nnz, n_coarse);
+}
+
+int ogl_mg_level_download(ogl_ctx *ctx, int32_t level, int32_t *row_ptrs, int32_t *cols, double *vals,
+                          int32_t *agg)
+{
+    CHECK_CTX(ctx);
+    return mg_level_download(ctx, level, row_ptrs, cols, vals, agg);
+}
+
 int ogl_precond_apply(ogl_ctx *ctx, const double *r_host, double *z_host)
 {
     CHECK_CTX(ctx);
@@ -644,6 +681,7 @@ int ogl_precond_apply(ogl_ctx *ctx, const double *r_host, double *z_host)
     if (!ctx->have_pattern || !ctx->have_precond)
         return fail(ctx, OGL_ERR_INVALID, "ogl_precond_apply before ogl_precond_setup");
     if (is_tri_precond(ctx->precond_kind)) OGL_TRY(tri_ensure_structure(ctx));
+    if (ctx->precond_kind == OGL_PRECOND_MULTIGRID) OGL_TRY(mg_ensure(ctx));
     double *r, *z;
     OGL_TRY(get_work(ctx, 0, &r));
     OGL_TRY(get_work(ctx, 1, &z));

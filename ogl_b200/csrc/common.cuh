@@ -235,6 +235,26 @@ struct Context {
         int max_lower = 0, max_upper = 0;   // longest strictly lower / upper part of a row
         int sf_grid = 0, sf_per_sm = 1;     // co-resident grid of the dependency-driven sweeps
     } tri;
+    // Multigrid (multigrid.cu): the hierarchy of the local matrix.  Level 0 aliases the context's CSR
+    // (and uses the caller's vectors); every coarser level owns its matrix and vectors.
+    struct MgLevel {
+        label n = 0;
+        int64_t nnz = 0;
+        label *rp = nullptr, *cols = nullptr, *rows = nullptr;
+        double *vals = nullptr;
+        double *inv_diag = nullptr;
+        label *agg = nullptr;           // [n] fine row -> coarse row (nullptr on the coarsest level)
+        label n_coarse = 0;
+        label *r_ptr = nullptr, *r_idx = nullptr;   // restriction: members of every aggregate, ascending
+        double *b = nullptr, *x = nullptr, *r = nullptr;   // right-hand side, correction, residual / scratch
+        double *p = nullptr, *q = nullptr;                 // coarsest level: CG vectors
+    };
+    struct Multigrid {
+        std::vector<MgLevel> levels;
+        double *scal = nullptr, *partials = nullptr;   // coarsest CG: rho, prev_rho, beta; dot-product partials
+        bool ready = false;
+    } mg;
+    int64_t mg_max_levels = 9, mg_min_coarse_rows = 10, mg_coarse_iters = 4;   // Preconditioner.H:297,317-320
     int64_t tri_sleep_ns = 0;     // dependency-driven sweep: pause of a waiting warp between two rounds of polls
     int64_t tri_ctas = 0;         // ... and its CTAs per SM (0 = as many as fit)
     int64_t tri_variant = 1;   // triangular sweeps: 0 one launch per dependency level, 1 ONE launch per sweep whose
@@ -382,6 +402,13 @@ int tri_setup(Context *ctx, int kind);                 // (analysis once per pat
 int tri_ensure_structure(Context *ctx);                // re-analyse after a pattern rebuild (cached factors)
 int tri_apply(Context *ctx, const double *r, double *z, bool guard_done);
 void tri_release(Context *ctx);
+// multigrid.cu -------------------------------------------------------------------
+int mg_setup(Context *ctx);
+int mg_ensure(Context *ctx);
+int mg_apply(Context *ctx, const double *r, double *z, bool guard_done);
+void mg_release(Context *ctx);
+int mg_level_info(Context *ctx, int level, label *n, label *nnz, label *n_coarse);
+int mg_level_download(Context *ctx, int level, label *rp, label *cols, double *vals, label *agg);
 bool use_p2p(const Context *ctx);
 void comm_teardown(Context *ctx);
 int comm_bench(Context *ctx, int mode, int reps, double *us);

@@ -262,9 +262,17 @@ int precond_setup(Context *ctx, int kind, label mbs)
     if (!ctx->have_pattern || !ctx->have_values)
         return fail(ctx, OGL_ERR_INVALID, "ogl_precond_setup before the matrix is assembled");
     if (kind != OGL_PRECOND_NONE && kind != OGL_PRECOND_BJ && kind != OGL_PRECOND_ISAI && kind != OGL_PRECOND_GISAI &&
-        !is_tri_precond(kind))
+        !is_tri_precond(kind) && kind != OGL_PRECOND_MULTIGRID)
         return fail(ctx, OGL_ERR_UNSUPPORTED,
-                    "preconditioner not supported; valid choices: none, BJ, ISAI, GISAI, ILU, IC, IRILU");
+                    "preconditioner not supported; valid choices: none, BJ, ISAI, GISAI, ILU, IC, IRILU, Multigrid");
+    if (kind == OGL_PRECOND_MULTIGRID) {
+        OGL_TRY(mg_setup(ctx));
+        ctx->precond_kind = kind;
+        ctx->max_block_size = 1;
+        ctx->have_precond = true;
+        ctx->precond_setups++;
+        return OGL_OK;
+    }
     if (is_tri_precond(kind)) {
         if (kind == OGL_PRECOND_IC && !ctx->symmetric)
             return fail(ctx, OGL_ERR_INVALID, "IC needs a symmetric matrix; use ILU");
@@ -446,11 +454,12 @@ int precond_apply(Context *ctx, const double *r, double *z, const double *dot_wi
         }
         return spmv_local(ctx, s2);
     }
-    const bool tri = is_tri_precond(ctx->precond_kind);
+    const bool tri = is_tri_precond(ctx->precond_kind) || ctx->precond_kind == OGL_PRECOND_MULTIGRID;
     if (tri) {
-        // Schwarz: the LOCAL factors; two triangular sweeps (or 5 + 5 Richardson sweeps), then the
-        // reduction the caller asked for as one more pass over z
-        OGL_TRY(tri_apply(ctx, r, z, guard_done));
+        // Schwarz: the LOCAL factors / hierarchy; two triangular sweeps (or 5 + 5 Richardson sweeps) or
+        // one V cycle, then the reduction the caller asked for as one more pass over z
+        if (ctx->precond_kind == OGL_PRECOND_MULTIGRID) OGL_TRY(mg_apply(ctx, r, z, guard_done));
+        else OGL_TRY(tri_apply(ctx, r, z, guard_done));
         if (!dot_with) return OGL_OK;
     }
     ApplyK a;

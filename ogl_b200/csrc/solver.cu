@@ -619,7 +619,7 @@ static int pk_of(const Context *ctx)
 {
     if (ctx->precond_kind == OGL_PRECOND_NONE) return 0;
     if (ctx->precond_kind == OGL_PRECOND_ISAI || ctx->precond_kind == OGL_PRECOND_GISAI ||
-        is_tri_precond(ctx->precond_kind))
+        is_tri_precond(ctx->precond_kind) || ctx->precond_kind == OGL_PRECOND_MULTIGRID)
         return 3;   // applied by its own launches (precond_apply)
     return ctx->max_block_size == 1 ? 1 : 2;
 }
@@ -1027,6 +1027,7 @@ int solve(Context *ctx, const ogl_solve_params *p, ogl_solve_result *res)
                     "peer-memory windows before ogl_solve (comm_mode 1 is not available)");
     if (p->frequency < 1) return fail(ctx, OGL_ERR_INVALID, "frequency must be >= 1");
     if (is_tri_precond(ctx->precond_kind)) OGL_TRY(tri_ensure_structure(ctx));   // + its work vectors, before any capture
+    if (ctx->precond_kind == OGL_PRECOND_MULTIGRID) OGL_TRY(mg_ensure(ctx));
     if (p->solver == OGL_SOLVER_GMRES) return solve_gmres(ctx, p, res);
     if (p->solver != OGL_SOLVER_CG && p->solver != OGL_SOLVER_BICGSTAB)
         return fail(ctx, OGL_ERR_UNSUPPORTED, "unknown solver kind");

@@ -26,10 +26,10 @@ from .parallel import Pstream
 
 
 # `preconditioner` keyword (Preconditioner.H:91-105 BJ, :106-124 ILU, :143-176 IRILU, :177-196 IC,
-# :225-242 ISAI, :243-260 GISAI); ILUT / ICT (ParILUT / ParICT) and Multigrid are rejected
+# :225-242 ISAI, :243-260 GISAI, :261-341 Multigrid); ILUT / ICT (ParILUT / ParICT) are rejected
 PRECOND_KINDS = {"none": L.OGL_PRECOND_NONE, "BJ": L.OGL_PRECOND_BJ, "ISAI": L.OGL_PRECOND_ISAI,
                  "GISAI": L.OGL_PRECOND_GISAI, "ILU": L.OGL_PRECOND_ILU, "IC": L.OGL_PRECOND_IC,
-                 "IRILU": L.OGL_PRECOND_IRILU}
+                 "IRILU": L.OGL_PRECOND_IRILU, "Multigrid": L.OGL_PRECOND_MULTIGRID}
 
 
 @dataclass
@@ -156,9 +156,16 @@ class GKOlduBaseSolver:
         self.precond_name = pre["preconditioner"] if isinstance(pre, dict) else str(pre)
         if self.precond_name not in PRECOND_KINDS:
             raise FatalError(f"OGL does not support the preconditioner: {self.precond_name}\n"
-                             "Valid Choices: none, BJ, ILU, IRILU, IC, ISAI, GISAI")
+                             "Valid Choices: none, BJ, ILU, IRILU, IC, ISAI, GISAI, Multigrid")
         if self.precond_name in ("ISAI", "GISAI") and int(self.precond_controls.get("sparsityPower", 1)) != 1:
             raise FatalError("ISAI / GISAI: only sparsityPower 1 is implemented")
+        if self.precond_name == "Multigrid":
+            # Preconditioner.H:297-320: cycle (v | w | f), maxLevels, minCoarseRows, coarseSolverIters
+            if str(self.precond_controls.get("cycle", "v")) != "v":
+                raise FatalError("Multigrid: only cycle v is implemented")
+            self.ctx.set_option("mg_max_levels", int(self.precond_controls.get("maxLevels", 9)))
+            self.ctx.set_option("mg_min_coarse_rows", int(self.precond_controls.get("minCoarseRows", 10)))
+            self.ctx.set_option("mg_coarse_iters", int(self.precond_controls.get("coarseSolverIters", 4)))
         self.host_matrix = HostMatrixWrapper(db, matrix, controls, field_name, self.ctx, self.pstream)
 
     # lduLduBase.H:189-308

@@ -22,6 +22,7 @@
 // run with OpenMP (the analogue of Ginkgo's omp executor; used only as the CPU
 // baseline in bench.py).
 #include "oracle.h"
+#include "multigrid.hpp"
 #include "trifactor.hpp"
 
 #include <chrono>
@@ -374,17 +375,36 @@ struct Jacobi {
     dvec isai_w, isai_wt;                        // ISAI / GISAI values over the pattern of A
     dvec fact;                                   // ILU / IC / IRILU: factors over the pattern of A (trifactor.hpp)
     std::vector<std::vector<orc_label>> dpos;    // ... and the position of every row's diagonal entry
+    std::vector<orc_mg::Hierarchy> mg;           // Multigrid: one hierarchy per rank (multigrid.hpp)
     dvec inv_diag;                               // mbs == 1
     std::vector<std::vector<orc_label>> bptr;    // mbs > 1
     std::vector<std::vector<orc_label>> boff;
     dvec inv_blocks;
 };
 
-Jacobi make_jacobi(const Sys &s, int kind, orc_label mbs)
+orc_mg::Csr local_csr(const Sys &s, int r)
+{
+    orc_mg::Csr A;
+    A.n = s.rk[r].n;
+    A.rp = s.row_ptrs[r];
+    A.cols.assign(s.rk[r].cols, s.rk[r].cols + s.rk[r].nnz);
+    A.vals.assign(s.rk[r].vals, s.rk[r].vals + s.rk[r].nnz);
+    return A;
+}
+
+Jacobi make_jacobi(const Sys &s, int kind, orc_label mbs, const orc_solve_params *prm = nullptr)
 {
     Jacobi J;
     J.kind = kind;
     J.mbs = mbs < 1 ? 1 : mbs;
+    if (kind == ORC_PRECOND_MULTIGRID) {
+        // Preconditioner.H:261-341 defaults: maxLevels 9, minCoarseRows 10, coarseSolverIters 4
+        const int max_levels = prm && prm->mg_max_levels > 0 ? prm->mg_max_levels : 9;
+        const orc_label min_rows = prm && prm->mg_min_coarse_rows > 0 ? prm->mg_min_coarse_rows : 10;
+        const int coarse_iters = prm && prm->mg_coarse_iters > 0 ? prm->mg_coarse_iters : 4;
+        for (int r = 0; r < s.R; ++r) J.mg.push_back(orc_mg::build(local_csr(s, r), max_levels, min_rows, coarse_iters));
+        return J;
+    }
     if (kind == ORC_PRECOND_ISAI || kind == ORC_PRECOND_GISAI) {
         J.isai_w.resize(s.R);
         J.isai_wt.resize(s.R);
@@ -472,6 +492,11 @@ void precond_apply(const Sys &s, const Jacobi &J, const dvec &r, dvec &z)
                 vec t(static_cast<size_t>(n));
                 apply(J.isai_w[q].data(), r[q].data(), t.data());
                 apply(J.isai_wt[q].data(), t.data(), z[q].data());
+            }
+        } else if (J.kind == ORC_PRECOND_MULTIGRID) {
+            if (n > 0) {
+                std::fill(z[q].begin(), z[q].end(), 0.0);
+                orc_mg::vcycle(J.mg[q], 0, r[q].data(), z[q].data());
             }
         } else if (J.kind == ORC_PRECOND_ILU || J.kind == ORC_PRECOND_IC || J.kind == ORC_PRECOND_IRILU) {
             const orc_label *rp = s.row_ptrs[q].data(), *cols = s.rk[q].cols, *dp = J.dpos[q].data();
@@ -820,7 +845,7 @@ int orc_solve(int n_ranks, const orc_rank_system *ranks,
         x[r].assign(ranks[r].x, ranks[r].x + ranks[r].n);
         b[r].assign(ranks[r].b, ranks[r].b + ranks[r].n);
     }
-    Jacobi J = make_jacobi(s, params->precond, params->max_block_size);
+    Jacobi J = make_jacobi(s, params->precond, params->max_block_size, params);
     if (J.kind < 0) return 5;  // ISAI: a row longer than the dense solver handles / no diagonal
     Criterion crit{s, *params, x, b, 0, 1.0, 0.0, 0.0, history, history_cap, 0};
     const auto t0 = std::chrono::steady_clock::now();
@@ -863,6 +888,52 @@ int orc_isai_generate(orc_label n, const orc_label *row_ptrs, const orc_label *c
                       int spd, orc_scalar *w, orc_scalar *wt)
 {
     return isai_generate(n, row_ptrs, cols, vals, spd != 0, w, wt) ? 0 : 1;
+}
+
+void *orc_mg_create(orc_label n, const orc_label *row_ptrs, const orc_label *cols, const orc_scalar *vals,
+                    int max_levels, orc_label min_coarse_rows, int coarse_iters)
+{
+    orc_mg::Csr A;
+    A.n = n;
+    A.rp.assign(row_ptrs, row_ptrs + n + 1);
+    A.cols.assign(cols, cols + row_ptrs[n]);
+    A.vals.assign(vals, vals + row_ptrs[n]);
+    return new orc_mg::Hierarchy(orc_mg::build(std::move(A), max_levels, min_coarse_rows, coarse_iters));
+}
+
+void orc_mg_destroy(void *h) { delete static_cast<orc_mg::Hierarchy *>(h); }
+
+int orc_mg_levels(const void *h) { return static_cast<int>(static_cast<const orc_mg::Hierarchy *>(h)->levels.size()); }
+
+int orc_mg_level_info(const void *h, int level, orc_label *n, orc_label *nnz, orc_label *n_coarse)
+{
+    const auto &H = *static_cast<const orc_mg::Hierarchy *>(h);
+    if (level < 0 || level >= static_cast<int>(H.levels.size())) return 1;
+    const auto &L = H.levels[level];
+    *n = L.A.n;
+    *nnz = static_cast<orc_label>(L.A.vals.size());
+    *n_coarse = L.agg.empty() ? 0 : L.n_coarse;
+    return 0;
+}
+
+int orc_mg_level_get(const void *h, int level, orc_label *row_ptrs, orc_label *cols, orc_scalar *vals,
+                     orc_label *agg)
+{
+    const auto &H = *static_cast<const orc_mg::Hierarchy *>(h);
+    if (level < 0 || level >= static_cast<int>(H.levels.size())) return 1;
+    const auto &L = H.levels[level];
+    std::copy(L.A.rp.begin(), L.A.rp.end(), row_ptrs);
+    std::copy(L.A.cols.begin(), L.A.cols.end(), cols);
+    std::copy(L.A.vals.begin(), L.A.vals.end(), vals);
+    if (agg) std::copy(L.agg.begin(), L.agg.end(), agg);
+    return 0;
+}
+
+void orc_mg_apply(const void *h, const orc_scalar *r, orc_scalar *z)
+{
+    const auto &H = *static_cast<const orc_mg::Hierarchy *>(h);
+    std::fill(z, z + H.levels[0].A.n, 0.0);
+    orc_mg::vcycle(H, 0, r, z);
 }
 
 int orc_trifactor(int kind, orc_label n, const orc_label *row_ptrs, const orc_label *cols,

@@ -139,7 +139,10 @@ enum { ORC_CG = 0, ORC_BICGSTAB = 1, ORC_GMRES = 2 };
 enum { ORC_PRECOND_NONE = 0, ORC_PRECOND_BJ = 1, ORC_PRECOND_ISAI = 2, ORC_PRECOND_GISAI = 3,
        /* exact ILU(0) / IC(0) with exact triangular solves (Preconditioner.H:106-124, 177-196) and
         * ILU(0) with 5 Jacobi-Richardson sweeps per factor (:143-176); trifactor.hpp */
-       ORC_PRECOND_ILU = 4, ORC_PRECOND_IC = 5, ORC_PRECOND_IRILU = 6 };
+       ORC_PRECOND_ILU = 4, ORC_PRECOND_IC = 5, ORC_PRECOND_IRILU = 6,
+       /* Multigrid: PGM aggregation, V cycle, Jacobi-Richardson smoother, CG coarsest solver
+        * (Preconditioner.H:261-341); multigrid.hpp */
+       ORC_PRECOND_MULTIGRID = 7 };
 
 typedef struct orc_solve_params {
     int solver;               /* ORC_CG ...                                  */
@@ -152,6 +155,9 @@ typedef struct orc_solve_params {
     orc_label frequency;      /* effective evaluation frequency              */
     orc_label krylov_dim;     /* GMRES restart length (Ginkgo default 100)   */
     orc_label threads;        /* 1 = reference executor order; >1 = OpenMP   */
+    orc_label mg_max_levels;      /* Multigrid maxLevels (<= 0: 9)           */
+    orc_label mg_min_coarse_rows; /* minCoarseRows (<= 0: 10)                */
+    orc_label mg_coarse_iters;    /* coarseSolverIters (<= 0: 4)             */
 } orc_solve_params;
 
 typedef struct orc_solve_result {
@@ -189,6 +195,17 @@ void orc_bj_invert_blocks(orc_label n, const orc_label *row_ptrs,
                           const orc_label *cols, const orc_scalar *vals,
                           orc_label n_blocks, const orc_label *block_ptrs,
                           orc_scalar *inv /* sum b^2 */);
+/* Multigrid hierarchy of one (local) matrix, exposed level by level for parity tests: level l holds
+ * its matrix (CSR) and, unless it is the coarsest, the aggregate of every row (fine -> coarse) */
+void *orc_mg_create(orc_label n, const orc_label *row_ptrs, const orc_label *cols, const orc_scalar *vals,
+                    int max_levels, orc_label min_coarse_rows, int coarse_iters);
+void orc_mg_destroy(void *h);
+int orc_mg_levels(const void *h);
+int orc_mg_level_info(const void *h, int level, orc_label *n, orc_label *nnz, orc_label *n_coarse);
+int orc_mg_level_get(const void *h, int level, orc_label *row_ptrs, orc_label *cols, orc_scalar *vals,
+                     orc_label *agg /* NULL on the coarsest level */);
+void orc_mg_apply(const void *h, const orc_scalar *r, orc_scalar *z);   /* one V cycle from a zero guess */
+
 /* ILU(0) / IC(0) factors over the CSR pattern of A (strictly lower part = L, upper part = U incl.
  * the diagonal; IC: lower part incl. the diagonal = L, upper part = its transpose); 0 on success,
  * 1 row without diagonal or with a repeated column, 2 IC on a structurally unsymmetric pattern */

@@ -65,7 +65,8 @@ class SolveParams(C.Structure):
     _fields_ = [("solver", C.c_int), ("precond", C.c_int), ("max_block_size", C.c_int32),
                 ("tolerance", C.c_double), ("rel_tol", C.c_double), ("min_iter", C.c_int32),
                 ("max_iter", C.c_int32), ("frequency", C.c_int32), ("krylov_dim", C.c_int32),
-                ("threads", C.c_int32)]
+                ("threads", C.c_int32), ("mg_max_levels", C.c_int32), ("mg_min_coarse_rows", C.c_int32),
+                ("mg_coarse_iters", C.c_int32)]
 
 
 class SolveResult(C.Structure):
@@ -75,7 +76,7 @@ class SolveResult(C.Structure):
 
 
 SOLVERS = {"GKOCG": 0, "GKOBiCGStab": 1, "GKOGMRES": 2}
-PRECONDS = {"none": 0, "BJ": 1, "ISAI": 2, "GISAI": 3, "ILU": 4, "IC": 5, "IRILU": 6}
+PRECONDS = {"none": 0, "BJ": 1, "ISAI": 2, "GISAI": 3, "ILU": 4, "IC": 5, "IRILU": 6, "Multigrid": 7}
 
 
 def lib():
@@ -276,12 +277,13 @@ def _rank_structs(asms: Sequence[Assembled], keep):
 
 def solve(asms: Sequence[Assembled], solver="GKOCG", preconditioner="BJ", max_block_size=1,
           tolerance=1e-6, rel_tol=0.0, min_iter=0, max_iter=1000, frequency=1, krylov_dim=100,
-          threads=1) -> OracleSolve:
+          threads=1, mg_max_levels=9, mg_min_coarse_rows=10, mg_coarse_iters=4) -> OracleSolve:
     keep: list = []
     arr = _rank_structs(asms, keep)
     mi = max_iter * 2 if solver == "GKOBiCGStab" else max_iter   # StoppingCriterion.H:188
     p = SolveParams(SOLVERS[solver], PRECONDS[preconditioner], max_block_size, tolerance, rel_tol,
-                    min_iter, mi, frequency, krylov_dim, threads)
+                    min_iter, mi, frequency, krylov_dim, threads, mg_max_levels, mg_min_coarse_rows,
+                    mg_coarse_iters)
     res = SolveResult()
     cap = mi + 8
     hist = np.zeros(cap)
@@ -355,6 +357,42 @@ def isai_values(n, row_ptrs, cols, vals, spd: bool):
     if rc != 0:
         raise RuntimeError("ISAI: row too long for the dense solver or missing diagonal")
     return w, wt
+
+
+class MgHierarchy:
+    """The oracle's Multigrid hierarchy of one (local) CSR matrix (multigrid.hpp), level by level."""
+
+    def __init__(self, n, row_ptrs, cols, vals, max_levels=9, min_coarse_rows=10, coarse_iters=4):
+        L = lib()
+        L.orc_mg_create.restype = C.c_void_p
+        rp, c, v = _i32(row_ptrs), _i32(cols), _f64(vals)
+        self.h = C.c_void_p(L.orc_mg_create(C.c_int32(n), _ip(rp), _ip(c), _fp(v), C.c_int(max_levels),
+                                            C.c_int32(min_coarse_rows), C.c_int(coarse_iters)))
+        self.n = n
+        self.levels = []
+        for l in range(L.orc_mg_levels(self.h)):
+            ln, lnnz, lnc = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+            L.orc_mg_level_info(self.h, C.c_int(l), C.byref(ln), C.byref(lnnz), C.byref(lnc))
+            lrp, lc = np.zeros(ln.value + 1, np.int32), np.zeros(lnnz.value, np.int32)
+            lv = np.zeros(lnnz.value)
+            agg = np.zeros(ln.value, np.int32) if lnc.value > 0 else None
+            L.orc_mg_level_get(self.h, C.c_int(l), _ip(lrp), _ip(lc), _fp(lv), _ip(agg) if agg is not None else None)
+            self.levels.append(dict(n=ln.value, nnz=lnnz.value, n_coarse=lnc.value, row_ptrs=lrp, cols=lc,
+                                    vals=lv, agg=agg))
+
+    def apply(self, r):
+        r = _f64(r)
+        z = np.zeros(self.n)
+        lib().orc_mg_apply(self.h, _fp(r), _fp(z))
+        return z
+
+    def close(self):
+        if self.h:
+            lib().orc_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 def trifactor(kind, n, row_ptrs, cols, vals):

@@ -24,6 +24,7 @@ CASES = {
     # ... and incomplete factorisations of the local blocks (exact triangular sweeps)
     "pressure_cg_ic": (lambda p: cases.pressure_3d(12, p, sign=-1.0), "GKOCG", "IC", 1, 1e-9),
     "momentum_bicgstab_ilu": (lambda p: cases.momentum_3d(10, p), "GKOBiCGStab", "ILU", 1, 1e-10),
+    "pressure_cg_multigrid": (lambda p: cases.pressure_3d(12, p, sign=-1.0), "GKOCG", "Multigrid", 1, 1e-9),
     "channel_gmres": (lambda p: cases.channel((16, 8, 8), p), "GKOGMRES", "BJ", 1, 1e-8),
     # all-Neumann + one reference cell: nearly singular, so solve tighter than the L2 bar
     # 2-D case: fold the z split into x ([2,2,2] -> [4,2,1] like test/integration.yaml:53-55)

@@ -12,7 +12,7 @@ SOLVER_ID = {"GKOCG": L.OGL_SOLVER_CG, "GKOBiCGStab": L.OGL_SOLVER_BICGSTAB,
 
 PRECOND_ID = {"none": L.OGL_PRECOND_NONE, "BJ": L.OGL_PRECOND_BJ, "ISAI": L.OGL_PRECOND_ISAI,
               "GISAI": L.OGL_PRECOND_GISAI, "ILU": L.OGL_PRECOND_ILU, "IC": L.OGL_PRECOND_IC,
-              "IRILU": L.OGL_PRECOND_IRILU}
+              "IRILU": L.OGL_PRECOND_IRILU, "Multigrid": L.OGL_PRECOND_MULTIGRID}
 
 
 def upload_system(ctx: Context, s, scaling=1.0, partition=True):

@@ -24,6 +24,7 @@ BASE = {"executor": "cuda", "relTol": 0.0, "adaptMinIter": False}
     (lambda: cases.pressure_3d(16, sign=-1.0)[0], "GKOCG", "IC", 1e-9),
     (lambda: cases.momentum_3d(14)[0], "GKOBiCGStab", "ILU", 1e-10),
     (lambda: cases.momentum_3d(14)[0], "GKOGMRES", "IRILU", 1e-10),
+    (lambda: cases.momentum_3d(14)[0], "GKOBiCGStab", "Multigrid", 1e-10),
 ])
 def test_plugin_solve_matches_oracle(oracle, builder, solver, precond, tol):
     s = builder()

@@ -540,7 +540,7 @@ def test_cg_gisai_on_symmetric_matrix_and_plugin_keyword(oracle):
         lduMatrix_solver_New("p", s, dict(controls, preconditioner={"preconditioner": "ISAI", "sparsityPower": 2}),
                              ObjectRegistry())
     with pytest.raises(FatalError):
-        lduMatrix_solver_New("p", s, dict(controls, preconditioner="Multigrid"), ObjectRegistry())
+        lduMatrix_solver_New("p", s, dict(controls, preconditioner="ILUT"), ObjectRegistry())
 
 
 @pytest.mark.parametrize("n,extra,force_ell", [(30000, 60000, False), (300000, 400000, False), (30000, 4000, True)])

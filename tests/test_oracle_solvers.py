@@ -294,3 +294,62 @@ def test_factorisation_is_local_under_schwarz(oracle):
     xg = gather_global(many, rn.x)
     assert np.linalg.norm(xg - r1.x[0]) / np.linalg.norm(r1.x[0]) < 1e-6
     assert rn.n_iterations >= r1.n_iterations      # block-local factors are the weaker preconditioner
+
+
+def test_multigrid_hierarchy_properties(oracle):
+    """Multigrid restatement (oracle/multigrid.hpp): every level is the Galerkin product P^T A P of the
+    one above with the piecewise-constant prolongation of its aggregates; aggregates are matched pairs
+    plus leftovers joined to a neighbouring aggregate; coarsening stops at minCoarseRows / maxLevels."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    for s in (cases.momentum_3d(10)[0], cases.pressure_3d(12, sign=-1.0)[0]):
+        a, rp, A = _csr_of(oracle, s)
+        H = oracle.MgHierarchy(s.n, rp, a.cols, a.vals)
+        assert 2 <= len(H.levels) <= 10 and H.levels[0]["n"] == s.n
+        assert np.array_equal(H.levels[0]["vals"], a.vals)
+        for fine, coarse in zip(H.levels[:-1], H.levels[1:]):
+            agg, nc = fine["agg"], fine["n_coarse"]
+            assert nc == coarse["n"] < fine["n"] and agg.min() == 0 and agg.max() == nc - 1
+            assert np.bincount(agg, minlength=nc).min() >= 1
+            Af = sp.csr_matrix((fine["vals"], fine["cols"], fine["row_ptrs"]), shape=(fine["n"],) * 2)
+            Ac = sp.csr_matrix((coarse["vals"], coarse["cols"], coarse["row_ptrs"]), shape=(nc, nc))
+            P = sp.csr_matrix((np.ones(fine["n"]), (np.arange(fine["n"]), agg)), shape=(fine["n"], nc))
+            assert abs(P.T @ Af @ P - Ac).max() <= 1e-13 * abs(Af).max()
+            # sorted, duplicate-free rows
+            for i in range(0, nc, max(nc // 50, 1)):
+                c = coarse["cols"][coarse["row_ptrs"][i]:coarse["row_ptrs"][i + 1]]
+                assert np.all(np.diff(c) > 0)
+        assert H.levels[-1]["agg"] is None
+        few = oracle.MgHierarchy(s.n, rp, a.cols, a.vals, max_levels=2)
+        assert len(few.levels) == 3
+        big = oracle.MgHierarchy(s.n, rp, a.cols, a.vals, min_coarse_rows=s.n // 3)
+        assert big.levels[-1]["n"] <= s.n // 3 < big.levels[-2]["n"]
+
+
+def test_multigrid_cycle_and_solves(oracle):
+    """One V cycle contracts the error; as a preconditioner it cuts the iteration counts of all three
+    solvers and the solutions agree with direct solves."""
+    from ogl_b200 import cases
+    s = cases.pressure_3d(12, sign=-1.0)[0]
+    a, rp, A = _csr_of(oracle, s)
+    H = oracle.MgHierarchy(s.n, rp, a.cols, a.vals)
+    x_true = np.random.default_rng(5).standard_normal(s.n)
+    b = A @ x_true
+    z = H.apply(b)
+    e0, e1 = np.sqrt(x_true @ (A @ x_true)), np.sqrt((x_true - z) @ (A @ (x_true - z)))
+    assert e1 < 0.9 * e0          # energy-norm contraction of the stationary iteration
+    for solver, system in (("GKOCG", cases.pressure_3d(12, sign=-1.0)), ("GKOBiCGStab", cases.momentum_3d(10)),
+                           ("GKOGMRES", cases.momentum_3d(10))):
+        Ag, bg = cases.assemble_global_csr(system)
+        asm = oracle.assemble(system[0])
+        o = oracle.solve([asm], solver, "Multigrid", tolerance=1e-9, krylov_dim=30)
+        oj = oracle.solve([asm], solver, "BJ", tolerance=1e-9, krylov_dim=30)
+        # (GMRES only looks at the residual when it restarts: its counts come in steps of the restart length)
+        assert o.n_iterations < (0.5 if solver != "GKOGMRES" else 0.7) * oj.n_iterations
+        xd = spl.spsolve(Ag.tocsc(), bg)
+        assert np.linalg.norm(o.x[0] - xd) / np.linalg.norm(xd) < 1e-6
+    # keyword values reach the hierarchy: a shallower one needs more iterations
+    asm = oracle.assemble(cases.pressure_3d(12, sign=-1.0)[0])
+    deep = oracle.solve([asm], "GKOCG", "Multigrid", tolerance=1e-9)
+    shallow = oracle.solve([asm], "GKOCG", "Multigrid", tolerance=1e-9, mg_max_levels=1)
+    assert shallow.n_iterations > deep.n_iterations

@@ -13,7 +13,10 @@ from ogl_b200.backend import Context
 
 CONFIGS = [("BJ", L.OGL_PRECOND_BJ, 1, 100, 0), ("IC", L.OGL_PRECOND_IC, 0, 100, 0)]
 CONFIGS += [("IC", L.OGL_PRECOND_IC, 1, sl, ct) for sl, ct in ((0, 0), (100, 0), (300, 0), (1000, 0), (0, 1), (100, 1), (300, 1))]
-CONFIGS += [("ILU", L.OGL_PRECOND_ILU, 1, 100, 0), ("IRILU", L.OGL_PRECOND_IRILU, 1, 100, 0)]
+CONFIGS += [("ILU", L.OGL_PRECOND_ILU, 1, 0, 0), ("IRILU", L.OGL_PRECOND_IRILU, 1, 0, 0),
+            ("Multigrid", L.OGL_PRECOND_MULTIGRID, 1, 0, 0)]
+if os.environ.get("TRI_PROBE_SHORT"):
+    CONFIGS = [c for c in CONFIGS if c[0] in ("BJ", "Multigrid") or (c[0] == "IC" and c[2:] == (1, 0, 0))]
 
 for cells in [int(v) for v in sys.argv[1:]] or [100, 200]:
     s = bench.build_rank_system(cells, 1, 0)
@@ -42,5 +45,7 @@ for cells in [int(v) for v in sys.argv[1:]] or [100, 200]:
                           "iters": best.n_iterations, "us_per_iter": round(best.solve_us / max(best.n_iterations, 1), 1),
                           "solve_ms": round(best.solve_us / 1e3, 2), "final": best.final_residual,
                           "setup_ms_first": round(setup_ms[0], 2), "setup_ms": round(setup_ms[1], 2),
-                          "levels": ctx.get_option("tri_levels_lower"), "launches": best.kernel_launches}), flush=True)
+                          "levels": ctx.get_option("tri_levels_lower"), "launches": best.kernel_launches,
+                          "mg_levels": [(l["n"], l["nnz"]) for l in ctx.mg_levels()] if name == "Multigrid" else None}),
+              flush=True)
     ctx.close()
