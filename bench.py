@@ -593,6 +593,11 @@ def run_gpu(args):
                 extra["configs1_pressure_100"] = extra_solve(
                     "100^3 pressure GKOCG+BJ (BASELINE configs[1]; working set ~ L2 size)",
                     cases.pressure_3d(100)[0], "GKOCG", "BJ", TOL, "pressure_100_x1", alg_bytes_pcg, peak)
+            # algebraic multigrid (PGM aggregation, V cycle) on the SPD twin of configs[1]: hierarchy built on the
+            # device inside the timed solve's setup, iteration count pinned by the oracle
+            extra["pressure_100_cg_multigrid"] = extra_solve(
+                "100^3 pressure GKOCG+Multigrid (maxLevels 9, V cycle), scaling -1", cases.pressure_3d(100)[0],
+                "GKOCG", "Multigrid", TOL, "pressure_100_x1_mg", None, peak, scaling=-1.0, reps=2)
             # block Jacobi on the benchmark system itself (apply fused into the x/r update)
             extra["pressure_cg_bj4"] = extra_solve(
                 f"{args.n}^3 pressure GKOCG+BJ(maxBlockSize 4): same system as the bench line", s, "GKOCG",

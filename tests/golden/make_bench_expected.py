@@ -35,6 +35,12 @@ def pressure_ic(n):
     return oracle.solve([a], "GKOCG", "IC", tolerance=bench.TOL, rel_tol=0.0, max_iter=bench.MAX_ITER, threads=1)
 
 
+def pressure_mg(n):
+    a = oracle.assemble(bench.build_rank_system(n, 1, 0))
+    a.vals, a.b = -a.vals, -a.b
+    return oracle.solve([a], "GKOCG", "Multigrid", tolerance=bench.TOL, rel_tol=0.0, max_iter=bench.MAX_ITER, threads=1)
+
+
 def momentum(n, precond="BJ"):
     s = cases.momentum_3d(n)[0]
     return oracle.solve([oracle.assemble(s)], "GKOBiCGStab", precond, tolerance=1e-5, rel_tol=0.0,
@@ -59,6 +65,7 @@ JOBS = {
     "momentum_200_x1": lambda: momentum(200),
     "pressure_200_x1_ic": lambda: pressure_ic(200),
     "momentum_200_x1_ilu": lambda: momentum(200, "ILU"),
+    "pressure_100_x1_mg": lambda: pressure_mg(100),
     "channel_128x64x64_x1": lambda: channel((128, 64, 64), (1, 1, 1)),
 }
 
