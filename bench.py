@@ -593,22 +593,11 @@ def run_gpu(args):
                 extra["configs1_pressure_100"] = extra_solve(
                     "100^3 pressure GKOCG+BJ (BASELINE configs[1]; working set ~ L2 size)",
                     cases.pressure_3d(100)[0], "GKOCG", "BJ", TOL, "pressure_100_x1", alg_bytes_pcg, peak)
-            # algebraic multigrid (PGM aggregation, V cycle) on the SPD twin of configs[1]: hierarchy built on the
-            # device inside the timed solve's setup, iteration count pinned by the oracle
-            extra["pressure_100_cg_multigrid"] = extra_solve(
-                "100^3 pressure GKOCG+Multigrid (maxLevels 9, V cycle), scaling -1", cases.pressure_3d(100)[0],
-                "GKOCG", "Multigrid", TOL, "pressure_100_x1_mg", None, peak, scaling=-1.0, reps=2)
             # block Jacobi on the benchmark system itself (apply fused into the x/r update)
             extra["pressure_cg_bj4"] = extra_solve(
                 f"{args.n}^3 pressure GKOCG+BJ(maxBlockSize 4): same system as the bench line", s, "GKOCG",
                 {"preconditioner": "BJ", "maxBlockSize": 4}, TOL, None, alg_bytes_pcg, peak)
             extra["pressure_cg_bj4"]["us_per_iteration_scalar_jacobi"] = 1e6 / it_per_s
-            # incomplete Cholesky (exact IC(0), exact triangular sweeps in dependency order) on the SPD twin
-            # of the same system: fewer iterations, each paying two sweeps of 3N-2 dependency levels
-            extra["pressure_cg_ic"] = extra_solve(
-                f"{args.n}^3 pressure GKOCG+IC, scaling -1: same system as the bench line", s, "GKOCG", "IC", TOL,
-                f"pressure_{args.n}_x1_ic", None, peak, scaling=-1.0, reps=2)
-            extra["pressure_cg_ic"]["solve_ms_scalar_jacobi"] = ms_res / args.steps
             mom = cases.momentum_3d(200)[0]
             extra["configs2_momentum_200_bicgstab"] = extra_solve(
                 "200^3 momentum GKOBiCGStab+BJ, tolerance 1e-5 (BASELINE configs[2])", mom, "GKOBiCGStab", "BJ",
@@ -620,9 +609,6 @@ def run_gpu(args):
                     "sample": f"{foam_done} PBiCGStab iterations (oracle/foam_pcg.cpp), {foam_sec:.1f} s"}
             except Exception as e:
                 extra["configs2_momentum_200_bicgstab"]["cpu_openfoam_native_pbicgstab"] = {"error": repr(e)[:200]}
-            extra["momentum_200_bicgstab_ilu"] = extra_solve(
-                "200^3 momentum GKOBiCGStab+ILU, tolerance 1e-5 (exact ILU(0), exact triangular sweeps)", mom,
-                "GKOBiCGStab", "ILU", 1e-5, "momentum_200_x1_ilu", None, peak, max_iter=1000, reps=2)
             del mom
             ch = cases.channel((128, 64, 64), (1, 1, 1))[0]
             rec = extra_solve("channel 128x64x64, cyclic in x and z, GKOGMRES(100)+BJ (BASELINE configs[3], "
@@ -637,6 +623,24 @@ def run_gpu(args):
             extra["configs3_channel_gmres"] = rec
         except Exception as e:
             extra["error"] = repr(e)[:400]
+        # the other preconditioner families, each guarded on its own: exact IC(0) / ILU(0) with
+        # dependency-ordered triangular sweeps (fewer iterations, each paying two sweeps of 3N-2 dependent levels)
+        # and algebraic multigrid (PGM aggregation, V cycle; hierarchy built on the device inside the setup)
+        def guarded(key, fn):
+            try:
+                extra[key] = fn()
+            except Exception as e:
+                extra[key] = {"error": repr(e)[:300]}
+        guarded("pressure_cg_ic", lambda: dict(extra_solve(
+            f"{args.n}^3 pressure GKOCG+IC, scaling -1: same system as the bench line", s, "GKOCG", "IC", TOL,
+            f"pressure_{args.n}_x1_ic", None, peak, scaling=-1.0, reps=2), solve_ms_scalar_jacobi=ms_res / args.steps))
+        guarded("momentum_200_bicgstab_ilu", lambda: extra_solve(
+            "200^3 momentum GKOBiCGStab+ILU, tolerance 1e-5 (exact ILU(0), exact triangular sweeps)",
+            cases.momentum_3d(200)[0], "GKOBiCGStab", "ILU", 1e-5, "momentum_200_x1_ilu", None, peak, max_iter=1000,
+            reps=2))
+        guarded("pressure_100_cg_multigrid", lambda: extra_solve(
+            "100^3 pressure GKOCG+Multigrid (maxLevels 9, V cycle), scaling -1", cases.pressure_3d(100)[0],
+            "GKOCG", "Multigrid", TOL, "pressure_100_x1_mg", None, peak, scaling=-1.0, reps=2))
 
     line = {
         "metric": "PCG iterations/sec", "value": it_per_s * n_gpus, "unit": "iter/s",

@@ -64,3 +64,24 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
                 assert "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_preconditioner_keywords_match_the_header_enum():
+    """The `preconditioner` keyword table of the Python host layer, the ctypes constants, the C++ host
+    layer and the oracle agree with include/ogl_b200.h (same names, same numbers)."""
+    from ogl_b200 import _lib
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    enum = dict((k, int(v)) for k, v in re.findall(r"OGL_PRECOND_([A-Z]+)\s*=\s*(\d+)", txt))
+    assert enum == {"NONE": 0, "BJ": 1, "ISAI": 2, "GISAI": 3, "ILU": 4, "IC": 5, "IRILU": 6, "MULTIGRID": 7}
+    for name, value in enum.items():
+        assert getattr(_lib, "OGL_PRECOND_" + name) == value
+    src = open(os.path.join(ROOT, "ogl_b200", "plugin.py")).read()
+    table = src[src.index("PRECOND_KINDS = {"):src.index("}", src.index("PRECOND_KINDS = {"))]
+    words = dict(re.findall(r'"(\w+)":\s*L\.OGL_PRECOND_(\w+)', table))
+    assert {w.upper(): k for w, k in words.items()} == {k: k for k in enum}
+    cpp = open(os.path.join(ROOT, "ogl_b200", "host_cpp", "Preconditioner.H")).read()
+    for word, kind in words.items():
+        assert re.search(r'name == "%s"\) kind = OGL_PRECOND_%s;' % (word, kind), cpp), word
+    import oracle
+    assert {k.upper(): v for k, v in oracle.PRECONDS.items()} == enum
