@@ -85,8 +85,8 @@ def test_unsupported_interfaces_and_preconditioners():
     s = cases.pressure_3d(6)[0]
     c = FoamCase(s)
     try:
-        with pytest.raises(FoamFatalError, match="does not support the preconditioner: ILU"):
-            c.solve("p", dict(BASE, solver="GKOCG", preconditioner="ILU"), s.psi, s.source)
+        with pytest.raises(FoamFatalError, match="does not support the preconditioner: ILUT"):
+            c.solve("p", dict(BASE, solver="GKOCG", preconditioner="ILUT"), s.psi, s.source)
     finally:
         c.close()
 

@@ -312,7 +312,7 @@ def test_plugin_surface_time_steps(oracle):
     with pytest.raises(FatalError):
         lduMatrix_solver_New("p", s, dict(controls, executor="omp"), ObjectRegistry())
     with pytest.raises(FatalError):
-        lduMatrix_solver_New("p", s, dict(controls, preconditioner="ILU"), ObjectRegistry())
+        lduMatrix_solver_New("p", s, dict(controls, preconditioner="ICT"), ObjectRegistry())
 
 
 def test_matrix_format_keyword(oracle):
