@@ -63,7 +63,7 @@ const char *ogl_last_error(const ogl_ctx *ctx);
 /* tuning knobs for experiments; unknown keys fail with OGL_ERR_INVALID, setting a key to its
  * current value keeps the cached iteration graph.  Kernel choice: "spmv_variant" (0 auto from the
  * row-length histogram, 1 stream, 2 thread/row, 3 warp/row, 4 TMA CSR, 5 warp tile, 6 pipelined
- * stream, 7 ELL), "ell_auto", "ell_coded" (pattern-coded ELL columns: 0 off, 1 auto, 2 force),
+ * stream, 7 ELL, 8 merge-path = entry-balanced slices for very uneven row lengths), "ell_auto", "ell_coded" (pattern-coded ELL columns: 0 off, 1 auto, 2 force),
  * "ell_tma" (TMA-fed coded ELL: 0 off, 1 on, 2 auto by size), "tma_stages", "ell_minb", "ell_chunk",
  * "fuse_p" (CG p-update inside the ELL SpMV), "fused_pcg" (persistent CG loop kernel: 0/1/2 auto),
  * "gmres_persist", "tri_variant" (ILU / IC sweeps: 0 one launch per dependency level, 1 one

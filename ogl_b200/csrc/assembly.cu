@@ -60,6 +60,17 @@ __global__ void k_count_rows(label n, label nf, const label *__restrict__ lower,
     }
 }
 
+// longest row (its entry count is known before the scatter): the per-row insertion sort below is
+// quadratic in the row length, so absurdly long rows are refused up front instead of stalling the device
+constexpr label kMaxRowEntries = 16384;
+__global__ void k_max_count(label n, const label *__restrict__ counts, label *mx)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int v = i < n ? counts[i] : 0;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(mx, (label)v);
+}
+
 __global__ void k_fill_ones(label n, label *a)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -326,12 +337,21 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     k_fill_ones<<<grid_for(n), kThreads, 0, st>>>(n, d_counts);
     k_count_rows<<<grid_for((int64_t)nf + n_if), kThreads, 0, st>>>(
         n, nf, d_lower, d_upper, n_if, d_ifr, d_ifc, d_counts, d_bad);
+    k_max_count<<<grid_for(n), kThreads, 0, st>>>(n, d_counts, d_max);
     {
         // stop before the scatter if the addressing is malformed (the counts
         // would not cover the entries the scatter writes)
         int bad0 = 0;
+        label longest = 0;
         cudaMemcpyAsync(&bad0, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&longest, d_max, sizeof(label), cudaMemcpyDeviceToHost, st);
         cudaError_t e0 = cudaStreamSynchronize(st);
+        if (e0 == cudaSuccess && bad0 == 0 && longest > kMaxRowEntries) {
+            cleanup();
+            return fail(ctx, OGL_ERR_UNSUPPORTED,
+                        "a matrix row with " + std::to_string(longest) + " entries: rows longer than " +
+                            std::to_string(kMaxRowEntries) + " are not supported by the device assembly");
+        }
         if (e0 != cudaSuccess || bad0 != 0) {
             cleanup();
             if (e0 != cudaSuccess)

@@ -139,7 +139,8 @@ static void destroy(Context *c)
                     c->d_g_vals,     c->d_trace,      c->d_push_dst,   c->d_bar,
                     c->ell.cols,     c->ell.vals,     c->ell.code,     c->ell.ptab,
                     c->gell.cols,    c->gell.vals,    c->gell.code,    c->gell.ptab,
-                    c->d_isai_w,     c->d_isai_wt};
+                    c->d_isai_w,     c->d_isai_wt,    c->d_mp_chunk_row, c->d_mp_carry_row,
+                    c->d_mp_carry_val};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     tri_release(c);
@@ -331,7 +332,7 @@ int ogl_set_option(ogl_ctx *ctx, const char *key, int64_t value)
     const bool known = ogl_get_option(ctx, key, &before) == OGL_OK;
     if (known && before == value && k != "trace") return OGL_OK;
     if (k == "spmv_variant") {
-        if (value < 0 || value > 7) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,7]");
+        if (value < 0 || value > 8) return fail(ctx, OGL_ERR_INVALID, "spmv_variant in [0,8]");
         ctx->spmv_variant = value;
     } else if (k == "chunk_iters") {
         if (value < 1) return fail(ctx, OGL_ERR_INVALID, "chunk_iters >= 1");

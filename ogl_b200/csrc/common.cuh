@@ -99,7 +99,8 @@ struct Context {
     std::string error;
 
     // options
-    int64_t spmv_variant = 0;    // 0 auto, 1 stream(LDG), 2 thread-per-row, 3 warp-per-row, 4 TMA pipeline
+    int64_t spmv_variant = 0;    // 0 auto, 1 stream(LDG), 2 thread-per-row, 3 warp-per-row, 4 TMA pipeline, 5 warp tile,
+                                 // 6 pipelined stream, 7 ELL, 8 merge-path (entry-balanced slices)
     int64_t chunk_iters = 16;    // iterations enqueued between two host polls
     int64_t use_graph = 1;       // replay a chunk as a CUDA graph
     int64_t profile_stride = 0;  // sample SpMV launch durations every k-th iteration
@@ -146,6 +147,10 @@ struct Context {
     int64_t fuse_p = 0;          // CG: p-update fused into the ELL SpMV (ell.cu:k_spmv_ell_cgp); measured slower than
                                  // the separate k_cg_p at 1 M and 8 M rows on 1 and 2 GPUs (profiles/r02_*probe*), so off
     int64_t ell_auto = 1;        // 1: spmv_variant 0 may pick the ELL kernels (spmv.cu:pick_variant)
+    // merge-path SpMV (spmv_merge.cu): first row starting at or behind every 2048-entry slice, carries
+    int mp_chunks = 0;
+    label *d_mp_chunk_row = nullptr, *d_mp_carry_row = nullptr;
+    double *d_mp_carry_val = nullptr;
     int64_t max_block_nnz = 0;   // stream kernel: max nnz of a kRowsPerBlock row block
     int64_t max_warp_nnz = 0;    // warp-tile kernel: max nnz of 32 consecutive rows
 
@@ -375,6 +380,7 @@ int spmv_nonlocal(Context *ctx, const double *recv, double *y, double alpha,
                   const double *dot_with, int nred, bool guard_done, int epi,
                   bool inline_epi);
 int spmv_setup(Context *ctx);
+int spmv_merge_setup(Context *ctx);   // spmv_merge.cu
 int spmv_ell_cgp(Context *ctx, const double *z, const double *p_old, double *p_new, double *q, bool ghost);
 void ell_invalidate(Context *ctx, bool structure);
 int ell_prepare_for_loop(Context *ctx, bool ghost);

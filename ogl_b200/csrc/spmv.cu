@@ -803,7 +803,7 @@ int spmv_setup(Context *ctx)
     if (ctx->blas1_blocks > max_grid) max_grid = ctx->blas1_blocks;
     OGL_TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)(max_grid + 1) * kMaxReduce));
     (void)spmv_l2_policy(ctx);   // create the policy words outside any graph capture
-    return OGL_OK;
+    return spmv_merge_setup(ctx);
 }
 
 // ---------------------------------------------------------------------------
@@ -861,7 +861,7 @@ unsigned long long spmv_l2_policy(Context *ctx)
 int spmv_variant_in_use(const Context *ctx);
 static int pick_variant(const Context *ctx)
 {
-    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 7) return (int)ctx->spmv_variant;
+    if (ctx->spmv_variant >= 1 && ctx->spmv_variant <= 8) return (int)ctx->spmv_variant;
     const size_t smem = (size_t)ctx->max_block_nnz * sizeof(double);
     const double mean_len = ctx->n > 0 ? (double)ctx->nnz / ctx->n : 0.0;
     // ell_auto (default off): short regular rows on one rank -> ELL.  The plain ELL SpMV is the
@@ -880,6 +880,9 @@ static int pick_variant(const Context *ctx)
     const double nnz = ctx->nnz > 0 ? (double)ctx->nnz : 1.0;
     const double share_long = (double)(ctx->row_len_hist[8 + 6] + ctx->row_len_hist[8 + 7]) / nnz;   // rows > 32
     const double share_huge = (double)ctx->row_len_hist[8 + 7] / nnz;                                 // rows > 64
+    // a few rows far longer than the rest (a cell coupled to thousands of others): every row-based kernel
+    // serialises on them -> entry-balanced slices (spmv_merge.cu)
+    if (ctx->max_row_len > 256 && (double)ctx->max_row_len > 16.0 * mean_len) return 8;
     if (share_long > 0.5) return 3;
     if (smem <= (size_t)kStreamSmemMax && share_huge < 0.05 && mean_len <= 48.0) return 6;   // pipelined stream
     return mean_len >= 16.0 ? 3 : 2;
@@ -920,6 +923,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     if (nred > 0 && !sa.dot_with) return fail(ctx, OGL_ERR_INVALID, "fused dot without vector");
     int variant = pick_variant(ctx);
     if (variant == 7 && sa.fused_halo) variant = 6;   // the flag-handshake kernel exists for CSR only
+    if (variant == 8 && (sa.fused_halo || sa.ghost_x)) variant = 6;   // merge-path: local matrix only
     if (sa.vals_override) {
         // another operator over the same local pattern (ISAI): CSR kernels, local block only
         if (sa.fused_halo || sa.ghost_x) return fail(ctx, OGL_ERR_INVALID, "vals_override is local-only");
@@ -927,6 +931,7 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
         if (variant == 7 || variant == 4) variant = 6;
         if (variant == 6 && (size_t)ctx->max_block_nnz * sizeof(double) > (size_t)kStreamSmemMax) variant = 2;
         k.ea = make_epi_args(ctx, sa.ar_count), k.ea.trace_tag = 20;
+        if (pick_variant(ctx) == 8) variant = 8;   // same pattern, same slices
     }
     // a rank without halo rows (n_halo == 0) runs the halo kernel on its local matrix
     const bool ghosted = (sa.fused_halo || sa.ghost_x) && ctx->have_ghosted;
@@ -1116,6 +1121,8 @@ int spmv_local(Context *ctx, const SpmvArgs &sa)
     } else if (variant == 7) {
         OGL_TRY(spmv_ell(ctx, k, sa, ghosted));
         return OGL_OK;
+    } else if (variant == 8) {
+        return spmv_merge(ctx, k, sa);
     } else if (variant == 2) {
         const int grid = (ctx->n + 255) / 256;
         DISPATCH(k_spmv_scalar, grid, 256, 0);

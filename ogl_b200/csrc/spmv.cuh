@@ -126,5 +126,7 @@ __device__ __forceinline__ void consumer_sync()
 
 // ell.cu: variant 7 launchers
 int spmv_ell(Context *ctx, SpmvK &k, const SpmvArgs &sa, bool ghosted);
+// spmv_merge.cu: variant 8
+int spmv_merge(Context *ctx, const SpmvK &k, const SpmvArgs &sa);
 
 }  // namespace ogl

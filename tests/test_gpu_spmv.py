@@ -38,8 +38,8 @@ def test_spmv_vs_oracle(ctx, oracle, builder, variant):
     ctx.set_option("spmv_variant", 0)
 
 
-def test_spmv_long_rows_fall_back_to_vector_kernel(ctx, oracle):
-    # an "arrow" matrix: row 0 couples to everything (row length n)
+def test_spmv_one_long_row_takes_the_merge_path_kernel(ctx, oracle):
+    # an "arrow" matrix: row 0 couples to everything (row length n) -> entry-balanced slices (variant 8)
     n = 3000
     lower = np.zeros(n - 1, np.int32)
     upper = np.arange(1, n, dtype=np.int32)
@@ -54,6 +54,7 @@ def test_spmv_long_rows_fall_back_to_vector_kernel(ctx, oracle):
     ref[1:] += up * x[0]
     assert np.allclose(y, ref, rtol=1e-12, atol=1e-12)
     assert ctx.get_option("max_row_len") == n
+    assert ctx.get_option("spmv_variant_in_use") == 8
 
 
 def test_spmv_properties_at_baseline_size(ctx):
