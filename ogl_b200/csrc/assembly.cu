@@ -60,9 +60,11 @@ __global__ void k_count_rows(label n, label nf, const label *__restrict__ lower,
     }
 }
 
-// longest row (its entry count is known before the scatter): the per-row insertion sort below is
-// quadratic in the row length, so absurdly long rows are refused up front instead of stalling the device
-constexpr label kMaxRowEntries = 16384;
+// longest row (its entry count is known before the scatter).  The per-row insertion sort below is
+// quadratic in the row length: rows beyond kLongRow entries (a cell coupled to thousands of others) are
+// left to a radix sort of their own (sort_long_rows)
+constexpr label kLongRow = 4096;
+constexpr int kMaxLongRows = 4096;
 __global__ void k_max_count(label n, const label *__restrict__ counts, label *mx)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -136,6 +138,55 @@ __global__ void k_sort_rows(label n, const label *__restrict__ row_ptrs, label *
     }
     for (label i = s; i < e; ++i) rows[i] = (label)r;
     atomicMax(max_len, e - s);
+}
+
+// k_sort_rows for a pattern with long rows: those are only recorded as (row, first, last) triples
+__global__ void k_sort_rows_capped(label n, const label *__restrict__ row_ptrs, label *rows, label *cols,
+                                   label *map, label *max_len, label *long_rows, int *n_long)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const label s = row_ptrs[r], e = row_ptrs[r + 1];
+    atomicMax(max_len, e - s);
+    if (e - s > kLongRow) {
+        const int k = atomicAdd(n_long, 1);
+        if (k < kMaxLongRows) {
+            long_rows[3 * k] = (label)r;
+            long_rows[3 * k + 1] = s;
+            long_rows[3 * k + 2] = e;
+        }
+        return;
+    }
+    for (label i = s + 1; i < e; ++i) {
+        const label c = cols[i], m = map[i];
+        label j = i - 1;
+        while (j >= s && (cols[j] > c || (cols[j] == c && map[j] > m))) {
+            cols[j + 1] = cols[j];
+            map[j + 1] = map[j];
+            --j;
+        }
+        cols[j + 1] = c;
+        map[j + 1] = m;
+    }
+    for (label i = s; i < e; ++i) rows[i] = (label)r;
+}
+
+// one long row: (col, slot) -> 64-bit keys whose ascending order is the insertion sort's order
+__global__ void k_pack_row_keys(label len, const label *__restrict__ cols, const label *__restrict__ map,
+                                unsigned long long *keys)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < len) keys[i] = ((unsigned long long)(unsigned int)cols[i] << 32) | (unsigned int)map[i];
+}
+
+__global__ void k_unpack_row_keys(label len, const unsigned long long *__restrict__ keys, label *cols, label *map,
+                                  label *rows, label row)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    cols[i] = (label)(keys[i] >> 32);
+    map[i] = (label)(keys[i] & 0xffffffffull);
+    rows[i] = row;
 }
 
 __global__ void k_iota(label n, label *a)
@@ -282,6 +333,57 @@ __global__ void k_gather_nonlocal(label n_halo, const label *__restrict__ map,
 
 }  // namespace
 
+// Rows of a pattern that has rows longer than kLongRow: the short ones by the per-thread insertion sort,
+// every long one by a CUB radix sort of its (col, slot) keys -- the same ascending (col, slot) order.
+static int sort_long_rows(Context *ctx, label n, label longest, label *d_max)
+{
+    cudaStream_t st = ctx->stream;
+    label *d_long = nullptr;
+    int *d_nlong = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys_s = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_long), cudaFree(d_nlong), cudaFree(d_keys), cudaFree(d_keys_s), cudaFree(d_tmp);
+    };
+    int rc = dev_alloc(ctx, &d_long, (size_t)3 * kMaxLongRows);
+    if (rc == OGL_OK) rc = dev_alloc(ctx, &d_nlong, 1);
+    if (rc == OGL_OK) rc = dev_alloc(ctx, &d_keys, (size_t)longest);
+    if (rc == OGL_OK) rc = dev_alloc(ctx, &d_keys_s, (size_t)longest);
+    if (rc != OGL_OK) {
+        cleanup();
+        return rc;
+    }
+    cudaMemsetAsync(d_nlong, 0, sizeof(int), st);
+    k_sort_rows_capped<<<grid_for(n), kThreads, 0, st>>>(n, ctx->d_row_ptrs, ctx->d_rows, ctx->d_cols, ctx->d_map,
+                                                          d_max, d_long, d_nlong);
+    int n_long = 0;
+    cudaMemcpyAsync(&n_long, d_nlong, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && n_long > kMaxLongRows) {
+        cleanup();
+        return fail(ctx, OGL_ERR_UNSUPPORTED, "more than " + std::to_string(kMaxLongRows) + " rows longer than " +
+                                                  std::to_string(kLongRow) + " entries");
+    }
+    std::vector<label> long_rows((size_t)3 * (n_long > 0 ? n_long : 1));
+    if (e == cudaSuccess && n_long > 0)
+        e = cudaMemcpy(long_rows.data(), d_long, sizeof(label) * 3 * (size_t)n_long, cudaMemcpyDeviceToHost);
+    size_t bytes = 0;
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_keys, d_keys_s, (int)longest, 0, 64, st);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tmp, bytes + 16);
+    for (int k = 0; e == cudaSuccess && k < n_long; ++k) {
+        const label r = long_rows[3 * k], s = long_rows[3 * k + 1], len = long_rows[3 * k + 2] - s;
+        k_pack_row_keys<<<grid_for(len), kThreads, 0, st>>>(len, ctx->d_cols + s, ctx->d_map + s, d_keys);
+        e = cub::DeviceRadixSort::SortKeys(d_tmp, bytes, d_keys, d_keys_s, (int)len, 0, 64, st);
+        k_unpack_row_keys<<<grid_for(len), kThreads, 0, st>>>(len, d_keys_s, ctx->d_cols + s, ctx->d_map + s,
+                                                              ctx->d_rows + s, r);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, OGL_ERR_CUDA, std::string("sort_long_rows: ") + cudaGetErrorString(e));
+    return OGL_OK;
+}
+
 int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *lower,
                      const label *upper, label n_if, const label *if_rows,
                      const label *if_cols)
@@ -298,6 +400,7 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     label *d_cursor = nullptr, *d_counts = nullptr, *d_max = nullptr;
     int *d_bad = nullptr;
     void *d_tmp = nullptr;
+    label longest_row = 0;
     auto cleanup = [&]() {
         cudaFree(d_lower), cudaFree(d_upper), cudaFree(d_ifr), cudaFree(d_ifc);
         cudaFree(d_cursor), cudaFree(d_counts), cudaFree(d_max), cudaFree(d_bad);
@@ -346,12 +449,7 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
         cudaMemcpyAsync(&bad0, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(&longest, d_max, sizeof(label), cudaMemcpyDeviceToHost, st);
         cudaError_t e0 = cudaStreamSynchronize(st);
-        if (e0 == cudaSuccess && bad0 == 0 && longest > kMaxRowEntries) {
-            cleanup();
-            return fail(ctx, OGL_ERR_UNSUPPORTED,
-                        "a matrix row with " + std::to_string(longest) + " entries: rows longer than " +
-                            std::to_string(kMaxRowEntries) + " are not supported by the device assembly");
-        }
+        longest_row = longest;
         if (e0 != cudaSuccess || bad0 != 0) {
             cleanup();
             if (e0 != cudaSuccess)
@@ -373,8 +471,16 @@ int pattern_from_ldu(Context *ctx, label n, label nf, bool sym, const label *low
     k_scatter<<<grid_for((int64_t)nf + n + n_if), kThreads, 0, st>>>(
         n, nf, sym ? 1 : 0, d_lower, d_upper, n_if, d_ifr, d_ifc, ctx->d_row_ptrs, d_cursor,
         ctx->d_cols, ctx->d_map);
-    k_sort_rows<<<grid_for(n), kThreads, 0, st>>>(n, ctx->d_row_ptrs, ctx->d_rows,
-                                                   ctx->d_cols, ctx->d_map, d_max);
+    if (longest_row <= kLongRow) {
+        k_sort_rows<<<grid_for(n), kThreads, 0, st>>>(n, ctx->d_row_ptrs, ctx->d_rows,
+                                                       ctx->d_cols, ctx->d_map, d_max);
+    } else {
+        const int rc_long = sort_long_rows(ctx, n, longest_row, d_max);
+        if (rc_long != OGL_OK) {
+            cleanup();
+            return rc_long;
+        }
+    }
     int bad = 0;
     label max_len = 0;
     cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
