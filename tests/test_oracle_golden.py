@@ -174,3 +174,20 @@ def test_comm_and_non_local_pattern(oracle):
             u = list(aq.target_ids).index(r)
             assert aq.target_sizes[u] == a.target_sizes[t]
             off += a.target_sizes[t]
+
+
+def test_preconditioner_restatements_reproduce_their_regression_fixtures(oracle):
+    """tests/golden/precond_oracle_vectors.npz (made by tests/golden/make_precond_golden.py) pins the
+    oracle's ILU / IC factors and applies, the IRILU apply and the multigrid aggregates / first coarse
+    matrix / V cycle on tiny systems against accidental change.  A regression fixture of the oracle itself:
+    these restatements have no reference vector to be pinned against (Ginkgo is absent)."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_precond_golden", os.path.join(path, "make_precond_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.build()
+    gold = np.load(os.path.join(path, "precond_oracle_vectors.npz"))
+    assert set(gold.files) == set(now)
+    for key in gold.files:
+        assert np.array_equal(gold[key], now[key]), key
