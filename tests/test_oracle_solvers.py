@@ -353,3 +353,64 @@ def test_multigrid_cycle_and_solves(oracle):
     deep = oracle.solve([asm], "GKOCG", "Multigrid", tolerance=1e-9)
     shallow = oracle.solve([asm], "GKOCG", "Multigrid", tolerance=1e-9, mg_max_levels=1)
     assert shallow.n_iterations > deep.n_iterations
+
+
+@pytest.mark.parametrize("precond", ["none", "BJ"])
+def test_cg_residual_history_matches_scipy_cg(oracle, precond):
+    """A third, library implementation of the same recurrence: scipy.sparse.linalg.cg (textbook PCG) driven
+    on the same matrix with the same Jacobi preconditioner.  Its iterates give the L1 residuals OGL's
+    criterion looks at; the oracle's residual history must follow them (1e-6 relative while the residual
+    is far above rounding) and stop at the same iteration."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    s = cases.pressure_3d(10, sign=-1.0)[0]
+    a, rp, A = _csr_of(oracle, s)
+    tol = 1e-8
+    o = oracle.solve([a], "GKOCG", precond, tolerance=tol)
+    M = sp.diags(1.0 / A.diagonal()) if precond == "BJ" else None
+    iterates = []
+    spl.cg(A, a.b, x0=np.zeros(s.n), rtol=1e-14, atol=0.0, maxiter=o.n_iterations + 5, M=M,
+           callback=lambda xk: iterates.append(xk.copy()))
+    res = np.array([np.abs(a.b - A @ xk).sum() / o.norm_factor for xk in iterates])
+    # oracle history[k] = residual at criterion call k; call 0 sees the initial residual, call k iterate k
+    hist = o.history
+    assert hist[0] == pytest.approx(np.abs(a.b).sum() / o.norm_factor, rel=1e-12)
+    m = min(len(hist) - 1, len(res))
+    big = res[:m] > 1e-7
+    assert np.allclose(hist[1:m + 1][big], res[:m][big], rtol=1e-6)
+    first = int(np.argmax(res < tol)) + 1           # iterate k is checked by criterion call k
+    assert abs(o.criterion_calls - 1 - first) <= 1
+
+
+def test_bicgstab_residual_history_matches_scipy_bicgstab(oracle):
+    """Same cross-check for BiCGStab on a momentum matrix: scipy's (right-preconditioned van der Vorst)
+    iterates against the residuals the oracle reports after every full iteration (every second criterion
+    call: the one in between looks at the intermediate residual s)."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    s = cases.momentum_3d(9)[0]
+    a, rp, A = _csr_of(oracle, s)
+    tol = 1e-9
+    o = oracle.solve([a], "GKOBiCGStab", "BJ", tolerance=tol)
+    M = sp.diags(1.0 / A.diagonal())
+    iterates = []
+    spl.bicgstab(A, a.b, x0=np.zeros(s.n), rtol=1e-15, atol=0.0, maxiter=o.n_iterations + 3, M=M,
+                 callback=lambda xk: iterates.append(xk.copy()))
+    res = np.array([np.abs(a.b - A @ xk).sum() / o.norm_factor for xk in iterates])
+    full = o.history[2::2]                           # calls 2, 4, ...: after iterations 1, 2, ...
+    m = min(len(full), len(res))
+    big = res[:m] > 1e-7
+    assert m >= 3 and np.allclose(full[:m][big], res[:m][big], rtol=1e-5)
+
+
+@pytest.mark.parametrize("m", [10, 20])
+def test_gmres_cycle_matches_scipy_gmres(oracle, m):
+    """One restart cycle of GMRES(m) without preconditioner minimises the residual over the same Krylov
+    space whoever builds it: the oracle's iterate after m inner steps equals scipy.sparse.linalg.gmres's."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    s = cases.momentum_3d(9)[0]
+    a, rp, A = _csr_of(oracle, s)
+    o = oracle.solve([a], "GKOGMRES", "none", tolerance=1e-30, krylov_dim=m, max_iter=m)
+    x, _ = spl.gmres(A, a.b, x0=np.zeros(s.n), restart=m, maxiter=1, rtol=1e-30, atol=0.0)
+    assert np.linalg.norm(o.x[0] - x) <= 1e-12 * np.linalg.norm(x)
