@@ -74,3 +74,35 @@ def test_sass_carries_the_paths_the_design_claims():
     assert "ATOMG.E.ADD.STRONG.GPU" in sass      # acq_rel tickets of the reductions / grid barrier
     assert "LDG.E.128" in sass and "STG.E.128" in sass   # 128-bit vector updates
     assert "HMMA" not in sass and "UTCHMMA" not in sass  # HBM-bound FP64 path: no tensor-core reshaping
+
+
+def _function_sass(obj, name_part):
+    """SASS text of the kernels of one object file of the build whose mangled name contains `name_part`."""
+    path = os.path.join(BUILD, obj)
+    if not os.path.exists(path):
+        pytest.skip(f"{obj} not built in-tree")
+    text = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    return [chunk for chunk in text.split("Function : ")[1:] if name_part in chunk.split("\n", 1)[0]]
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_sass_of_the_sweep_and_merge_path_kernels(table):
+    """The dependency-driven triangular sweeps poll and publish with gpu-scope relaxed accesses and vote on
+    the warp's completion inside ONE loop (no lane ever parks outside it while another still polls); the
+    merge-path SpMV reads its slice with 128-bit loads and parks the products in shared memory."""
+    sweeps = _function_sass("trifactor.o", "k_trisolve_sf_short")
+    assert len(sweeps) == 6                                     # {lower unit, lower, upper} x {4, 8 operands}
+    for sass in sweeps:
+        assert "LDG.E.64.STRONG.GPU" in sass and "STG.E.64.STRONG.GPU" in sass
+        assert "VOTE.ALL" in sass
+        # the publishing store sits before the vote in program order (it is issued from inside the loop)
+        assert sass.index("STG.E.64.STRONG.GPU") < sass.index("VOTE.ALL")
+    merge = _function_sass("spmv_merge.o", "k_spmv_merge")
+    main = [s for s in merge if "fixup" not in s.split("\n", 1)[0] and "_dot" not in s.split("\n", 1)[0]]
+    assert len(main) == 2
+    for sass in main:
+        assert re.search(r"LDG\.E(\.EF)?\.128", sass) and "STS.128" in sass and "LDS" in sass
+    # co-residency budget of the sweeps: the 8-operand kernels keep 2 CTAs of 256 threads per SM
+    for parts in (("k_trisolve_sf_short<true, true, 8>",), ("k_trisolve_sf_short<false, false, 8>",)):
+        regs, _, _ = find(table, *parts)
+        assert regs <= 128
