@@ -484,3 +484,42 @@ def test_pgm_aggregates_match_an_independent_implementation_in_both_semantics(or
         seq, n_seq = _pgm_python(s.n, rp, a.cols, a.vals, False)
         assert np.array_equal(H.levels[0]["agg"], snap) and H.levels[0]["n_coarse"] == n_snap
         assert n_seq == n_snap and np.array_equal(seq, snap)
+
+
+def test_incomplete_factors_match_a_dense_right_looking_elimination(oracle):
+    """ILU(0) and IC(0) once more by an independent route: dense, right-looking (KIJ) elimination that drops
+    every update outside the pattern of A -- a different operation order from the oracle's row-wise IKJ /
+    dot-product forms -- agrees with the oracle's factors to rounding."""
+    import scipy.sparse as sp
+    from ogl_b200 import cases
+    s = cases.momentum_3d(5)[0]
+    a, rp, A = _csr_of(oracle, s)
+    pat = (A != 0).toarray() | np.eye(s.n, dtype=bool)
+    M = A.toarray().copy()
+    for k in range(s.n):
+        for i in range(k + 1, s.n):
+            if not pat[i, k]:
+                continue
+            M[i, k] /= M[k, k]
+            for j in range(k + 1, s.n):
+                if pat[i, j] and pat[k, j]:
+                    M[i, j] -= M[i, k] * M[k, j]
+    f = oracle.trifactor("ILU", s.n, rp, a.cols, a.vals)
+    F = sp.csr_matrix((f, a.cols, rp), shape=(s.n, s.n)).toarray()
+    assert np.abs(F - M * pat).max() <= 1e-12 * np.abs(M).max()
+    s = cases.pressure_3d(5, sign=-1.0)[0]
+    a, rp, A = _csr_of(oracle, s)
+    pat = (A != 0).toarray()
+    L = np.tril(A.toarray())
+    for k in range(s.n):
+        L[k, k] = np.sqrt(L[k, k])
+        for i in range(k + 1, s.n):
+            if pat[i, k]:
+                L[i, k] /= L[k, k]
+        for j in range(k + 1, s.n):
+            for i in range(j, s.n):
+                if pat[i, j] and pat[i, k] and pat[j, k]:
+                    L[i, j] -= L[i, k] * L[j, k]
+    f = oracle.trifactor("IC", s.n, rp, a.cols, a.vals)
+    F = np.tril(sp.csr_matrix((f, a.cols, rp), shape=(s.n, s.n)).toarray())
+    assert np.abs(F - L).max() <= 1e-12 * np.abs(L).max()
